@@ -1,0 +1,405 @@
+"""Host-side mirror of the reference's R interface over the C-ABI of libfable_b200.so.
+
+Function names, argument order and returned element names follow the reference:
+  R/FABLE_wrapper.R:12-68   FABLEPosteriorSampler(Y, gamma0, delta0sq, maxProp, MC)
+  R/FABLE_wrapper.R:80-128  FABLEPosteriorMean(Y, gamma0, delta0sq, maxProp)
+  R/RcppExports.R:20-75     CPPCriterionFunction, CPPBisectionRecursion, CPPRankEstimator,
+                            FABLEHyperParameters, CPPcov_correct_matrix, CPPFABLEPostMean,
+                            CPPFABLESampler, CPPsvd
+Every function marshals numpy float64 arrays as column-major `double*` into the C-ABI and raises
+`FableError` (R: `stop()`) on a non-zero status.  No arithmetic on matrix-sized data happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfable_b200.so")
+_lib = None
+_dp = C.POINTER(C.c_double)
+_i64 = C.c_int64
+
+
+class FableError(RuntimeError):
+    """Raised for every non-zero fable_status (the Rcpp layer raises Rcpp::stop with the same text)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"libfable_b200 status {code}: {msg}")
+        self.code = code
+
+
+def library_path():
+    return _SO
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise FableError(2, f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+    lib = C.CDLL(_SO)
+    lib.fable_last_error.restype = C.c_char_p
+    lib.fable_last_error.argtypes = [C.c_void_p]
+    lib.fable_ctx_launch_count.restype = C.c_int64
+    lib.fable_ctx_launch_count.argtypes = [C.c_void_p]
+    lib.fable_ctx_stream.restype = C.c_void_p
+    lib.fable_ctx_stream.argtypes = [C.c_void_p]
+    lib.fable_ctx_destroy.restype = None
+    lib.fable_ctx_destroy.argtypes = [C.c_void_p]
+    lib.fable_posterior_destroy.restype = None
+    lib.fable_posterior_destroy.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _F(a, name="matrix"):
+    """float64 column-major view/copy (R's memory order)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        return np.ascontiguousarray(a)
+    if a.ndim != 2:
+        raise FableError(1, f"{name} must be a matrix")
+    return np.asfortranarray(a)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class Context:
+    """fable_ctx: one device, one stream set.  `seed` keys the Philox stream (fable-philox-v1)."""
+
+    def __init__(self, device=0, seed=12345):
+        lib = _load()
+        h = C.c_void_p()
+        rc = lib.fable_ctx_create(C.c_int(device), C.c_uint64(seed), C.byref(h))
+        if rc != 0:
+            raise FableError(rc, lib.fable_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _load().fable_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise FableError(rc, _load().fable_last_error(self._h).decode())
+
+    def set_seed(self, seed):
+        self.check(_load().fable_ctx_set_seed(self._h, C.c_uint64(seed)))
+
+    @property
+    def launches(self):
+        return int(_load().fable_ctx_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return int(_load().fable_ctx_stream(self._h) or 0)
+
+    def synchronize(self):
+        self.check(_load().fable_ctx_synchronize(self._h))
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("FABLE_B200_DEVICE", os.environ.get("LOCAL_RANK", "0"))),
+                               int(os.environ.get("FABLE_B200_SEED", "12345")))
+    return _default_ctx
+
+
+def _ctx(ctx):
+    return ctx if ctx is not None else default_context()
+
+
+def _inputs(Y, U_Y, V_Y, svalsY):
+    Y = _F(Y, "Y"); U = _F(U_Y, "U_Y"); V = _F(V_Y, "V_Y"); d = _F(svalsY, "svalsY")
+    n, p = Y.shape
+    r = d.shape[0]
+    if U.shape != (n, r) and not (U.shape[0] == n and U.shape[1] >= r):
+        raise FableError(1, "U_Y must be n x length(svalsY)")
+    if V.shape != (p, r) and not (V.shape[0] == p and V.shape[1] >= r):
+        raise FableError(1, "V_Y must be p x length(svalsY)")
+    return Y, U, V, d, n, p, r
+
+
+# ------------------------------------------------------------------------------------------------
+# a1 / a2
+# ------------------------------------------------------------------------------------------------
+def svd(Y, ctx=None):
+    """Drop-in for base-R `svd(Y)` as the wrappers use it: list(d, u, v)."""
+    ctx = _ctx(ctx)
+    Y = _F(Y, "Y")
+    n, p = Y.shape
+    r = min(n, p)
+    U = np.empty((n, r), order="F"); d = np.empty(r); V = np.empty((p, r), order="F")
+    ctx.check(_load().fable_svd(ctx._h, _ptr(Y), _i64(n), _i64(p), _ptr(U), _ptr(d), _ptr(V)))
+    return {"d": d, "u": U, "v": V}
+
+
+def CPPsvd(X, flag=4, ctx=None):
+    """CPPsvd (updated-FABLE-functions.cpp:40-74): list(U, d, V); `flag` selected a LAPACK driver
+    there and has no effect here (one algorithm)."""
+    s = svd(X, ctx)
+    return {"U": s["u"], "d": s["d"], "V": s["v"]}
+
+
+def kmax_rule(svalsY, maxProp):
+    d = _F(svalsY)
+    out = C.c_int()
+    rc = _load().fable_kmax(_ptr(d), _i64(d.shape[0]), C.c_double(maxProp), C.byref(out))
+    if rc != 0:
+        raise FableError(rc, "kMax rule: no index reaches maxProp")
+    return out.value
+
+
+# ------------------------------------------------------------------------------------------------
+# a3 / a4 / a5
+# ------------------------------------------------------------------------------------------------
+def CPPCriterionFunction(kInd, Y, U_Y, V_Y, svalsY, ctx=None):
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)
+    out = C.c_double()
+    ctx.check(_load().fable_criterion(ctx._h, C.c_int(int(kInd)), _ptr(Y), _i64(n), _i64(p), _ptr(U), _ptr(V),
+                                      _ptr(d), _i64(r), C.byref(out)))
+    return out.value
+
+
+def CPPBisectionRecursion(lower, upper, Y, U_Y, V_Y, svalsY, ctx=None):
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)
+    lo = C.c_int(); hi = C.c_int()
+    ctx.check(_load().fable_bisection(ctx._h, C.c_int(int(lower)), C.c_int(int(upper)), _ptr(Y), _i64(n), _i64(p),
+                                      _ptr(U), _ptr(V), _ptr(d), _i64(r), C.byref(lo), C.byref(hi)))
+    return np.array([float(lo.value), float(hi.value)])   # arma::vec of doubles (cpp:263-267)
+
+
+def CPPRankEstimator(Y, U_Y, V_Y, svalsY, kMax, ctx=None):
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)
+    k = C.c_int()
+    ctx.check(_load().fable_rank_estimator(ctx._h, _ptr(Y), _i64(n), _i64(p), _ptr(U), _ptr(V), _ptr(d), _i64(r),
+                                           C.c_int(int(kMax)), C.byref(k)))
+    return k.value
+
+
+# ------------------------------------------------------------------------------------------------
+# a6 / a7
+# ------------------------------------------------------------------------------------------------
+def FABLEHyperParameters(Y, U_Y, V_Y, svalsY, kEst, ctx=None, want_G=True):
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)
+    k = int(kEst)
+    if not (1 <= k <= r):
+        raise FableError(1, "kEst must be in 1..length(svalsY)")
+    sig = np.empty(p); G0 = np.empty((p, k), order="F"); tau = C.c_double()
+    G = np.empty((p, p), order="F") if want_G else None
+    ctx.check(_load().fable_hyper_parameters(ctx._h, _ptr(Y), _i64(n), _i64(p), _ptr(U), _ptr(V), _ptr(d), _i64(r),
+                                             C.c_int(k), _ptr(sig), _ptr(G0), C.byref(tau), _ptr(G)))
+    out = {"SigmaSqEstimate": sig, "G": G, "EstimatedRank": k, "G0": G0, "tauSqEstimate": tau.value}
+    return out
+
+
+def CPPcov_correct_matrix(sigsq_hat, llprime_hat, ctx=None):
+    """Upper-triangle vector, column-major trimatu order (cpp:401-428)."""
+    ctx = _ctx(ctx)
+    sig = _F(sigsq_hat); G = _F(llprime_hat)
+    p = sig.shape[0]
+    if G.shape != (p, p):
+        raise FableError(1, "llprime_hat must be p x p")
+    out = np.empty(p * (p + 1) // 2)
+    ctx.check(_load().fable_cov_correct_matrix(ctx._h, _ptr(sig), _ptr(G), _i64(p), _ptr(out)))
+    return out
+
+
+def cov_correct_matrix(sigsq_hat, llprime_hat, ctx=None):
+    """Full p x p B: the pure-R twin the wrapper calls (R/FABLE_code.R:189-206)."""
+    ctx = _ctx(ctx)
+    sig = _F(sigsq_hat); G = _F(llprime_hat)
+    p = sig.shape[0]
+    if G.shape != (p, p):
+        raise FableError(1, "llprime_hat must be p x p")
+    out = np.empty((p, p), order="F")
+    ctx.check(_load().fable_cov_correct_full(ctx._h, _ptr(sig), _ptr(G), _i64(p), _ptr(out)))
+    return out
+
+
+def var_inflation(sigsq_hat, G0, variant="wrapper", ctx=None):
+    """The scalar the wrappers derive from the correction matrix, as a fused reduction over
+    G = G0 G0' that never stores B.  variant: 'wrapper' (R/FABLE_wrapper.R:41-44) or 'script'
+    (extras/replicationCodes/runtimeScript.R:75-78)."""
+    ctx = _ctx(ctx)
+    sig = _F(sigsq_hat); G0 = _F(G0)
+    p, k = G0.shape
+    out = C.c_double()
+    ctx.check(_load().fable_var_inflation(ctx._h, _ptr(sig), _ptr(G0), _i64(p), C.c_int(k),
+                                          C.c_int({"wrapper": 0, "script": 1}[variant]), C.byref(out)))
+    return out.value
+
+
+# ------------------------------------------------------------------------------------------------
+# a8
+# ------------------------------------------------------------------------------------------------
+def CPPFABLEPostMean(Y, gamma0, delta0sq, U_Y, V_Y, svalsY, kMax, ctx=None, want_cov=True, internals=False):
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)
+    kMax = int(kMax)
+    if not (1 <= kMax <= r):
+        raise FableError(1, "kMax must be in 1..length(svalsY)")
+    Cov = np.empty((p, p), order="F") if want_cov else None
+    k = C.c_int()
+    G0s = np.empty((p, kMax), order="F") if internals else None   # only the first kEst columns are written
+    Sh = np.empty(p) if internals else None
+    ctx.check(_load().fable_post_mean(ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq),
+                                      _ptr(U), _ptr(V), _ptr(d), _i64(r), C.c_int(kMax), _ptr(Cov), C.byref(k),
+                                      _ptr(G0s), _ptr(Sh)))
+    out = {"CovPostMean": Cov, "kEst": k.value}
+    if internals:
+        out["G0"] = np.asfortranarray(G0s.reshape(-1, order="F")[: p * k.value].reshape((p, k.value), order="F"))
+        out["SigmaHat"] = Sh
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a9
+# ------------------------------------------------------------------------------------------------
+def CPPFABLESampler(Y, gamma0, delta0sq, MC, U_Y, V_Y, svalsY, kEst, varInflation, ctx=None, gam=None, z=None,
+                    m0=0, want_G=True, want_samples=True, psi_moments=False):
+    """Element names as cpp:620-627.  `gam`/`z`: injected draws (gam[m, j]; z[m, l, j]); default is
+    the native Philox stream.  `psi_moments=True` adds PsiSum / PsiSumSq (entry-wise sums over the
+    draws of Psi_m = Lambda_m Lambda_m' + diag(sigma2_m))."""
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)
+    k = int(kEst); MC = int(MC)
+    if not (1 <= k <= r):
+        raise FableError(1, "kEst must be in 1..length(svalsY)")
+    if MC < 1:
+        raise FableError(1, "MC must be >= 1")
+    g = zz = None
+    if gam is not None or z is not None:
+        if gam is None or z is None:
+            raise FableError(1, "injected draws need both gam and z")
+        g = np.ascontiguousarray(gam, dtype=np.float64).reshape(MC, p)
+        zz = np.ascontiguousarray(z, dtype=np.float64).reshape(MC, k, p)
+    L = np.empty((MC, k * p), order="F") if want_samples else None
+    S = np.empty((MC, p), order="F") if want_samples else None
+    pm = np.empty(p); pi = np.empty(p); tau = C.c_double()
+    G = np.empty((p, p), order="F") if want_G else None
+    s1 = np.empty((p, p), order="F") if psi_moments else None
+    s2 = np.empty((p, p), order="F") if psi_moments else None
+    ctx.check(_load().fable_sampler(ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq),
+                                    _i64(MC), _ptr(U), _ptr(V), _ptr(d), _i64(r), C.c_int(k),
+                                    C.c_double(varInflation), _ptr(g), _ptr(zz), _i64(m0), _ptr(L), _ptr(S),
+                                    _ptr(pm), _ptr(pi), C.byref(tau), _ptr(G), _ptr(s1), _ptr(s2)))
+    out = {"LambdaSamples": L, "SigmaSqSamples": S, "SigmaSqEstimatePostMean": pm, "SigmaSqEstimatePlugIn": pi,
+           "EstimatedRank": k, "VarianceInflation": float(varInflation), "tauSqEstimate": tau.value, "G": G}
+    if psi_moments:
+        out["PsiSum"] = s1; out["PsiSumSq"] = s2
+    return out
+
+
+class Posterior:
+    """fable_posterior: the row posterior resident in HBM + batched draw / covariance kernels."""
+
+    def __init__(self, Y, gamma0, delta0sq, U_Y, V_Y, svalsY, kEst, varInflation, ctx=None):
+        self.ctx = _ctx(ctx)
+        Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)
+        self.n, self.p, self.k = n, p, int(kEst)
+        h = C.c_void_p()
+        self.ctx.check(_load().fable_posterior_create(self.ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0),
+                                                      C.c_double(delta0sq), _ptr(U), _ptr(V), _ptr(d), _i64(r),
+                                                      C.c_int(self.k), C.c_double(varInflation), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _load().fable_posterior_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get(self):
+        G0 = np.empty((self.p, self.k), order="F"); gnd = np.empty(self.p); sig = np.empty(self.p); sc = np.empty(4)
+        self.ctx.check(_load().fable_posterior_get(self._h, _ptr(G0), _ptr(gnd), _ptr(sig), _ptr(sc)))
+        return {"G0": G0, "gnd": gnd, "sig": sig, "tausq": sc[0], "a_n": sc[1], "gamma_n": sc[2], "w": sc[3]}
+
+    def draw_batch(self, m0, B, dev_psi=0, psi_slots=0, accumulate=True, dev_gam=0, dev_z=0):
+        """dev_* are raw device addresses (ints), e.g. torch tensors' data_ptr()."""
+        self.ctx.check(_load().fable_posterior_draw_batch(self._h, _i64(m0), C.c_int(B), C.c_void_p(dev_psi or None),
+                                                          C.c_int(psi_slots), C.c_int(1 if accumulate else 0),
+                                                          C.c_void_p(dev_gam or None), C.c_void_p(dev_z or None)))
+
+    def samples(self, m0, MC, gam=None, z=None, want_lambda=True, want_sigma=True):
+        L = np.empty((MC, self.k * self.p), order="F") if want_lambda else None
+        S = np.empty((MC, self.p), order="F") if want_sigma else None
+        g = None if gam is None else np.ascontiguousarray(gam, dtype=np.float64)
+        zz = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        self.ctx.check(_load().fable_posterior_samples(self._h, _i64(m0), _i64(MC), _i64(MC), _ptr(L), _ptr(S),
+                                                       _ptr(g), _ptr(zz)))
+        return L, S
+
+    def accum_dev(self):
+        a = C.c_void_p(); b = C.c_void_p()
+        self.ctx.check(_load().fable_posterior_accum_dev(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def accum_reset(self):
+        self.ctx.check(_load().fable_posterior_accum_reset(self._h))
+
+    def accum_mirror(self):
+        self.ctx.check(_load().fable_posterior_accum_mirror(self._h))
+
+    def accum_fetch(self):
+        s1 = np.empty((self.p, self.p), order="F"); s2 = np.empty((self.p, self.p), order="F")
+        self.ctx.check(_load().fable_posterior_accum_fetch(self._h, _ptr(s1), _ptr(s2)))
+        return s1, s2
+
+
+# ------------------------------------------------------------------------------------------------
+# a11: the two public wrappers (R/FABLE_wrapper.R)
+# ------------------------------------------------------------------------------------------------
+def FABLEPosteriorMean(Y, gamma0=1.0, delta0sq=1.0, maxProp=0.5, ctx=None):
+    t0 = time.perf_counter()                                             # wrapper:85
+    Y = _F(Y, "Y")                                                       # as.matrix, wrapper:87
+    svdY = svd(Y, ctx)                                                   # wrapper:90
+    kMax = kmax_rule(svdY["d"], maxProp)                                 # wrapper:94
+    mod = CPPFABLEPostMean(Y, gamma0, delta0sq, svdY["u"], svdY["v"], svdY["d"], kMax, ctx)   # wrapper:102
+    return {"FABLEPostMean": mod["CovPostMean"], "svdY": svdY, "estRank": mod["kEst"],
+            "runTime": time.perf_counter() - t0}                         # wrapper:121-124
+
+
+def FABLEPosteriorSampler(Y, gamma0=1.0, delta0sq=1.0, maxProp=0.95, MC=1000, ctx=None, gam=None, z=None):
+    t0 = time.perf_counter()                                             # wrapper:18
+    Y = _F(Y, "Y")
+    svdY = svd(Y, ctx)                                                   # wrapper:23
+    U, V, d = svdY["u"], svdY["v"], svdY["d"]
+    kMax = kmax_rule(d, maxProp)                                         # wrapper:27
+    kEst = CPPRankEstimator(Y, U, V, d, kMax, ctx)                       # wrapper:29
+    hyp = FABLEHyperParameters(Y, U, V, d, kEst, ctx)                    # wrapper:35
+    # wrapper:41-44 -- cov_correct_matrix + (sum(B)/(p(p+1)/2))^2, fused: B is never stored
+    varInfl = var_inflation(hyp["SigmaSqEstimate"], hyp["G0"], "wrapper", ctx)
+    zz = z(MC, kEst, Y.shape[1]) if callable(z) else z
+    smp = CPPFABLESampler(Y, gamma0, delta0sq, MC, U, V, d, kEst, varInfl, ctx, gam=gam, z=zz)   # wrapper:46
+    return {"CCFABLESamples": smp, "FABLEHyperParameters": hyp, "svdY": svdY, "estRank": kEst,
+            "varInflation": varInfl, "runTime": time.perf_counter() - t0}   # wrapper:59-64

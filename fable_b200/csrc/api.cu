@@ -1,0 +1,641 @@
+// C-ABI of libfable_b200.so (include/fable_b200.h): the host layer that sits where the reference's
+// Rcpp exports sit (src/RcppExports.cpp:96-172) and drives the sm_100a kernels.
+// Control flow that the reference runs on the host (bisection, final window, argmin:
+// src/updated-FABLE-functions.cpp:215-341) is replayed here verbatim on criterion values computed
+// on the device.  No CPU arithmetic fallback exists for any matrix-sized quantity.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int KSMALL = 32;   // ranks up to this use the streaming row kernel; above: DMMA residual GEMM
+
+thread_local std::string g_create_error;
+
+struct Inputs {
+  DevBuf Y, U, V, d;
+  int64_t n = 0, p = 0, r = 0;
+  int kcols = 0;   // number of leading singular triplets resident
+};
+
+int check_dims(fable_ctx* ctx, const void* Y, int64_t n, int64_t p, const void* U, const void* V, const void* d,
+               int64_t r) {
+  FB_REQUIRE(ctx, Y && U && V && d, "NULL input matrix");
+  FB_REQUIRE(ctx, n >= 1 && p >= 1, "Y must have at least one row and one column");
+  FB_REQUIRE(ctx, r >= 1 && r <= (n < p ? n : p), "length(svalsY) must be in 1..min(n,p)");
+  return FABLE_OK;
+}
+
+int upload(fable_ctx* ctx, DevBuf& b, const double* h, size_t count) {
+  FB_CUDA(ctx, b.alloc(count * sizeof(double)));
+  FB_CUDA(ctx, cudaMemcpyAsync(b.ptr, h, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return FABLE_OK;
+}
+
+// U is n x r and V is p x r column-major, so their first kcols columns are one contiguous block.
+int upload_inputs(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* U, const double* V,
+                  const double* d, int64_t r, int kcols, Inputs& in) {
+  FB_TRY(check_dims(ctx, Y, n, p, U, V, d, r));
+  FB_REQUIRE(ctx, kcols >= 1 && kcols <= r, "rank must be in 1..length(svalsY)");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  in.n = n; in.p = p; in.r = r; in.kcols = kcols;
+  FB_TRY(upload(ctx, in.Y, Y, static_cast<size_t>(n) * p));
+  FB_TRY(upload(ctx, in.U, U, static_cast<size_t>(n) * kcols));
+  FB_TRY(upload(ctx, in.V, V, static_cast<size_t>(p) * kcols));
+  FB_TRY(upload(ctx, in.d, d, static_cast<size_t>(kcols)));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+// scratch reused across criterion calls
+struct RowScratch {
+  DevBuf c, q, s, resid;
+  int kcap = 0;
+  int ensure(fable_ctx* ctx, int64_t p, int k) {
+    if (k > kcap) { FB_CUDA(ctx, c.alloc(static_cast<size_t>(p) * k * sizeof(double))); kcap = k; }
+    if (!q.ptr) {
+      FB_CUDA(ctx, q.alloc(p * sizeof(double)));
+      FB_CUDA(ctx, s.alloc(p * sizeof(double)));
+      FB_CUDA(ctx, resid.alloc(p * sizeof(double)));
+    }
+    return FABLE_OK;
+  }
+};
+
+// c = V_k .* d_k, q, raw residual sums (and s when want_s) for rank k.
+int row_pass(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, bool want_s) {
+  FB_TRY(sc.ensure(ctx, in.p, k));
+  FB_TRY(fb_cq(ctx, in.V.d(), in.p, in.d.d(), in.p, k, sc.c.d(), in.p, sc.q.d()));
+  if (k <= KSMALL) {
+    FB_TRY(fb_rowstats(ctx, in.Y.d(), in.n, in.p, in.n, in.U.d(), in.n, sc.c.d(), in.p, k,
+                       want_s ? sc.s.d() : nullptr, sc.resid.d()));
+  } else {
+    FB_TRY(fb_gemm_resid(ctx, in.n, in.p, k, in.Y.d(), in.n, in.U.d(), in.n, sc.c.d(), in.p, sc.resid.d()));
+    if (want_s) FB_TRY(fb_colsumsq(ctx, in.Y.d(), in.n, in.p, in.n, sc.s.d()));
+  }
+  return FABLE_OK;
+}
+
+// CPPCriterionFunction (cpp:127-213) on resident inputs.
+int criterion_dev(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, double* out) {
+  FB_REQUIRE(ctx, k >= 1 && k <= in.kcols, "criterion: kInd out of range");   // arma: cols(0,k-1) throws
+  FB_TRY(row_pass(ctx, in, k, sc, false));
+  double sumlog = 0.0;
+  const double dn = static_cast<double>(in.n), dp = static_cast<double>(in.p);
+  FB_TRY(fb_sum_log_scaled(ctx, sc.resid.d(), in.p, 1.0 / dn, &sumlog));
+  if (!std::isfinite(sumlog)) return ctx->fail(FABLE_ERR_NUMERIC, "criterion: non-positive residual variance");
+  const double LL = (-dn * dp / 2.0) - (dn * sumlog / 2.0);                     // cpp:199
+  const double maxint = dn > dp ? dn : dp, minint = dn < dp ? dn : dp;          // cpp:206-207
+  *out = (-2.0 * LL) + (static_cast<double>(k) * maxint * std::log(minint));    // cpp:209
+  return FABLE_OK;
+}
+
+struct CritCache {
+  fable_ctx* ctx; const Inputs& in; RowScratch sc; std::map<int, double> memo;
+  CritCache(fable_ctx* c, const Inputs& i) : ctx(c), in(i) {}
+  int eval(int k, double* v) {
+    auto it = memo.find(k);
+    if (it != memo.end()) { *v = it->second; return FABLE_OK; }   // same inputs -> same value (cpp:233 re-evaluates)
+    FB_TRY(criterion_dev(ctx, in, k, sc, v));
+    memo[k] = *v;
+    return FABLE_OK;
+  }
+};
+
+// CPPBisectionRecursion (cpp:215-271), iterative form of the tail recursion.
+int bisection(CritCache& cc, int lower, int upper, int* lo, int* hi) {
+  while (upper - lower > 5) {                                    // cpp:223
+    const int mid = (lower + upper) / 2;                         // cpp:225
+    double cl, cm;
+    FB_TRY(cc.eval(lower, &cl));                                 // cpp:233
+    FB_TRY(cc.eval(mid, &cm));                                   // cpp:235
+    if (cl < cm) { upper = mid; continue; }                      // cpp:237-239
+    const int tq = (mid + upper) / 2;                            // cpp:243
+    double ct;
+    FB_TRY(cc.eval(tq, &ct));                                    // cpp:247
+    if (cm <= ct) upper = mid; else lower = mid;                 // cpp:249-255
+  }
+  *lo = lower; *hi = upper;
+  return FABLE_OK;
+}
+
+// CPPRankEstimator (cpp:281-341)
+int rank_dev(fable_ctx* ctx, const Inputs& in, int kMax, int* kEst) {
+  FB_REQUIRE(ctx, kMax >= 1 && kMax <= in.kcols, "kMax must be in 1..length(svalsY)");
+  CritCache cc(ctx, in);
+  int lo, hi;
+  FB_TRY(bisection(cc, 1, kMax, &lo, &hi));                      // cpp:314
+  int best = lo; double bestv = 0.0;
+  for (int k = lo; k <= hi; ++k) {                               // cpp:321-330
+    double v;
+    FB_TRY(cc.eval(k, &v));
+    if (k == lo || v < bestv) { best = k; bestv = v; }           // index_min = first minimum (cpp:337)
+  }
+  *kEst = best;
+  return FABLE_OK;
+}
+
+struct RowPosterior {
+  DevBuf G0, gnd, sig, sigmahat;
+  double tausq = 0, w = 0, gamma_n = 0;
+};
+
+// A.2 of SURVEY.md: cpp:371-391 (shrunk=0) or cpp:470-499 / 564-592 (shrunk=1)
+int row_posterior(fable_ctx* ctx, const Inputs& in, int k, double gamma0, double delta0sq, int shrunk,
+                  RowPosterior& rp) {
+  RowScratch sc;
+  FB_TRY(row_pass(ctx, in, k, sc, true));
+  FB_TRY(fb_tausq(ctx, sc.q.d(), sc.resid.d(), in.n, in.p, k, &rp.tausq));
+  if (!(rp.tausq > 0.0) || !std::isfinite(rp.tausq))
+    return ctx->fail(FABLE_ERR_NUMERIC, "row posterior: tauSq estimate is not positive and finite");
+  rp.w = static_cast<double>(in.n) + 1.0 / rp.tausq;
+  rp.gamma_n = gamma0 + static_cast<double>(in.n);
+  FB_CUDA(ctx, rp.G0.alloc(static_cast<size_t>(in.p) * k * sizeof(double)));
+  FB_CUDA(ctx, rp.gnd.alloc(in.p * sizeof(double)));
+  FB_CUDA(ctx, rp.sig.alloc(in.p * sizeof(double)));
+  FB_CUDA(ctx, rp.sigmahat.alloc(in.p * sizeof(double)));
+  FB_TRY(fb_finish_posterior(ctx, sc.c.d(), in.p, sc.s.d(), sc.q.d(), sc.resid.d(), in.n, in.p, k, gamma0,
+                             delta0sq, rp.tausq, shrunk, rp.G0.d(), in.p, rp.gnd.d(), rp.sig.d(),
+                             rp.sigmahat.d()));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // scratch is released on return
+  return FABLE_OK;
+}
+
+int download(fable_ctx* ctx, double* h, const double* dptr, size_t count) {
+  if (!h) return FABLE_OK;
+  FB_CUDA(ctx, cudaMemcpyAsync(h, dptr, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return FABLE_OK;
+}
+
+// dense p x p  A A' + diag(s) into a host buffer, via a device p x p
+int rankk_cov_to_host(fable_ctx* ctx, const double* dA, int64_t lda, const double* ds, int64_t p, int k,
+                      double* hOut) {
+  DevBuf out;
+  FB_CUDA(ctx, out.alloc(static_cast<size_t>(p) * p * sizeof(double)));
+  FB_TRY(fable_dev_rankk_cov(ctx, dA, lda, ds, p, k, out.d()));
+  FB_TRY(download(ctx, hOut, out.d(), static_cast<size_t>(p) * p));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+}  // namespace
+
+struct fable_posterior {
+  fable_ctx* ctx = nullptr;
+  int64_t n = 0, p = 0, pp = 0;
+  int k = 0, KP = 0;
+  double gamma0 = 0, delta0sq = 0, varInflation = 0, a_n = 0;
+  RowPosterior rp;
+  DevBuf Lw, s2w;
+  int Bcap = 0;
+  DevBuf acc_sum, acc_sq;
+  bool mirrored = false;
+};
+
+extern "C" {
+
+int fable_abi_version(void) { return FABLE_B200_ABI_VERSION; }
+
+int fable_ctx_create(int device, uint64_t seed, fable_ctx** out) {
+  if (!out) { g_create_error = "fable_ctx_create: NULL out pointer"; return FABLE_ERR_INVALID; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    (void)cudaGetLastError();
+    g_create_error = std::string("no CUDA device available (libfable_b200 has no CPU fallback): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return FABLE_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) { g_create_error = "fable_ctx_create: device ordinal out of range"; return FABLE_ERR_INVALID; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return FABLE_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = std::string("device '") + prop.name + "' is compute capability " + std::to_string(prop.major) +
+                     "." + std::to_string(prop.minor) + "; libfable_b200 carries sm_100a code only";
+    return FABLE_ERR_CUDA;
+  }
+  fable_ctx* ctx = new (std::nothrow) fable_ctx();
+  if (!ctx) { g_create_error = "out of host memory"; return FABLE_ERR_NOMEM; }
+  ctx->device = device; ctx->seed = seed; ctx->sms = prop.multiProcessorCount;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete ctx;
+    return FABLE_ERR_CUDA;
+  }
+  *out = ctx;
+  return FABLE_OK;
+}
+
+void fable_ctx_destroy(fable_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* fable_last_error(const fable_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int fable_ctx_set_seed(fable_ctx* ctx, uint64_t seed) { if (!ctx) return FABLE_ERR_INVALID; ctx->seed = seed; return FABLE_OK; }
+int fable_ctx_set_interrupt(fable_ctx* ctx, int (*poll)(void*), void* user) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  ctx->poll = poll; ctx->poll_user = user;
+  return FABLE_OK;
+}
+int64_t fable_ctx_launch_count(const fable_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int fable_ctx_synchronize(fable_ctx* ctx) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+void* fable_ctx_stream(fable_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+
+// ---- a1 / a2 -------------------------------------------------------------------------------------
+int fable_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, double* d, double* V) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, Y && U && d && V, "svd: NULL pointer");
+  FB_REQUIRE(ctx, n >= 1 && p >= 1, "svd: Y must have at least one row and one column");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t r = n < p ? n : p;
+  DevBuf dY, dU, dd, dV;
+  FB_TRY(upload(ctx, dY, Y, static_cast<size_t>(n) * p));
+  FB_CUDA(ctx, dU.alloc(static_cast<size_t>(n) * r * sizeof(double)));
+  FB_CUDA(ctx, dV.alloc(static_cast<size_t>(p) * r * sizeof(double)));
+  FB_CUDA(ctx, dd.alloc(static_cast<size_t>(r) * sizeof(double)));
+  FB_TRY(fb_svd(ctx, dY.d(), n, p, dU.d(), dd.d(), dV.d()));
+  FB_TRY(download(ctx, U, dU.d(), static_cast<size_t>(n) * r));
+  FB_TRY(download(ctx, d, dd.d(), static_cast<size_t>(r)));
+  FB_TRY(download(ctx, V, dV.d(), static_cast<size_t>(p) * r));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+int fable_kmax(const double* d, int64_t r, double maxProp, int* kMax) {
+  if (!d || !kMax || r < 1) return FABLE_ERR_INVALID;
+  double total = 0.0;
+  for (int64_t i = 0; i < r; ++i) total += d[i];             // sum(svalsY)
+  double run = 0.0;
+  for (int64_t i = 0; i < r; ++i) {                          // cumsum(svalsY)/sum >= maxProp
+    run += d[i];
+    if (run / total >= maxProp) { *kMax = static_cast<int>(i + 1); return FABLE_OK; }
+  }
+  return FABLE_ERR_INVALID;                                  // R: min(integer(0)) = Inf + warning
+}
+
+// ---- a3 / a4 / a5 --------------------------------------------------------------------------------
+int fable_criterion(fable_ctx* ctx, int kInd, const double* Y, int64_t n, int64_t p, const double* U,
+                    const double* V, const double* d, int64_t r, double* out) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, out, "criterion: NULL output");
+  FB_REQUIRE(ctx, kInd >= 1 && kInd <= r, "criterion: kInd must be in 1..length(svalsY)");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kInd, in));
+  RowScratch sc;
+  return criterion_dev(ctx, in, kInd, sc, out);
+}
+
+int fable_bisection(fable_ctx* ctx, int lower, int upper, const double* Y, int64_t n, int64_t p,
+                    const double* U, const double* V, const double* d, int64_t r, int* lo, int* hi) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, lo && hi, "bisection: NULL output");
+  FB_REQUIRE(ctx, lower >= 1 && upper >= lower && upper <= r, "bisection: need 1 <= lower <= upper <= length(svalsY)");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, upper, in));
+  CritCache cc(ctx, in);
+  return bisection(cc, lower, upper, lo, hi);
+}
+
+int fable_rank_estimator(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* U,
+                         const double* V, const double* d, int64_t r, int kMax, int* kEst) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, kEst, "rank estimator: NULL output");
+  FB_REQUIRE(ctx, kMax >= 1 && kMax <= r, "kMax must be in 1..length(svalsY)");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kMax, in));
+  return rank_dev(ctx, in, kMax, kEst);
+}
+
+// ---- a6 ------------------------------------------------------------------------------------------
+int fable_hyper_parameters(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* U,
+                           const double* V, const double* d, int64_t r, int kEst, double* sig, double* G0,
+                           double* tausq, double* G) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, kEst >= 1 && kEst <= r, "kEst must be in 1..length(svalsY)");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kEst, in));
+  RowPosterior rp;
+  FB_TRY(row_posterior(ctx, in, kEst, 1.0, 1.0, /*shrunk=*/0, rp));
+  FB_TRY(download(ctx, sig, rp.sig.d(), p));
+  FB_TRY(download(ctx, G0, rp.G0.d(), static_cast<size_t>(p) * kEst));
+  if (tausq) *tausq = rp.tausq;
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (G) FB_TRY(rankk_cov_to_host(ctx, rp.G0.d(), p, nullptr, p, kEst, G));   // cpp:391
+  return FABLE_OK;
+}
+
+// ---- a7 ------------------------------------------------------------------------------------------
+static int cov_correct_host(fable_ctx* ctx, const double* sig, const double* G, int64_t p, double* out, int upper) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, sig && G && out && p >= 1, "cov_correct: bad arguments");
+  FB_REQUIRE(ctx, p <= 65535, "cov_correct (dense form): p too large; use fable_var_inflation");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf ds, dG, dO;
+  FB_TRY(upload(ctx, ds, sig, p));
+  FB_TRY(upload(ctx, dG, G, static_cast<size_t>(p) * p));
+  const size_t outn = upper ? static_cast<size_t>(p) * (p + 1) / 2 : static_cast<size_t>(p) * p;
+  FB_CUDA(ctx, dO.alloc(outn * sizeof(double)));
+  FB_TRY(fb_cov_correct_dense(ctx, ds.d(), dG.d(), p, dO.d(), upper));
+  FB_TRY(download(ctx, out, dO.d(), outn));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+int fable_cov_correct_matrix(fable_ctx* ctx, const double* sig, const double* G, int64_t p, double* Bupper) {
+  return cov_correct_host(ctx, sig, G, p, Bupper, 1);
+}
+int fable_cov_correct_full(fable_ctx* ctx, const double* sig, const double* G, int64_t p, double* B) {
+  return cov_correct_host(ctx, sig, G, p, B, 0);
+}
+
+static int var_inflation_from_sums(double su, double sd, int64_t p, int variant, double* out) {
+  const double tri = static_cast<double>(p) * (static_cast<double>(p) + 1.0) / 2.0;
+  const double total = variant == 0 ? (2.0 * su - sd) : su;   // full-matrix sum (wrapper:44) vs upper triangle (script)
+  const double m = total / tri;
+  *out = m * m;
+  return FABLE_OK;
+}
+
+int fable_var_inflation(fable_ctx* ctx, const double* sig, const double* G0, int64_t p, int k, int variant,
+                        double* out) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, sig && G0 && out && p >= 1 && k >= 1, "var_inflation: bad arguments");
+  FB_REQUIRE(ctx, variant == 0 || variant == 1, "var_inflation: variant must be 0 (wrapper) or 1 (script)");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf ds, dG0;
+  FB_TRY(upload(ctx, ds, sig, p));
+  FB_TRY(upload(ctx, dG0, G0, static_cast<size_t>(p) * k));
+  double su, sd;
+  FB_TRY(fb_var_inflation(ctx, ds.d(), dG0.d(), p, p, k, &su, &sd));
+  return var_inflation_from_sums(su, sd, p, variant, out);
+}
+
+// ---- a8 ------------------------------------------------------------------------------------------
+int fable_post_mean(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
+                    const double* U, const double* V, const double* d, int64_t r, int kMax, double* Cov,
+                    int* kEst, double* G0s, double* SigmaHat) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, kEst, "post_mean: NULL kEst");
+  FB_REQUIRE(ctx, kMax >= 1 && kMax <= r, "kMax must be in 1..length(svalsY)");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kMax, in));
+  int k = 1;
+  FB_TRY(rank_dev(ctx, in, kMax, &k));                                           // cpp:457
+  RowPosterior rp;
+  FB_TRY(row_posterior(ctx, in, k, gamma0, delta0sq, /*shrunk=*/1, rp));
+  *kEst = k;
+  FB_TRY(download(ctx, G0s, rp.G0.d(), static_cast<size_t>(p) * k));
+  FB_TRY(download(ctx, SigmaHat, rp.sigmahat.d(), p));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (Cov) FB_TRY(rankk_cov_to_host(ctx, rp.G0.d(), p, rp.sigmahat.d(), p, k, Cov));   // cpp:491, 509-512
+  return FABLE_OK;
+}
+
+// ---- posterior object ----------------------------------------------------------------------------
+int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
+                           double delta0sq, const double* U, const double* V, const double* d, int64_t r,
+                           int kEst, double varInflation, fable_posterior** out) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, out, "posterior_create: NULL out");
+  *out = nullptr;
+  FB_REQUIRE(ctx, kEst >= 1 && kEst <= r, "kEst must be in 1..length(svalsY)");
+  FB_REQUIRE(ctx, varInflation >= 0.0 && std::isfinite(varInflation), "varInflation must be finite and >= 0");
+  FB_REQUIRE(ctx, gamma0 + static_cast<double>(n) > 2.0, "gamma0 + n must exceed 2");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kEst, in));
+  fable_posterior* post = new (std::nothrow) fable_posterior();
+  if (!post) return ctx->fail(FABLE_ERR_NOMEM, "out of host memory");
+  post->ctx = ctx; post->n = n; post->p = p; post->pp = round_up(p, 64); post->k = kEst; post->KP = kEst;
+  post->gamma0 = gamma0; post->delta0sq = delta0sq; post->varInflation = varInflation;
+  int rc = row_posterior(ctx, in, kEst, gamma0, delta0sq, /*shrunk=*/1, post->rp);
+  if (rc != FABLE_OK) { delete post; return rc; }
+  post->a_n = std::sqrt(varInflation) / std::sqrt(post->rp.w);                 // cpp:597
+  *out = post;
+  return FABLE_OK;
+}
+
+void fable_posterior_destroy(fable_posterior* post) {
+  if (!post) return;
+  cudaSetDevice(post->ctx->device);
+  delete post;
+}
+
+int fable_posterior_get(fable_posterior* post, double* G0s, double* gnd, double* sig, double* scalars) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_TRY(download(ctx, G0s, post->rp.G0.d(), static_cast<size_t>(post->p) * post->k));
+  FB_TRY(download(ctx, gnd, post->rp.gnd.d(), post->p));
+  FB_TRY(download(ctx, sig, post->rp.sig.d(), post->p));
+  if (scalars) { scalars[0] = post->rp.tausq; scalars[1] = post->a_n; scalars[2] = post->rp.gamma_n; scalars[3] = post->rp.w; }
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+static SampleArgs sample_args(const fable_posterior* post, const double* dgam, const double* dz, int64_t m_inj0) {
+  SampleArgs a;
+  a.G0 = post->rp.G0.d(); a.ldg = post->p; a.gnd = post->rp.gnd.d(); a.a_n = post->a_n;
+  a.shape = 0.5 * post->rp.gamma_n;                                            // cpp:604
+  a.p = post->p; a.k = post->k; a.seed = post->ctx->seed; a.gam = dgam; a.z = dz; a.m_inj0 = m_inj0;
+  return a;
+}
+
+static int ensure_accum(fable_posterior* post) {
+  fable_ctx* ctx = post->ctx;
+  if (post->acc_sum.ptr) return FABLE_OK;
+  const size_t bytes = static_cast<size_t>(post->p) * post->p * sizeof(double);
+  FB_CUDA(ctx, post->acc_sum.alloc(bytes));
+  FB_CUDA(ctx, post->acc_sq.alloc(bytes));
+  FB_CUDA(ctx, cudaMemsetAsync(post->acc_sum.ptr, 0, bytes, ctx->stream));
+  FB_CUDA(ctx, cudaMemsetAsync(post->acc_sq.ptr, 0, bytes, ctx->stream));
+  post->mirrored = false;
+  return FABLE_OK;
+}
+
+int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots,
+                               int accumulate, const double* dev_gam, const double* dev_z) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, B >= 1 && m0 >= 0, "draw_batch: need B >= 1 and m0 >= 0");
+  FB_REQUIRE(ctx, dev_psi || accumulate, "draw_batch: nothing to do");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (B > post->Bcap) {
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FB_CUDA(ctx, post->Lw.alloc(static_cast<size_t>(B) * post->KP * post->pp * sizeof(double)));
+    FB_CUDA(ctx, post->s2w.alloc(static_cast<size_t>(B) * post->pp * sizeof(double)));
+    post->Bcap = B;
+  }
+  if (accumulate) { FB_TRY(ensure_accum(post)); post->mirrored = false; }
+  FB_TRY(fb_sample_work(ctx, sample_args(post, dev_gam, dev_z, m0), m0, B, post->pp, post->KP, post->Lw.d(),
+                        post->s2w.d()));
+  PsiArgs a;
+  a.Lw = post->Lw.d(); a.s2w = post->s2w.d(); a.pp = post->pp; a.p = post->p; a.k = post->k; a.KP = post->KP;
+  a.B = B; a.psi = dev_psi; a.psi_slots = psi_slots; a.slot0 = 0;
+  a.acc_sum = accumulate ? post->acc_sum.d() : nullptr; a.acc_sq = accumulate ? post->acc_sq.d() : nullptr;
+  return fb_psi(ctx, a);
+}
+
+int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64_t ldm, double* LambdaSamples,
+                            double* SigmaSqSamples, const double* gam_inj, const double* z_inj) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, MC >= 1 && ldm >= MC && m0 >= 0, "samples: need MC >= 1, ldm >= MC, m0 >= 0");
+  FB_REQUIRE(ctx, (gam_inj == nullptr) == (z_inj == nullptr), "injected draws need both gam and z");
+  if (!LambdaSamples && !SigmaSqSamples) return FABLE_OK;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t p = post->p; const int k = post->k;
+  DevBuf dgam, dz;
+  if (gam_inj) {
+    FB_TRY(upload(ctx, dgam, gam_inj, static_cast<size_t>(MC) * p));
+    FB_TRY(upload(ctx, dz, z_inj, static_cast<size_t>(MC) * p * k));
+  }
+  const SampleArgs sa = sample_args(post, gam_inj ? dgam.d() : nullptr, gam_inj ? dz.d() : nullptr, m0);
+  // chunk over rows j so that the device staging stays below ~4 GiB; a row chunk is a contiguous
+  // block of columns of the MC x (k p) host matrix.
+  const int64_t budget = (int64_t(1) << 32) / 8;
+  int64_t nj_max = budget / (MC * (k + 1));
+  if (nj_max < 1) nj_max = 1;
+  if (nj_max > p) nj_max = p;
+  DevBuf dL, dS;
+  if (LambdaSamples) FB_CUDA(ctx, dL.alloc(static_cast<size_t>(MC) * nj_max * k * sizeof(double)));
+  if (SigmaSqSamples) FB_CUDA(ctx, dS.alloc(static_cast<size_t>(MC) * nj_max * sizeof(double)));
+  for (int64_t j0 = 0; j0 < p; j0 += nj_max) {
+    const int64_t nj = p - j0 < nj_max ? p - j0 : nj_max;
+    FB_TRY(fb_sample_ref(ctx, sa, m0, MC, j0, nj, MC, LambdaSamples ? dL.d() : nullptr,
+                         SigmaSqSamples ? dS.d() : nullptr));
+    if (LambdaSamples)
+      FB_CUDA(ctx, cudaMemcpy2DAsync(LambdaSamples + ldm * (j0 * k), ldm * sizeof(double), dL.d(), MC * sizeof(double),
+                                     MC * sizeof(double), nj * k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (SigmaSqSamples)
+      FB_CUDA(ctx, cudaMemcpy2DAsync(SigmaSqSamples + ldm * j0, ldm * sizeof(double), dS.d(), MC * sizeof(double),
+                                     MC * sizeof(double), nj, cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->poll && ctx->poll(ctx->poll_user)) return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");
+  }
+  return FABLE_OK;
+}
+
+int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** dev_sumsq) {
+  if (!post) return FABLE_ERR_INVALID;
+  FB_CUDA(post->ctx, cudaSetDevice(post->ctx->device));
+  FB_TRY(ensure_accum(post));
+  if (dev_sum) *dev_sum = post->acc_sum.d();
+  if (dev_sumsq) *dev_sumsq = post->acc_sq.d();
+  return FABLE_OK;
+}
+
+int fable_posterior_accum_reset(fable_posterior* post) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!post->acc_sum.ptr) return ensure_accum(post);
+  const size_t bytes = static_cast<size_t>(post->p) * post->p * sizeof(double);
+  FB_CUDA(ctx, cudaMemsetAsync(post->acc_sum.ptr, 0, bytes, ctx->stream));
+  FB_CUDA(ctx, cudaMemsetAsync(post->acc_sq.ptr, 0, bytes, ctx->stream));
+  post->mirrored = false;
+  return FABLE_OK;
+}
+
+int fable_posterior_accum_mirror(fable_posterior* post) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_TRY(ensure_accum(post));
+  FB_TRY(fb_mirror_upper(ctx, post->acc_sum.d(), post->p));
+  FB_TRY(fb_mirror_upper(ctx, post->acc_sq.d(), post->p));
+  post->mirrored = true;
+  return FABLE_OK;
+}
+
+int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sumsq) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  if (!post->mirrored) FB_TRY(fable_posterior_accum_mirror(post));
+  const size_t cnt = static_cast<size_t>(post->p) * post->p;
+  FB_TRY(download(ctx, sum, post->acc_sum.d(), cnt));
+  FB_TRY(download(ctx, sumsq, post->acc_sq.d(), cnt));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+// ---- a9 ------------------------------------------------------------------------------------------
+int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
+                  int64_t MC, const double* U, const double* V, const double* d, int64_t r, int kEst,
+                  double varInflation, const double* gam_inj, const double* z_inj, int64_t m0,
+                  double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
+                  double* tausq, double* G, double* psi_sum, double* psi_sumsq) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, MC >= 1, "MC must be >= 1");
+  FB_REQUIRE(ctx, (gam_inj == nullptr) == (z_inj == nullptr), "injected draws need both gam and z");
+  FB_REQUIRE(ctx, (psi_sum == nullptr) == (psi_sumsq == nullptr), "psi_sum and psi_sumsq go together");
+  fable_posterior* post = nullptr;
+  FB_TRY(fable_posterior_create(ctx, Y, n, p, gamma0, delta0sq, U, V, d, r, kEst, varInflation, &post));
+  struct Guard { fable_posterior* p; ~Guard() { fable_posterior_destroy(p); } } guard{post};
+  FB_TRY(download(ctx, SigmaPostMean, post->rp.sigmahat.d(), p));              // cpp:622
+  FB_TRY(download(ctx, SigmaPlugIn, post->rp.sig.d(), p));                     // cpp:623
+  if (tausq) *tausq = post->rp.tausq;                                          // cpp:626
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FB_TRY(fable_posterior_samples(post, m0, MC, MC, LambdaSamples, SigmaSqSamples, gam_inj, z_inj));
+  if (psi_sum) {
+    DevBuf dgam, dz;
+    if (gam_inj) {
+      FB_TRY(upload(ctx, dgam, gam_inj, static_cast<size_t>(MC) * p));
+      FB_TRY(upload(ctx, dz, z_inj, static_cast<size_t>(MC) * p * kEst));
+    }
+    FB_TRY(fable_posterior_accum_reset(post));
+    const int B = 32;
+    for (int64_t b0 = 0; b0 < MC; b0 += B) {
+      const int nb = static_cast<int>(MC - b0 < B ? MC - b0 : B);
+      FB_TRY(fable_posterior_draw_batch(post, m0 + b0, nb, nullptr, 0, 1,
+                                        gam_inj ? dgam.d() + b0 * p : nullptr,
+                                        gam_inj ? dz.d() + b0 * p * kEst : nullptr));
+      if (ctx->poll && ctx->poll(ctx->poll_user)) return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");
+    }
+    FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
+  }
+  if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), p, nullptr, p, kEst, G));   // cpp:627
+  return FABLE_OK;
+}
+
+// ---- device-pointer primitives --------------------------------------------------------------------
+int fable_dev_rankk_cov(fable_ctx* ctx, const double* dA, int64_t lda, const double* ds, int64_t p, int k,
+                        double* dOut) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, dA && dOut && p >= 1 && k >= 1 && lda >= p, "rankk_cov: bad arguments");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PsiArgs a;
+  a.Lw = dA; a.s2w = ds; a.pp = lda; a.p = p; a.k = k; a.KP = k; a.B = 1;
+  a.psi = dOut; a.psi_slots = 1; a.slot0 = 0; a.acc_sum = nullptr; a.acc_sq = nullptr;
+  return fb_psi(ctx, a);
+}
+
+int fable_dev_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K, double alpha,
+                   const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, dA && dB && dC, "gemm: NULL pointer");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return fb_gemm(ctx, a_kfast != 0, b_kfast != 0, M, N, K, alpha, dA, lda, dB, ldb, dC, ldc);
+}
+
+int fable_dev_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, dG && dW && dQ, "syevj: NULL pointer");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return fb_syevj(ctx, dG, m, dW, dQ, sweeps);
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// Shared host/device plumbing of libfable_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/fable_b200.h"
+
+struct fable_ctx {
+  int device = 0;
+  int sms = 148;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int (*poll)(void*) = nullptr;
+  void* poll_user = nullptr;
+
+  int fail(int code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+};
+
+#define FB_CUDA(ctx, expr)                                                                       \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      (void)cudaGetLastError();                                                                  \
+      return (ctx)->fail(e__ == cudaErrorMemoryAllocation ? FABLE_ERR_NOMEM : FABLE_ERR_CUDA,    \
+                         std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                             ":" + std::to_string(__LINE__) + ")");                              \
+    }                                                                                            \
+  } while (0)
+
+#define FB_TRY(expr)               \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != FABLE_OK) return rc__; \
+  } while (0)
+
+#define FB_REQUIRE(ctx, cond, msg)                                   \
+  do {                                                               \
+    if (!(cond)) return (ctx)->fail(FABLE_ERR_INVALID, std::string(msg)); \
+  } while (0)
+
+// every kernel launch goes through this so bench.py can report "gpu_launches".
+#define FB_LAUNCHED(ctx)                 \
+  do {                                   \
+    ++(ctx)->launches;                   \
+    FB_CUDA(ctx, cudaGetLastError());    \
+  } while (0)
+
+// RAII device buffer of doubles (or bytes via raw()).
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : ptr(o.ptr), bytes(o.bytes) { o.ptr = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); ptr = o.ptr; bytes = o.bytes; o.ptr = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+  }
+  cudaError_t alloc(size_t nbytes) {
+    release();
+    if (nbytes == 0) nbytes = 16;
+    cudaError_t e = cudaMalloc(&ptr, nbytes);
+    if (e == cudaSuccess) bytes = nbytes; else ptr = nullptr;
+    return e;
+  }
+  double* d() const { return static_cast<double*>(ptr); }
+};
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// ---- internal device-level entry points shared between translation units -------------------
+// rows.cu
+// d_c = YtU (p x k, ldc); d_s (may be NULL) = column sums of squares; d_resid = RAW residual sums.
+int fb_rowstats(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t ldy, const double* dU,
+                int64_t ldu, const double* d_c, int64_t ldc, int k, double* d_s, double* d_resid);
+int fb_colsumsq(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t ldy, double* d_s);
+int fb_cq(fable_ctx* ctx, const double* dV, int64_t ldv, const double* dd, int64_t p, int k,
+          double* d_c, int64_t ldc, double* d_q);
+// reduce.cu
+int fb_sum_log_scaled(fable_ctx* ctx, const double* d_x, int64_t p, double scale, double* host_out);
+int fb_tausq(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, int k,
+             double* host_tausq);
+int fb_finish_posterior(fable_ctx* ctx, const double* d_c, int64_t ldc, const double* d_s,
+                        const double* d_q, const double* d_resid, int64_t n, int64_t p, int k,
+                        double gamma0, double delta0sq, double tausq, int shrunk, double* d_G0,
+                        int64_t ldg, double* d_gnd, double* d_sig, double* d_sigmahat);
+int fb_var_inflation(fable_ctx* ctx, const double* d_sig, const double* d_G0, int64_t ldg, int64_t p,
+                     int k, double* host_sum_upper, double* host_sum_diag);
+int fb_cov_correct_dense(fable_ctx* ctx, const double* d_sig, const double* d_G, int64_t p,
+                         double* d_out, int upper_vector);
+int fb_sum_partials(fable_ctx* ctx, const double* d_part, int64_t nparts, int64_t len, int64_t stride,
+                    double alpha, double* d_out);
+// gemm.cu
+int fb_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K, double alpha,
+            const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc);
+// residual column sums of squares: d_resid[j] = sum_i (Y[i,j] - sum_l U[i,l] C[j,l])^2, l < k.
+int fb_gemm_resid(fable_ctx* ctx, int64_t n, int64_t p, int k, const double* dY, int64_t ldy,
+                  const double* dU, int64_t ldu, const double* dC, int64_t ldc, double* d_resid);
+// eig.cu
+int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps);
+// svd.cu: thin SVD of the device matrix dY (n x p, ld n): dU n x r, dd r, dV p x r (dense lds).
+int fb_svd(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, double* dU, double* dd, double* dV);
+// psi.cu
+struct PsiArgs {
+  const double* Lw;    // working-layout draws: Lw[(b*KP + l)*pp + j]
+  const double* s2w;   // sigma^2 draws: s2w[b*pp + j]   (may be NULL: no diagonal term)
+  int64_t pp;          // padded row count (multiple of the tile edge)
+  int64_t p;
+  int k, KP;
+  int B;               // draws in this batch
+  double* psi;         // materialised output, slot stride p*p (NULL: none)
+  int psi_slots;
+  int slot0;           // slot of draw b is (slot0 + b) % psi_slots
+  double* acc_sum;     // p x p accumulators (NULL: none); upper tiles only
+  double* acc_sq;
+};
+int fb_psi(fable_ctx* ctx, const PsiArgs& a);
+int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p);
+// sampler.cu
+struct SampleArgs {
+  const double* G0;    // p x k shrunk loadings mean, leading dimension ldg
+  int64_t ldg;
+  const double* gnd;   // p
+  double a_n, shape;   // shape = gamma_n / 2
+  int64_t p;
+  int k;
+  uint64_t seed;
+  const double* gam;   // injected (device) or NULL; element [(m - m_inj0)*p + j]
+  const double* z;     // injected (device) or NULL; element [(m - m_inj0)*p*k + l*p + j]
+  int64_t m_inj0;
+};
+int fb_sample_work(fable_ctx* ctx, const SampleArgs& a, int64_t m0, int B, int64_t pp, int KP,
+                   double* Lw, double* s2w);
+int fb_sample_ref(fable_ctx* ctx, const SampleArgs& a, int64_t m0, int64_t MC, int64_t j0,
+                  int64_t nj, int64_t ldm, double* dLambda, double* dSigma);

@@ -1,0 +1,245 @@
+// FP64 tensor-core GEMM (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4 on sm_100a; tcgen05 has no f64
+// kind) used for every dense contraction of the path:
+//   * Gram step  Y Y' (n <= p) or Y'Y (p < n)   -- replaces the dgesdd inside base-R svd(Y)
+//                                                   (reference R/FABLE_wrapper.R:23, 90)
+//   * V = Y'U D^-1 / U = Y V D^-1 back-multiplication
+//   * the rank-k' reconstruction + residual of CPPCriterionFunction
+//     (src/updated-FABLE-functions.cpp:161-166): fused epilogue, U D V' is never stored.
+//
+// C (M x N) = alpha * A B',  A: M x K, B: N x K.  Each operand is either "K-slow" (column-major
+// M x K: element (m,kk) at m + ld*kk) or "K-fast" (element (m,kk) at kk + ld*m).
+// CTA tile 128 x 128 x 16, 8 warps as 2 (M) x 4 (N), warp tile 64 x 32 = 8 x 4 DMMA tiles.
+// Shared tiles are [kk][m] with row stride 132 doubles (132 mod 16 = 4): the 16 lanes of a
+// half-warp (g = 0..3, t = 0..3) read bank 4t+g -> conflict-free 8-byte fragment loads.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int LDS_ = BM + 4;
+constexpr int STAGE_DOUBLES = BK * LDS_;
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <bool KFAST>
+__device__ __forceinline__ void load_tile_regs(const double* __restrict__ X, int64_t ld, int64_t rows,
+                                               int64_t row0, int64_t k0, int64_t kend, double (&r)[8]) {
+  if (!KFAST) {
+    const int m = threadIdx.x & 127, kb = threadIdx.x >> 7;
+    const int64_t gm = row0 + m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t gk = k0 + kb + 2 * i;
+      r[i] = (gm < rows && gk < kend) ? X[gm + ld * gk] : 0.0;
+    }
+  } else {
+    const int kk = threadIdx.x & 15, mb = threadIdx.x >> 4;
+    const int64_t gk = k0 + kk;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t gm = row0 + mb + 16 * i;
+      r[i] = (gm < rows && gk < kend) ? X[gk + ld * gm] : 0.0;
+    }
+  }
+}
+
+template <bool KFAST>
+__device__ __forceinline__ void store_tile_smem(double* __restrict__ S, const double (&r)[8]) {
+  if (!KFAST) {
+    const int m = threadIdx.x & 127, kb = threadIdx.x >> 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[(kb + 2 * i) * LDS_ + m] = r[i];
+  } else {
+    const int kk = threadIdx.x & 15, mb = threadIdx.x >> 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) S[kk * LDS_ + mb + 16 * i] = r[i];
+  }
+}
+
+// RESID = false: C[z] = alpha * partial product (z = split index, partial stride M*N when split)
+// RESID = true : out[blockIdx.x * N + n] = sum_{m in tile} (Yres[m + ldy*n] - acc)^2
+template <bool AKF, bool BKF, bool RESID>
+__global__ void __launch_bounds__(256)
+k_gemm(int64_t M, int64_t N, int64_t K, int64_t kper, double alpha, const double* __restrict__ A, int64_t lda,
+       const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc, int64_t split_stride,
+       const double* __restrict__ Yres, int64_t ldy) {
+  extern __shared__ double smem[];
+  double* As = smem;                      // [2][BK][LDS_]
+  double* Bs = smem + 2 * STAGE_DOUBLES;  // [2][BK][LDS_]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM, n0 = static_cast<int64_t>(blockIdx.y) * BN;
+  const int64_t kbeg = static_cast<int64_t>(blockIdx.z) * kper;
+  const int64_t kend = (kbeg + kper < K) ? kbeg + kper : K;
+
+  double c[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+
+  double ra[8], rb[8];
+  load_tile_regs<AKF>(A, lda, M, m0, kbeg, kend, ra);
+  load_tile_regs<BKF>(B, ldb, N, n0, kbeg, kend, rb);
+  store_tile_smem<AKF>(As, ra);
+  store_tile_smem<BKF>(Bs, rb);
+  __syncthreads();
+
+  int buf = 0;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = (k0 + BK < kend);
+    if (more) {
+      load_tile_regs<AKF>(A, lda, M, m0, k0 + BK, kend, ra);
+      load_tile_regs<BKF>(B, ldb, N, n0, k0 + BK, kend, rb);
+    }
+    const double* as = As + buf * STAGE_DOUBLES + wm * 64 + g;
+    const double* bs = Bs + buf * STAGE_DOUBLES + wn * 32 + g;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ++ks) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = as[(ks * 4 + t) * LDS_ + i * 8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = bs[(ks * 4 + t) * LDS_ + j * 8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(c[i][j], af[i], bf[j]);
+    }
+    if (more) {
+      store_tile_smem<AKF>(As + (buf ^ 1) * STAGE_DOUBLES, ra);
+      store_tile_smem<BKF>(Bs + (buf ^ 1) * STAGE_DOUBLES, rb);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  if (!RESID) {
+    double* Cz = C + static_cast<int64_t>(blockIdx.z) * split_stride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t n = n0 + wn * 32 + j * 8 + 2 * t + e;
+        if (n >= N) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t m = m0 + wm * 64 + i * 8 + g;
+          if (m < M) Cz[m + ldc * n] = alpha * c[i][j][e];
+        }
+      }
+    }
+  } else {
+    __syncthreads();          // everyone is done with the operand tiles: reuse smem for the reduce
+    double* red = smem;       // [2 (wm)][BN]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int nl = wn * 32 + j * 8 + 2 * t + e;
+        const int64_t n = n0 + nl;
+        double acc = 0.0;
+        if (n < N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0 + wm * 64 + i * 8 + g;
+            if (m < M) {
+              const double r = Yres[m + ldy * n] - c[i][j][e];
+              acc = fma(r, r, acc);
+            }
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (g == 0) red[wm * BN + nl] = acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < BN) {
+      const int64_t n = n0 + threadIdx.x;
+      if (n < N) C[static_cast<int64_t>(blockIdx.x) * N + n] = red[threadIdx.x] + red[BN + threadIdx.x];
+    }
+  }
+}
+
+constexpr size_t kSmemBytes = 4 * STAGE_DOUBLES * sizeof(double);
+
+template <bool AKF, bool BKF, bool RESID>
+int launch(fable_ctx* ctx, dim3 grid, int64_t M, int64_t N, int64_t K, int64_t kper, double alpha, const double* A,
+           int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t split_stride,
+           const double* Yres, int64_t ldy) {
+  static bool attr = false;
+  if (!attr) {
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_gemm<AKF, BKF, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kSmemBytes)));
+    attr = true;
+  }
+  k_gemm<AKF, BKF, RESID><<<grid, 256, kSmemBytes, ctx->stream>>>(M, N, K, kper, alpha, A, lda, B, ldb, C, ldc,
+                                                                 split_stride, Yres, ldy);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
+}  // namespace
+
+int fb_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K, double alpha,
+            const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc) {
+  FB_REQUIRE(ctx, M > 0 && N > 0 && K > 0, "gemm: empty problem");
+  const int64_t gm = ceil_div(M, BM), gn = ceil_div(N, BN);
+  FB_REQUIRE(ctx, gn <= 65535, "gemm: N too large for one launch");
+  // split K so that the grid covers the 148 SMs about twice
+  int64_t splits = 1;
+  const int64_t ktiles = ceil_div(K, BK);
+  if (gm * gn < 2 * ctx->sms) {
+    splits = ceil_div(2 * static_cast<int64_t>(ctx->sms), gm * gn);
+    if (splits > ktiles / 4) splits = ktiles / 4 > 0 ? ktiles / 4 : 1;
+    if (splits > 64) splits = 64;
+  }
+  const int64_t kper = round_up(ceil_div(K, splits), BK);
+  splits = ceil_div(K, kper);
+  dim3 grid(static_cast<unsigned>(gm), static_cast<unsigned>(gn), static_cast<unsigned>(splits));
+  DevBuf part;
+  double* out = dC;
+  int64_t out_ld = ldc, stride = 0;
+  double a_eff = alpha;
+  if (splits > 1) {
+    FB_CUDA(ctx, part.alloc(static_cast<size_t>(splits) * M * N * sizeof(double)));
+    out = part.d(); out_ld = M; stride = M * N; a_eff = 1.0;
+  }
+#define FB_GEMM_CASE(AK, BKF_)                                                                                \
+  if (a_kfast == AK && b_kfast == BKF_)                                                                       \
+    FB_TRY((launch<AK, BKF_, false>(ctx, grid, M, N, K, kper, a_eff, dA, lda, dB, ldb, out, out_ld, stride,   \
+                                    nullptr, 0)));
+  FB_GEMM_CASE(0, 0) FB_GEMM_CASE(0, 1) FB_GEMM_CASE(1, 0) FB_GEMM_CASE(1, 1)
+#undef FB_GEMM_CASE
+  if (splits > 1) {
+    if (ldc == M) {
+      FB_TRY(fb_sum_partials(ctx, part.d(), splits, M * N, M * N, alpha, dC));
+    } else {
+      for (int64_t n = 0; n < N; ++n)  // rare: strided output
+        FB_TRY(fb_sum_partials(ctx, part.d() + n * M, splits, M, M * N, alpha, dC + n * ldc));
+    }
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // partial buffer is freed on return
+  }
+  return FABLE_OK;
+}
+
+int fb_gemm_resid(fable_ctx* ctx, int64_t n, int64_t p, int k, const double* dY, int64_t ldy, const double* dU,
+                  int64_t ldu, const double* dC, int64_t ldc, double* d_resid) {
+  const int64_t gm = ceil_div(n, BM), gn = ceil_div(p, BN);
+  FB_REQUIRE(ctx, gn <= 65535, "gemm_resid: p too large for one launch");
+  DevBuf part;
+  FB_CUDA(ctx, part.alloc(static_cast<size_t>(gm) * p * sizeof(double)));
+  dim3 grid(static_cast<unsigned>(gm), static_cast<unsigned>(gn), 1);
+  FB_TRY((launch<false, false, true>(ctx, grid, n, p, k, round_up(k, BK), 1.0, dU, ldu, dC, ldc, part.d(), 0, 0,
+                                     dY, ldy)));
+  FB_TRY(fb_sum_partials(ctx, part.d(), gm, p, p, 1.0, d_resid));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}

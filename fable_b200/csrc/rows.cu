@@ -1,0 +1,140 @@
+// Row-posterior statistics: one streaming pass over Y (column-major n x p, column j contiguous).
+// Reference: src/updated-FABLE-functions.cpp:371-383 == :470-483 == :564-577
+//   YtU = V_k .* d_k                       -> c_jl, q_j = sum_l c_jl^2
+//   sigsq_hat = colsum((Y - U_k D_k V_k')^2)/n   -> resid_j (explicit residual, never s_j - q_j)
+//   sum(square(Y),0)                       -> s_j            (:499, :592)
+// p independent columns: warp-per-column-group, lanes stride the n rows (coalesced), U_k staged
+// in shared memory.  HBM-read bound: 8 n p bytes.  Ranks above KSMALL go through the DMMA
+// residual GEMM (gemm.cu) instead.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CW = 4;          // columns per warp
+constexpr int WARPS = 8;
+constexpr int COLS_PER_BLOCK = CW * WARPS;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_cq(const double* __restrict__ V, int64_t ldv, const double* __restrict__ d, int64_t p, int k,
+     double* __restrict__ c, int64_t ldc, double* __restrict__ q) {
+  const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (j >= p) return;
+  double acc = 0.0;
+  for (int l = 0; l < k; ++l) {
+    const double x = V[j + ldv * l] * d[l];
+    c[j + ldc * l] = x;
+    acc = fma(x, x, acc);
+  }
+  if (q) q[j] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+k_colsumsq(const double* __restrict__ Y, int64_t n, int64_t p, int64_t ldy, double* __restrict__ s) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = blockIdx.x * static_cast<int64_t>(WARPS) + (threadIdx.x >> 5);
+  if (j >= p) return;
+  const double* y = Y + ldy * j;
+  double acc = 0.0;
+  for (int64_t i = lane; i < n; i += 32) acc = fma(y[i], y[i], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) s[j] = acc;
+}
+
+// dynamic smem: Us[k][NI] then cs[COLS_PER_BLOCK][k]
+__global__ void __launch_bounds__(256)
+k_rowstats(const double* __restrict__ Y, int64_t n, int64_t p, int64_t ldy, const double* __restrict__ U,
+           int64_t ldu, const double* __restrict__ c, int64_t ldc, int k, int NI,
+           double* __restrict__ s_out, double* __restrict__ resid_out) {
+  extern __shared__ double smem[];
+  double* Us = smem;
+  double* cs = smem + static_cast<size_t>(k) * NI;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t jb = blockIdx.x * static_cast<int64_t>(COLS_PER_BLOCK);
+  for (int idx = threadIdx.x; idx < COLS_PER_BLOCK * k; idx += 256) {
+    const int jj = idx / k, l = idx % k;
+    cs[idx] = (jb + jj < p) ? c[jb + jj + ldc * l] : 0.0;
+  }
+  double ar[CW], as[CW];
+#pragma unroll
+  for (int t = 0; t < CW; ++t) { ar[t] = 0.0; as[t] = 0.0; }
+  const double* cw = cs + static_cast<size_t>(warp * CW) * k;
+  for (int64_t i0 = 0; i0 < n; i0 += NI) {
+    const int ni = static_cast<int>(n - i0 < NI ? n - i0 : NI);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < k * NI; idx += 256) {
+      const int l = idx / NI, i = idx % NI;
+      Us[idx] = (i < ni) ? U[i0 + i + ldu * l] : 0.0;
+    }
+    __syncthreads();
+    for (int i = lane; i < ni; i += 32) {
+      double f[CW];
+#pragma unroll
+      for (int t = 0; t < CW; ++t) f[t] = 0.0;
+      for (int l = 0; l < k; ++l) {
+        const double u = Us[l * NI + i];
+#pragma unroll
+        for (int t = 0; t < CW; ++t) f[t] = fma(u, cw[t * k + l], f[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < CW; ++t) {
+        const int64_t j = jb + warp * CW + t;
+        if (j < p) {
+          const double y = Y[i0 + i + ldy * j];
+          const double r = y - f[t];
+          ar[t] = fma(r, r, ar[t]);
+          as[t] = fma(y, y, as[t]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < CW; ++t) {
+    const double r = warp_sum(ar[t]), s = warp_sum(as[t]);
+    const int64_t j = jb + warp * CW + t;
+    if (lane == 0 && j < p) {
+      resid_out[j] = r;
+      if (s_out) s_out[j] = s;
+    }
+  }
+}
+
+}  // namespace
+
+int fb_cq(fable_ctx* ctx, const double* dV, int64_t ldv, const double* dd, int64_t p, int k, double* d_c,
+          int64_t ldc, double* d_q) {
+  k_cq<<<static_cast<unsigned>(ceil_div(p, 256)), 256, 0, ctx->stream>>>(dV, ldv, dd, p, k, d_c, ldc, d_q);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
+int fb_colsumsq(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t ldy, double* d_s) {
+  k_colsumsq<<<static_cast<unsigned>(ceil_div(p, WARPS)), 256, 0, ctx->stream>>>(dY, n, p, ldy, d_s);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
+// d_c: p x k (ldc) = YtU; outputs s (may be NULL), resid (sum of squared residuals, NOT divided by n)
+int fb_rowstats(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t ldy, const double* dU,
+                int64_t ldu, const double* d_c, int64_t ldc, int k, double* d_s, double* d_resid) {
+  const size_t budget = 96 * 1024 / sizeof(double);
+  int64_t NI = (static_cast<int64_t>(budget) - COLS_PER_BLOCK * k) / k;
+  NI = NI / 32 * 32;
+  FB_REQUIRE(ctx, NI >= 32, "rowstats: rank too large for the small-k kernel");
+  if (NI > round_up(n, 32)) NI = round_up(n, 32);
+  const size_t smem = (static_cast<size_t>(k) * NI + static_cast<size_t>(COLS_PER_BLOCK) * k) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_rowstats, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set = true;
+  }
+  k_rowstats<<<static_cast<unsigned>(ceil_div(p, COLS_PER_BLOCK)), 256, smem, ctx->stream>>>(
+      dY, n, p, ldy, dU, ldu, d_c, ldc, k, static_cast<int>(NI), d_s, d_resid);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}

@@ -1,0 +1,168 @@
+/* fable_b200.h -- C-ABI of libfable_b200.so: the B200 (sm_100a) drop-in for the estimation and
+ * sampling hot path of the FABLE R package (shounakch/FABLE).
+ *
+ * Every entry point replaces one function the reference reaches through Rcpp's `.Call` shims
+ * (reference `src/RcppExports.cpp:96-172`, registered at `:212-228`).  The reference side binds
+ * these from its Rcpp translation unit (see INTEGRATION.md for the stub a maintainer adds).
+ *
+ * Conventions
+ *   - plain C, `extern "C"`; no torch / Rcpp / Armadillo types cross this boundary.
+ *   - every matrix is FP64 COLUMN-MAJOR (R / Armadillo memory order), leading dimension = rows.
+ *   - `fable_*` functions take HOST pointers, never retain them past return, and write results
+ *     straight into caller-allocated host memory (R vectors): one D2H copy, no intermediates.
+ *   - `fable_dev_*` functions take DEVICE pointers (resident-in-HBM path used by bench.py, the
+ *     multi-GPU drivers and the host layer itself).
+ *   - return value: 0 = FABLE_OK, otherwise an error code; `fable_last_error(ctx)` returns the
+ *     message.  The library never calls exit/abort and never calls back into R.
+ *   - there is NO CPU fallback: every function fails with FABLE_ERR_CUDA when no sm_100 device
+ *     is usable.
+ *   - a context is bound to one device and is not thread-safe; use one per calling thread/GPU.
+ */
+#ifndef FABLE_B200_H
+#define FABLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FABLE_B200_ABI_VERSION 1
+
+typedef enum {
+  FABLE_OK = 0,
+  FABLE_ERR_INVALID = 1,   /* bad dimension / rank / NULL pointer / non-finite scalar   */
+  FABLE_ERR_CUDA = 2,      /* CUDA runtime error or no usable sm_100 device              */
+  FABLE_ERR_NOMEM = 3,     /* device or pinned-host allocation failed                    */
+  FABLE_ERR_NUMERIC = 4,   /* eigensolver did not converge / non-positive variance        */
+  FABLE_ERR_INTERRUPT = 5  /* the caller's interrupt callback asked to stop              */
+} fable_status;
+
+typedef struct fable_ctx fable_ctx;             /* one device, one stream set, scratch pools */
+typedef struct fable_posterior fable_posterior; /* device-resident row posterior + draw state  */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int fable_abi_version(void);
+/* device: CUDA ordinal.  seed: key of the counter-based Philox4x32-10 stream ("fable-philox-v1",
+ * DESIGN.md); the Rcpp layer derives it from R's RNG inside RNGScope so set.seed() is honoured
+ * (reference RNGScope: src/RcppExports.cpp:159). */
+int fable_ctx_create(int device, uint64_t seed, fable_ctx** out);
+void fable_ctx_destroy(fable_ctx* ctx);
+const char* fable_last_error(const fable_ctx* ctx); /* ctx may be NULL: last create() failure */
+int fable_ctx_set_seed(fable_ctx* ctx, uint64_t seed);
+/* optional: polled between draw batches; non-zero return aborts with FABLE_ERR_INTERRUPT
+ * (reference: Rcpp::checkUserInterrupt, updated-FABLE-functions.cpp:699). */
+int fable_ctx_set_interrupt(fable_ctx* ctx, int (*poll)(void*), void* user);
+/* number of kernels this context has launched since creation (bench.py "gpu_launches"). */
+int64_t fable_ctx_launch_count(const fable_ctx* ctx);
+int fable_ctx_synchronize(fable_ctx* ctx);
+/* the context's main stream as a cudaStream_t cast to void* (for CUDA-event timing). */
+void* fable_ctx_stream(fable_ctx* ctx);
+
+/* ---- a1/a2: thin SVD of Y and the kMax rule ---------------------------------------------------
+ * Replaces base-R `svd(Y)` inside the wrappers (reference R/FABLE_wrapper.R:23-26, 90-93) and the
+ * exported-but-unused CPPsvd (updated-FABLE-functions.cpp:40-74).
+ * Y n x p.  r = min(n,p).  U n x r, d r (descending), V p x r.  Gram (DMMA) + Jacobi eigensolve
+ * + back-multiplication.  Signs: each V column has its largest-|entry| positive. */
+int fable_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, double* d, double* V);
+/* min{ i : cumsum(d)_i / sum(d) >= maxProp }, 1-based (R/FABLE_wrapper.R:27, 94). Host-only. */
+int fable_kmax(const double* d, int64_t r, double maxProp, int* kMax);
+
+/* ---- a3: CPPCriterionFunction (updated-FABLE-functions.cpp:127-213) ------------------------- */
+int fable_criterion(fable_ctx* ctx, int kInd, const double* Y, int64_t n, int64_t p,
+                    const double* U, const double* V, const double* d, int64_t r, double* out);
+/* ---- a4: CPPBisectionRecursion (:215-271) -> (lower, upper) ---------------------------------- */
+int fable_bisection(fable_ctx* ctx, int lower, int upper, const double* Y, int64_t n, int64_t p,
+                    const double* U, const double* V, const double* d, int64_t r, int* lo, int* hi);
+/* ---- a5: CPPRankEstimator (:281-341) --------------------------------------------------------- */
+int fable_rank_estimator(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* U,
+                         const double* V, const double* d, int64_t r, int kMax, int* kEst);
+
+/* ---- a6: FABLEHyperParameters (:343-399), UNSHRUNK G0 = YtU/sqrt(n) ---------------------------
+ * sig p, G0 p x k, tausq scalar, G p x p (NULL to skip the dense p x p). */
+int fable_hyper_parameters(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* U,
+                           const double* V, const double* d, int64_t r, int kEst, double* sig,
+                           double* G0, double* tausq, double* G);
+
+/* ---- a7: coverage-correction ---------------------------------------------------------------------
+ * fable_cov_correct_matrix = CPPcov_correct_matrix (:401-428): upper-triangle vector, column-major
+ * trimatu order, length p(p+1)/2, from sig (p) and a dense G (p x p).
+ * fable_var_inflation: the scalar the wrappers derive from it, computed as a fused reduction that
+ * never stores B.  G is given by its factor G0 (p x k, G = G0 G0').  variant 0 = wrapper formula
+ * (sum over the FULL matrix / (p(p+1)/2))^2 (R/FABLE_wrapper.R:41-44); variant 1 = script formula
+ * mean(upper triangle)^2 (extras/replicationCodes/runtimeScript.R:75-78). */
+int fable_cov_correct_matrix(fable_ctx* ctx, const double* sig, const double* G, int64_t p,
+                             double* Bupper);
+int fable_cov_correct_full(fable_ctx* ctx, const double* sig, const double* G, int64_t p,
+                           double* B); /* R twin cov_correct_matrix (R/FABLE_code.R:189-206) */
+int fable_var_inflation(fable_ctx* ctx, const double* sig, const double* G0, int64_t p, int k,
+                        int variant, double* out);
+
+/* ---- a8: CPPFABLEPostMean (:440-519) ----------------------------------------------------------
+ * Cov p x p (= CovPostMean).  Optional extra outputs (NULL to skip) expose the internals the
+ * reference keeps private, for parity checks: G0s p x k (shrunk Lambda mean), SigmaHat p. */
+int fable_post_mean(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
+                    double delta0sq, const double* U, const double* V, const double* d, int64_t r,
+                    int kMax, double* Cov, int* kEst, double* G0s, double* SigmaHat);
+
+/* ---- a9: CPPFABLESampler (:532-629) -------------------------------------------------------------
+ * Outputs (any may be NULL to skip): LambdaSamples MC x (k p) [element (m, j*k+l) at m+MC*(j*k+l)],
+ * SigmaSqSamples MC x p, SigmaPostMean p, SigmaPlugIn p, tausq, G p x p (= G0 G0', shrunk G0).
+ * Draw source: gam_inj / z_inj non-NULL -> INJECTED draws in the reference's consumption order
+ * (gam[m*p+j]; z[m*p*k + l*p + j]); both NULL -> native Philox stream, draw index m0+m.
+ * psi_sum / psi_sumsq (p x p each, NULL to skip): entry-wise sum_m Psi_m and sum_m Psi_m^2 of
+ * Psi_m = Lambda_m Lambda_m' + diag(sigma2_m) (entry formula :672-684; the mean is :688). */
+int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
+                  double delta0sq, int64_t MC, const double* U, const double* V, const double* d,
+                  int64_t r, int kEst, double varInflation, const double* gam_inj,
+                  const double* z_inj, int64_t m0, double* LambdaSamples, double* SigmaSqSamples,
+                  double* SigmaPostMean, double* SigmaPlugIn, double* tausq, double* G,
+                  double* psi_sum, double* psi_sumsq);
+
+/* ---- resident-in-HBM posterior object (what fable_sampler is built from) ---------------------- */
+/* Uploads Y, U_k, V_k, d_k, runs the row-posterior kernels, keeps G0 / gnd / a_n on the device. */
+int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
+                           double delta0sq, const double* U, const double* V, const double* d,
+                           int64_t r, int kEst, double varInflation, fable_posterior** out);
+void fable_posterior_destroy(fable_posterior* post);
+/* copy-out of the row posterior (NULL to skip): G0s p x k, gnd p, sig p, scalars[4] =
+ * {tausq, a_n, gamma_n, w = n + 1/tausq}. */
+int fable_posterior_get(fable_posterior* post, double* G0s, double* gnd, double* sig, double* scalars);
+/* One batch of B draws m0..m0+B-1 entirely on the device:
+ *   sampler kernel -> Lambda_m, sigma2_m (working layout) -> covariance kernel.
+ * dev_psi: device buffer of `psi_slots` p x p matrices (NULL = do not materialise); draw m lands in
+ * slot (m - m0) % psi_slots.  accumulate != 0 adds the batch into the posterior's own sum / sumsq
+ * accumulators (upper tiles; mirrored on fetch).  gam/z: injected DEVICE buffers or NULL. */
+int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi,
+                               int psi_slots, int accumulate, const double* dev_gam,
+                               const double* dev_z);
+/* reference-layout samples for draws m0..m0+MC-1 into HOST arrays with leading dimension ldm
+ * (>= MC; rows m-m0) -- NULL to skip either. */
+int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64_t ldm,
+                            double* LambdaSamples, double* SigmaSqSamples,
+                            const double* gam_inj, const double* z_inj);
+/* accumulators: device pointers (full p x p, upper tiles valid until mirrored), reset, fetch. */
+int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** dev_sumsq);
+int fable_posterior_accum_reset(fable_posterior* post);
+int fable_posterior_accum_mirror(fable_posterior* post); /* make both triangles valid (device) */
+int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sumsq); /* host out  */
+
+/* ---- device-pointer primitives ------------------------------------------------------------------ */
+/* out[u + p*v] = sum_l A[u + lda*l] A[v + lda*l] + (u==v ? s[u] : 0), dense symmetric p x p
+ * (serves G = G0 G0' :391/:491/:627 and CovPostMean :512).  s may be NULL. */
+int fable_dev_rankk_cov(fable_ctx* ctx, const double* dA, int64_t lda, const double* ds, int64_t p,
+                        int k, double* dOut);
+/* C (M x N, ldc) = alpha * op(A) op(B)':  A is M x K, B is N x K.  a_kfast / b_kfast: the K index
+ * is the contiguous one of that operand (i.e. it is stored K x M with leading dimension ld).
+ * FP64 DMMA tensor-core GEMM (Gram YY' / Y'Y, V = Y'U D^-1, rank-k reconstruction). */
+int fable_dev_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K,
+                   double alpha, const double* dA, int64_t lda, const double* dB, int64_t ldb,
+                   double* dC, int64_t ldc);
+/* symmetric eigen-decomposition of the m x m matrix dG (destroyed): eigenvalues descending in
+ * dW (m), eigenvectors in the columns of dQ (m x m). */
+int fable_dev_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FABLE_B200_H */
