@@ -377,6 +377,27 @@ class Posterior:
 
 
 # ------------------------------------------------------------------------------------------------
+# device-pointer primitives (addresses as ints, e.g. torch tensors' data_ptr())
+# ------------------------------------------------------------------------------------------------
+def dev_rankk_cov(ctx, dA, lda, ds, p, k, dOut):
+    ctx.check(_load().fable_dev_rankk_cov(ctx._h, C.c_void_p(dA), _i64(lda), C.c_void_p(ds or None), _i64(p),
+                                          C.c_int(k), C.c_void_p(dOut)))
+
+
+def dev_gemm(ctx, a_kfast, b_kfast, M, N, K, alpha, dA, lda, dB, ldb, dC, ldc):
+    ctx.check(_load().fable_dev_gemm(ctx._h, C.c_int(a_kfast), C.c_int(b_kfast), _i64(M), _i64(N), _i64(K),
+                                     C.c_double(alpha), C.c_void_p(dA), _i64(lda), C.c_void_p(dB), _i64(ldb),
+                                     C.c_void_p(dC), _i64(ldc)))
+
+
+def dev_syevj(ctx, dG, m, dW, dQ):
+    sweeps = C.c_int()
+    ctx.check(_load().fable_dev_syevj(ctx._h, C.c_void_p(dG), _i64(m), C.c_void_p(dW), C.c_void_p(dQ),
+                                      C.byref(sweeps)))
+    return sweeps.value
+
+
+# ------------------------------------------------------------------------------------------------
 # a11: the two public wrappers (R/FABLE_wrapper.R)
 # ------------------------------------------------------------------------------------------------
 def FABLEPosteriorMean(Y, gamma0=1.0, delta0sq=1.0, maxProp=0.5, ctx=None):

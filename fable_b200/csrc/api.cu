@@ -235,6 +235,8 @@ int fable_ctx_create(int device, uint64_t seed, fable_ctx** out) {
 void fable_ctx_destroy(fable_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->ring) cudaFree(ctx->ring);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -255,6 +257,47 @@ int fable_ctx_synchronize(fable_ctx* ctx) {
   return FABLE_OK;
 }
 void* fable_ctx_stream(fable_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+
+int fable_ctx_kernel_timing(fable_ctx* ctx, int enable) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  ctx->timing = enable != 0;
+  ctx->ev_used = 0;
+  return FABLE_OK;
+}
+
+int fable_ctx_kernel_time(fable_ctx* ctx, double* total_ms, int64_t* launches) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    float ms = 0.f;
+    FB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = static_cast<int64_t>(ctx->ev_used / 2);
+  return FABLE_OK;
+}
+
+int fable_ctx_set_psi_ring(fable_ctx* ctx, int slots) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, slots >= 0, "psi ring: slots must be >= 0");
+  ctx->ring_slots = slots;
+  if (slots == 0 && ctx->ring) {
+    FB_CUDA(ctx, cudaSetDevice(ctx->device));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->ring); ctx->ring = nullptr; ctx->ring_bytes = 0;
+  }
+  return FABLE_OK;
+}
+
+int fable_ctx_psi_ring(fable_ctx* ctx, double** dev_ring, int* slots) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  if (dev_ring) *dev_ring = ctx->ring;
+  if (slots) *slots = ctx->ring ? ctx->ring_slots : 0;
+  return FABLE_OK;
+}
 
 // ---- a1 / a2 -------------------------------------------------------------------------------------
 int fable_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, double* d, double* V) {
@@ -278,12 +321,14 @@ int fable_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, 
 
 int fable_kmax(const double* d, int64_t r, double maxProp, int* kMax) {
   if (!d || !kMax || r < 1) return FABLE_ERR_INVALID;
-  double total = 0.0;
-  for (int64_t i = 0; i < r; ++i) total += d[i];             // sum(svalsY)
-  double run = 0.0;
+  // R accumulates sum() and cumsum() sequentially in long double and rounds each result to double.
+  long double acc = 0.0L;
+  for (int64_t i = 0; i < r; ++i) acc += d[i];               // sum(svalsY)
+  const double total = static_cast<double>(acc);
+  acc = 0.0L;
   for (int64_t i = 0; i < r; ++i) {                          // cumsum(svalsY)/sum >= maxProp
-    run += d[i];
-    if (run / total >= maxProp) { *kMax = static_cast<int>(i + 1); return FABLE_OK; }
+    acc += d[i];
+    if (static_cast<double>(acc) / total >= maxProp) { *kMax = static_cast<int>(i + 1); return FABLE_OK; }
   }
   return FABLE_ERR_INVALID;                                  // R: min(integer(0)) = Inf + warning
 }
@@ -597,10 +642,20 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
       FB_TRY(upload(ctx, dz, z_inj, static_cast<size_t>(MC) * p * kEst));
     }
     FB_TRY(fable_posterior_accum_reset(post));
+    if (ctx->ring_slots > 0) {
+      const size_t need = static_cast<size_t>(ctx->ring_slots) * p * p * sizeof(double);
+      if (need != ctx->ring_bytes) {
+        FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->ring) { cudaFree(ctx->ring); ctx->ring = nullptr; ctx->ring_bytes = 0; }
+        FB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->ring), need));
+        ctx->ring_bytes = need;
+      }
+    }
     const int B = 32;
     for (int64_t b0 = 0; b0 < MC; b0 += B) {
       const int nb = static_cast<int>(MC - b0 < B ? MC - b0 : B);
-      FB_TRY(fable_posterior_draw_batch(post, m0 + b0, nb, nullptr, 0, 1,
+      FB_TRY(fable_posterior_draw_batch(post, m0 + b0, nb, ctx->ring_slots > 0 ? ctx->ring : nullptr,
+                                        ctx->ring_slots, 1,
                                         gam_inj ? dgam.d() + b0 * p : nullptr,
                                         gam_inj ? dz.d() + b0 * p * kEst : nullptr));
       if (ctx->poll && ctx->poll(ctx->poll_user)) return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");

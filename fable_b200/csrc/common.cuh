@@ -18,6 +18,14 @@ struct fable_ctx {
   int64_t launches = 0;
   int (*poll)(void*) = nullptr;
   void* poll_user = nullptr;
+  // optional per-kernel CUDA-event timing of the covariance kernel (bench.py roofline)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;     // pairs: [2i] before, [2i+1] after the launch
+  size_t ev_used = 0;
+  // optional device ring of materialised Psi draws kept by fable_sampler (fable_ctx_set_psi_ring)
+  int ring_slots = 0;
+  double* ring = nullptr;
+  size_t ring_bytes = 0;
 
   int fail(int code, const std::string& msg) {
     err = msg;

@@ -190,6 +190,17 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
   const int64_t nT = ceil_div(a.p, TILE);
   const int64_t tiles = nT * (nT + 1) / 2;
   const int64_t chunk = 1 << 30;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx->timing) {
+    while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+      cudaEvent_t e;
+      FB_CUDA(ctx, cudaEventCreate(&e));
+      ctx->ev_pool.push_back(e);
+    }
+    ev0 = ctx->ev_pool[ctx->ev_used]; ev1 = ctx->ev_pool[ctx->ev_used + 1];
+    ctx->ev_used += 2;
+    FB_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+  }
   for (int64_t t0 = 0; t0 < tiles; t0 += chunk) {
     const unsigned g = static_cast<unsigned>(tiles - t0 < chunk ? tiles - t0 : chunk);
     if (mat && acc) k_psi<true, true><<<g, 256, 0, ctx->stream>>>(a, t0);
@@ -197,6 +208,7 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
     else k_psi<false, true><<<g, 256, 0, ctx->stream>>>(a, t0);
     FB_LAUNCHED(ctx);
   }
+  if (ev1) FB_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
   return FABLE_OK;
 }
 

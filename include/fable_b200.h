@@ -58,6 +58,17 @@ int64_t fable_ctx_launch_count(const fable_ctx* ctx);
 int fable_ctx_synchronize(fable_ctx* ctx);
 /* the context's main stream as a cudaStream_t cast to void* (for CUDA-event timing). */
 void* fable_ctx_stream(fable_ctx* ctx);
+/* Per-launch CUDA-event timing of the covariance kernel on the context's stream.  enable != 0
+ * starts (and clears) the record; fable_ctx_kernel_time synchronises and returns the summed device
+ * time in milliseconds and the number of launches recorded since it was enabled. */
+int fable_ctx_kernel_timing(fable_ctx* ctx, int enable);
+int fable_ctx_kernel_time(fable_ctx* ctx, double* total_ms, int64_t* launches);
+/* slots > 0: fable_sampler's Psi pass also MATERIALISES every draw Psi_m (dense p x p) into a device
+ * ring of `slots` matrices owned by the context (draw m in slot m % slots), next to the sum / sumsq
+ * accumulators -- the block-wise covariance formation named by the north star, left resident for
+ * device-side consumers (fable_ctx_psi_ring).  slots == 0 (default): accumulate only. */
+int fable_ctx_set_psi_ring(fable_ctx* ctx, int slots);
+int fable_ctx_psi_ring(fable_ctx* ctx, double** dev_ring, int* slots);
 
 /* ---- a1/a2: thin SVD of Y and the kMax rule ---------------------------------------------------
  * Replaces base-R `svd(Y)` inside the wrappers (reference R/FABLE_wrapper.R:23-26, 90-93) and the

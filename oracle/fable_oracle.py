@@ -48,7 +48,10 @@ def svd_thin(Y):
 def kmax_rule(d, maxProp):
     """`min(which(cumsum(d)/sum(d) >= maxProp))` (R/FABLE_wrapper.R:27, 94); 1-based."""
     d = np.asarray(d, dtype=np.float64)
-    frac = np.cumsum(d) / np.sum(d)
+    # R accumulates both sum() and cumsum() sequentially in long double and rounds to double
+    # (R sources summary.c rsum / cum.c cumsum), so cumsum(d)[r] == sum(d) exactly.
+    cs = np.cumsum(d.astype(np.longdouble))
+    frac = cs.astype(np.float64) / np.float64(cs[-1])
     idx = np.nonzero(frac >= maxProp)[0]
     if idx.size == 0:
         raise ValueError("kMax rule: no index reaches maxProp (R would return Inf with a warning)")

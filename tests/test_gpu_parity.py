@@ -1,0 +1,335 @@
+"""GPU parity tests: every entry point of the C-ABI (through the Python mirror of the reference's
+R interface) against the CPU oracle on the same inputs, the frozen golden fixtures, and -- at
+BASELINE.json's full sizes -- size-independent properties.
+
+Tolerance: BASELINE.json north_star -- 1e-10 relative in FP64 (SURVEY.md §8c metrics: matrices
+max|x-ref|/max|ref|, positive vectors element-wise relative, integers exact).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import fable_b200 as fb
+from fable_b200 import synth
+from oracle import fable_oracle as orc
+from oracle import c_oracle
+from conftest import relerr_mat, relerr_vec, TOL
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["a", "b", "c"]
+
+
+def _svd_inputs(n, p, k, rep):
+    Y = synth.factor_data(n, p, k, rep=rep)
+    u, d, v = orc.svd_thin(Y)
+    return Y, u, d, v
+
+
+# ---- golden fixtures ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_golden_estimation(ctx, golden, name):
+    g = lambda key: golden[f"{name}_{key}"]
+    Y, u, d, v = g("Y"), g("u"), g("d"), g("v")
+    kMax95, kMax50 = int(g("kMax95")), int(g("kMax50"))
+    crit = np.array([fb.CPPCriterionFunction(k, Y, u, v, d, ctx=ctx) for k in range(1, kMax95 + 1)])
+    assert relerr_vec(crit, g("crit")) < TOL
+    assert fb.CPPRankEstimator(Y, u, v, d, kMax50, ctx=ctx) == int(g("kEst50"))
+    kEst = fb.CPPRankEstimator(Y, u, v, d, kMax95, ctx=ctx)
+    assert kEst == int(g("kEst95"))
+    np.testing.assert_array_equal(fb.CPPBisectionRecursion(1, kMax95, Y, u, v, d, ctx=ctx), g("bis").astype(float))
+    hyp = fb.FABLEHyperParameters(Y, u, v, d, kEst, ctx=ctx)
+    assert relerr_vec(hyp["SigmaSqEstimate"], g("hyp_sig")) < TOL
+    assert relerr_mat(hyp["G0"], g("hyp_G0")) < TOL
+    assert relerr_mat(hyp["G"], g("hyp_G")) < TOL
+    assert abs(hyp["tauSqEstimate"] / float(g("hyp_tau")) - 1) < TOL
+    assert relerr_vec(fb.CPPcov_correct_matrix(hyp["SigmaSqEstimate"], hyp["G"], ctx=ctx), g("Bupper")) < TOL
+    B = fb.cov_correct_matrix(hyp["SigmaSqEstimate"], hyp["G"], ctx=ctx)
+    assert relerr_mat(B, orc.cov_correct_matrix_R(g("hyp_sig"), g("hyp_G"))) < TOL
+    assert abs(fb.var_inflation(hyp["SigmaSqEstimate"], hyp["G0"], "wrapper", ctx=ctx) / float(g("vi_wrapper")) - 1) < TOL
+    assert abs(fb.var_inflation(hyp["SigmaSqEstimate"], hyp["G0"], "script", ctx=ctx) / float(g("vi_script")) - 1) < TOL
+    pm = fb.CPPFABLEPostMean(Y, 1.0, 1.0, u, v, d, kMax50, ctx=ctx, internals=True)
+    assert pm["kEst"] == int(g("kEst50"))
+    assert relerr_mat(pm["CovPostMean"], g("pm_cov")) < TOL
+    assert relerr_mat(pm["G0"], g("pm_G0")) < TOL
+    assert relerr_vec(pm["SigmaHat"], g("pm_sigmahat")) < TOL
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_sampler_injected(ctx, golden, name):
+    g = lambda key: golden[f"{name}_{key}"]
+    Y, u, d, v = g("Y"), g("u"), g("d"), g("v")
+    kEst = int(g("kEst95"))
+    out = fb.CPPFABLESampler(Y, 1.0, 1.0, 7, u, v, d, kEst, float(g("vi_wrapper")), ctx=ctx, gam=g("gam"), z=g("z"),
+                             psi_moments=True)
+    assert relerr_mat(out["LambdaSamples"], g("smp_L")) < TOL
+    assert relerr_vec(out["SigmaSqSamples"], g("smp_S")) < TOL
+    assert relerr_vec(out["SigmaSqEstimatePostMean"], g("smp_postmean")) < TOL
+    assert relerr_vec(out["SigmaSqEstimatePlugIn"], g("hyp_sig")) < TOL
+    assert relerr_mat(out["G"], g("smp_G")) < TOL
+    assert abs(out["tauSqEstimate"] / float(g("smp_tau")) - 1) < TOL
+    assert relerr_mat(out["PsiSum"], g("psi_sum")) < TOL
+    assert relerr_mat(out["PsiSumSq"], g("psi_sumsq")) < TOL
+    assert out["EstimatedRank"] == kEst and out["VarianceInflation"] == float(g("vi_wrapper"))
+
+
+# ---- SVD replacement (a1): sign-invariant comparison + decomposition properties -------------------
+@pytest.mark.parametrize("n,p,k", [(40, 120, 3), (64, 48, 2), (33, 77, 4), (200, 1000, 5), (300, 130, 4), (1, 5, 1), (5, 1, 1)])
+def test_svd_against_lapack(ctx, n, p, k):
+    Y = synth.factor_data(n, p, k, rep=n + p)
+    s = fb.svd(Y, ctx=ctx)
+    u, d, v = orc.svd_thin(Y)
+    assert relerr_vec(s["d"], d) < TOL
+    r = min(n, p)
+    assert s["u"].shape == (n, r) and s["v"].shape == (p, r)
+    assert relerr_mat((s["u"] * s["d"]) @ s["v"].T, Y) < TOL
+    assert relerr_mat(s["u"].T @ s["u"], np.eye(r)) < 1e-9 and relerr_mat(s["v"].T @ s["v"], np.eye(r)) < 1e-9
+    # canonical signs (largest |entry| of each v column positive) -> vectors comparable where the
+    # spectrum is well separated (the leading k factor directions)
+    sgn = np.sign(v[np.argmax(np.abs(v), axis=0), np.arange(r)])
+    kk = min(k, r)
+    assert relerr_mat(s["v"][:, :kk], (v * sgn)[:, :kk]) < 1e-8
+    assert relerr_mat(s["u"][:, :kk], (u * sgn)[:, :kk]) < 1e-8
+
+
+# ---- C1: n=500, p=1000, k=10 (BASELINE.json configs[0]) end to end vs the oracle ------------------
+@pytest.fixture(scope="module")
+def c1():
+    Y, u, d, v = _svd_inputs(500, 1000, 10, 0)
+    return dict(Y=Y, u=u, d=d, v=v)
+
+
+def test_c1_rank_and_postmean(ctx, c1):
+    Y, u, d, v = c1["Y"], c1["u"], c1["d"], c1["v"]
+    for maxProp in (0.5, 0.95):
+        kMax = orc.kmax_rule(d, maxProp)
+        assert fb.kmax_rule(d, maxProp) == kMax
+        assert fb.CPPRankEstimator(Y, u, v, d, kMax, ctx=ctx) == orc.rank_estimator(Y, u, v, d, kMax)
+    kMax = orc.kmax_rule(d, 0.5)
+    ref = orc.post_mean(Y, 1.0, 1.0, u, v, d, kMax)
+    got = fb.CPPFABLEPostMean(Y, 1.0, 1.0, u, v, d, kMax, ctx=ctx, internals=True)
+    assert got["kEst"] == ref["kEst"]
+    assert relerr_mat(got["CovPostMean"], ref["CovPostMean"]) < TOL
+    assert relerr_mat(got["G0"], ref["G0"]) < TOL and relerr_vec(got["SigmaHat"], ref["SigmaHat"]) < TOL
+    assert np.array_equal(got["CovPostMean"], got["CovPostMean"].T)
+
+
+def test_c1_criterion_large_ranks_use_the_dmma_path(ctx, c1):
+    """Ranks above 32 go through the DMMA residual GEMM: same values as the explicit residual."""
+    Y, u, d, v = c1["Y"], c1["u"], c1["d"], c1["v"]
+    for k in (1, 32, 33, 100, 257, 440):
+        assert abs(fb.CPPCriterionFunction(k, Y, u, v, d, ctx=ctx) / orc.criterion(k, Y, u, v, d) - 1) < TOL
+
+
+def test_c1_wrappers_end_to_end(ctx, c1):
+    Y = c1["Y"]
+    ref = orc.FABLEPosteriorMean(Y)
+    got = fb.FABLEPosteriorMean(Y, ctx=ctx)
+    assert got["estRank"] == ref["estRank"]
+    assert relerr_vec(got["svdY"]["d"], ref["svdY"]["d"]) < TOL
+    assert relerr_mat(got["FABLEPostMean"], ref["FABLEPostMean"]) < TOL       # sign-invariant
+    MC = 1000
+    p = Y.shape[1]
+    gam, zfull = synth.injected_draws(MC, p, 10, 0.5 * (1.0 + Y.shape[0]), seed=777)
+    refs = orc.FABLEPosteriorSampler(Y, MC=MC, gam=gam, z=zfull)
+    gots = fb.FABLEPosteriorSampler(Y, MC=MC, ctx=ctx, gam=gam, z=zfull)
+    assert gots["estRank"] == refs["estRank"] == 10
+    assert abs(gots["varInflation"] / refs["varInflation"] - 1) < TOL
+    a, b = gots["CCFABLESamples"], refs["CCFABLESamples"]
+    assert relerr_vec(a["SigmaSqSamples"], b["SigmaSqSamples"]) < TOL          # sign-invariant
+    assert relerr_mat(a["G"], b["G"]) < TOL
+    assert relerr_vec(a["SigmaSqEstimatePostMean"], b["SigmaSqEstimatePostMean"]) < TOL
+    # Lambda draws depend on the singular-vector signs: both SVDs canonicalised the same way
+    sgn = np.sign(refs["svdY"]["v"][np.argmax(np.abs(refs["svdY"]["v"]), axis=0), np.arange(refs["svdY"]["v"].shape[1])])[:10]
+    Lref = b["LambdaSamples"].reshape(MC, p, 10)
+    # Lambda_m = G0 + a_n sd z: flipping column l of V flips G0[:, l] only
+    G0 = b["G0"]
+    Lflip = (Lref - G0[None]) + (G0 * sgn)[None]
+    assert relerr_mat(a["LambdaSamples"], Lflip.reshape(MC, p * 10)) < 1e-8
+
+
+def test_c1_sampler_cpp_boundary_injected(ctx, c1):
+    Y, u, d, v = c1["Y"], c1["u"], c1["d"], c1["v"]
+    MC, k = 64, 10
+    gam, z = synth.injected_draws(MC, Y.shape[1], k, 0.5 * (1.0 + Y.shape[0]), seed=778)
+    ref = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.26, gam, z)
+    got = fb.CPPFABLESampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.26, ctx=ctx, gam=gam, z=z, psi_moments=True)
+    assert relerr_mat(got["LambdaSamples"], ref["LambdaSamples"]) < TOL
+    assert relerr_vec(got["SigmaSqSamples"], ref["SigmaSqSamples"]) < TOL
+    s1, s2 = c_oracle.psi_moments(ref["LambdaSamples"], ref["SigmaSqSamples"], k)
+    assert relerr_mat(got["PsiSum"], s1) < TOL and relerr_mat(got["PsiSumSq"], s2) < TOL
+    assert np.array_equal(got["PsiSum"], got["PsiSum"].T)
+
+
+# ---- native RNG: GPU stream == CPU statement of fable-philox-v1; moments; invariances --------------
+def test_native_stream_matches_cpu_specification(ctx, c1):
+    Y, u, d, v = c1["Y"], c1["u"], c1["d"], c1["v"]
+    MC, k, p, n = 40, 10, Y.shape[1], Y.shape[0]
+    ctx.set_seed(2024)
+    got = fb.CPPFABLESampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.26, ctx=ctx, want_G=False)
+    gam, z = c_oracle.rng_fill(2024, 0, MC, p, k, 0.5 * (1.0 + n))
+    ref = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.26, gam, z, want_G=False)
+    # device log/sincos/sqrt differ from glibc by <= 2 ulp: far inside 1e-10
+    assert relerr_vec(got["SigmaSqSamples"], ref["SigmaSqSamples"]) < TOL
+    assert relerr_mat(got["LambdaSamples"], ref["LambdaSamples"]) < TOL
+    # a draw is a pure function of (seed, m, j): an offset call reproduces the tail
+    got2 = fb.CPPFABLESampler(Y, 1.0, 1.0, 10, u, v, d, k, 1.26, ctx=ctx, m0=30, want_G=False)
+    np.testing.assert_array_equal(got2["SigmaSqSamples"], got["SigmaSqSamples"][30:])
+    np.testing.assert_array_equal(got2["LambdaSamples"], got["LambdaSamples"][30:])
+    ctx.set_seed(12345)
+
+
+def test_native_moments_within_monte_carlo_error(ctx):
+    n, p, k, MC = 100, 64, 3, 20000
+    Y, u, d, v = _svd_inputs(n, p, k, 21)
+    out = fb.CPPFABLESampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.5, ctx=ctx, psi_moments=True)
+    st = orc._shrunk_stats(Y, u, v, d, k, 1.0, 1.0)
+    a_n = math.sqrt(1.5) / math.sqrt(st["w"])
+    a = 0.5 * st["gamma_n"]
+    Es = st["gnd"] / (st["gamma_n"] - 2)
+    sd_s = np.sqrt((0.5 * st["gnd"]) ** 2 / ((a - 1) ** 2 * (a - 2)) / MC)
+    assert np.all(np.abs(out["SigmaSqSamples"].mean(axis=0) - Es) < 5 * sd_s)
+    L = out["LambdaSamples"].reshape(MC, p, k)
+    assert np.all(np.abs(L.mean(axis=0) - st["G0"]) < 5 * np.sqrt(a_n ** 2 * Es / MC)[:, None])
+    # E[Psi_uv] = G_uv (u != v); E[Psi_uu] = G_uu + (1 + k a_n^2) E[sigma2_u]   
+    G = st["G0"] @ st["G0"].T
+    want = G + np.diag((1 + k * a_n ** 2) * Es)
+    mean = out["PsiSum"] / MC
+    var = out["PsiSumSq"] / MC - mean ** 2
+    assert np.all(np.abs(mean - want) < 6 * np.sqrt(var / MC) + 1e-12)
+
+
+# ---- resident posterior object: batches, slots, accumulators ---------------------------------------
+def test_posterior_batches_accumulate_like_one_pass(ctx, c1):
+    import torch
+    Y, u, d, v = c1["Y"], c1["u"], c1["d"], c1["v"]
+    k, p = 10, Y.shape[1]
+    post = fb.Posterior(Y, 1.0, 1.0, u, v, d, k, 1.26, ctx=ctx)
+    st = post.get()
+    ref = orc._shrunk_stats(Y, u, v, d, k, 1.0, 1.0)
+    assert relerr_mat(st["G0"], ref["G0"]) < TOL and relerr_vec(st["gnd"], ref["gnd"]) < TOL
+    assert abs(st["tausq"] / ref["tausq"] - 1) < TOL
+    MC = 24
+    slots = 3
+    psi = torch.empty((slots, p, p), dtype=torch.float64, device="cuda")
+    for m0, B in ((0, 5), (5, 16), (21, 3)):          # ragged batches
+        post.draw_batch(m0, B, dev_psi=psi.data_ptr(), psi_slots=slots, accumulate=True)
+    ctx.synchronize()
+    s1, s2 = post.accum_fetch()
+    L, S = post.samples(0, MC)
+    r1, r2 = c_oracle.psi_moments(L, S, k)
+    assert relerr_mat(s1, r1) < TOL and relerr_mat(s2, r2) < TOL
+    # the last batch (m0=21, B=3) left draws 21, 22, 23 in slots 0, 1, 2
+    for b in range(3):
+        want = c_oracle.psi_draw(L, S, k, 21 + b)
+        got = psi[b].cpu().numpy().T       # column-major p x p on the device
+        assert relerr_mat(got, want) < TOL
+        assert np.array_equal(got, got.T)
+    post.accum_reset()
+    post.draw_batch(0, MC, accumulate=True)
+    t1, t2 = post.accum_fetch()
+    assert relerr_mat(t1, s1) < 1e-13 and relerr_mat(t2, s2) < 1e-13
+    post.close()
+
+
+@pytest.mark.parametrize("p,k", [(1, 1), (63, 1), (64, 2), (65, 3), (130, 13), (200, 20), (257, 33)])
+def test_rankk_cov_ragged_shapes(ctx, p, k):
+    """dense A A' + diag(s) (G = G0 G0', CovPostMean) at tile-edge sizes and ranks above one chunk."""
+    import torch
+    rng = np.random.default_rng(p * 100 + k)
+    A = np.asfortranarray(rng.standard_normal((p, k))); s = rng.uniform(0.5, 2, p)
+    dA = torch.from_numpy(A.T.copy()).cuda()          # (k, p) row-major == p x k column-major
+    ds = torch.from_numpy(s).cuda()
+    out = torch.empty((p, p), dtype=torch.float64, device="cuda")
+    fb.api.dev_rankk_cov(ctx, dA.data_ptr(), p, ds.data_ptr(), p, k, out.data_ptr())
+    ctx.synchronize()
+    want = A @ A.T + np.diag(s)
+    assert relerr_mat(out.cpu().numpy().T, want) < 1e-13
+
+
+# ---- DMMA GEMM + eigensolver primitives -------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (127, 129, 17), (128, 128, 16), (300, 200, 1000), (64, 1000, 33)])
+@pytest.mark.parametrize("akf,bkf", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_dmma_gemm(ctx, M, N, K, akf, bkf):
+    import torch
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)); B = rng.standard_normal((N, K))
+    # K-slow = column-major M x K (torch (K, M) row-major); K-fast = torch (M, K) row-major
+    dA = torch.from_numpy(A.copy() if akf else A.T.copy()).cuda()
+    dB = torch.from_numpy(B.copy() if bkf else B.T.copy()).cuda()
+    dC = torch.empty((N, M), dtype=torch.float64, device="cuda")
+    fb.api.dev_gemm(ctx, akf, bkf, M, N, K, 0.5, dA.data_ptr(), K if akf else M, dB.data_ptr(), K if bkf else N,
+                    dC.data_ptr(), M)
+    ctx.synchronize()
+    assert relerr_mat(dC.cpu().numpy().T, 0.5 * A @ B.T) < 1e-13
+
+
+@pytest.mark.parametrize("m", [1, 2, 7, 64, 301])
+def test_jacobi_eigensolver(ctx, m):
+    import torch
+    rng = np.random.default_rng(m)
+    X = rng.standard_normal((m, m + 5))
+    G = X @ X.T
+    dG = torch.from_numpy(G.copy()).cuda()
+    dW = torch.empty(m, dtype=torch.float64, device="cuda"); dQ = torch.empty((m, m), dtype=torch.float64, device="cuda")
+    sweeps = fb.api.dev_syevj(ctx, dG.data_ptr(), m, dW.data_ptr(), dQ.data_ptr())
+    w = dW.cpu().numpy(); Q = dQ.cpu().numpy().T
+    assert sweeps <= 30
+    assert relerr_vec(w, np.linalg.eigvalsh(G)[::-1]) < 1e-11
+    assert relerr_mat(Q @ np.diag(w) @ Q.T, G) < 1e-12
+    assert relerr_mat(Q.T @ Q, np.eye(m)) < 1e-12
+
+
+# ---- error behaviour (reference: Armadillo bounds errors surface as R errors, §8b) ------------------
+def test_errors_are_status_codes_not_crashes(ctx, golden):
+    Y, u, d, v = golden["a_Y"], golden["a_u"], golden["a_d"], golden["a_v"]
+    with pytest.raises(fb.FableError) as ei:
+        fb.CPPCriterionFunction(0, Y, u, v, d, ctx=ctx)                       # cols(0, -1)
+    assert ei.value.code == 1
+    with pytest.raises(fb.FableError):
+        fb.CPPCriterionFunction(d.size + 1, Y, u, v, d, ctx=ctx)
+    with pytest.raises(fb.FableError):
+        fb.CPPRankEstimator(Y, u, v, d, d.size + 1, ctx=ctx)
+    with pytest.raises(fb.FableError):
+        fb.CPPFABLESampler(Y, 1.0, 1.0, 0, u, v, d, 2, 1.0, ctx=ctx)
+    with pytest.raises(fb.FableError):
+        fb.CPPFABLESampler(Y, 1.0, 1.0, 3, u, v, d, 2, 1.0, ctx=ctx, gam=np.ones((3, Y.shape[1])))
+    # the context stays usable after an error
+    assert fb.CPPRankEstimator(Y, u, v, d, int(golden["a_kMax50"]), ctx=ctx) == int(golden["a_kEst50"])
+
+
+# ---- full-size properties (BASELINE.json configs[1]: n=1000, p=5000, k=10) ---------------------------
+def test_c2_full_size_properties(ctx):
+    import torch
+    n, p, k = 1000, 5000, 10
+    Y = synth.factor_data(n, p, k, rep=0)
+    s = fb.svd(Y, ctx=ctx)
+    # Frobenius identity: sum d^2 == ||Y||_F^2; orthogonality of the leading block
+    assert abs(np.sum(s["d"] ** 2) / np.sum(Y * Y) - 1) < 1e-12
+    assert relerr_mat(s["u"][:, :50].T @ s["u"][:, :50], np.eye(50)) < 1e-10
+    kMax = fb.kmax_rule(s["d"], 0.5)
+    assert fb.CPPRankEstimator(Y, s["u"], s["v"], s["d"], kMax, ctx=ctx) == 10
+    pm = fb.CPPFABLEPostMean(Y, 1.0, 1.0, s["u"], s["v"], s["d"], kMax, ctx=ctx, internals=True)
+    C = pm["CovPostMean"]
+    assert np.array_equal(C, C.T)
+    # rank-k structure: CovPostMean - diag(SigmaHat) == G0 G0' on a random sample of entries
+    rng = np.random.default_rng(0)
+    iu = rng.integers(0, p, 2000); iv = rng.integers(0, p, 2000)
+    want = np.einsum("il,il->i", pm["G0"][iu], pm["G0"][iv]) + np.where(iu == iv, pm["SigmaHat"][iu], 0.0)
+    assert np.max(np.abs(C[iu, iv] - want)) < 1e-12 * np.max(np.abs(want))
+    # linearity of the accumulators: sum over two disjoint draw ranges == sum over the union
+    post = fb.Posterior(Y, 1.0, 1.0, s["u"], s["v"], s["d"], 10, 1.26, ctx=ctx)
+    post.draw_batch(0, 8, accumulate=True); a1, a2 = post.accum_fetch()
+    post.accum_reset(); post.draw_batch(0, 3, accumulate=True); post.draw_batch(3, 5, accumulate=True)
+    b1, b2 = post.accum_fetch()
+    assert relerr_mat(b1, a1) < 1e-13 and relerr_mat(b2, a2) < 1e-13
+    # a materialised draw equals Lambda_m Lambda_m' + diag(sigma2_m) rebuilt from the returned samples
+    psi = torch.empty((1, p, p), dtype=torch.float64, device="cuda")
+    post.draw_batch(5, 1, dev_psi=psi.data_ptr(), psi_slots=1, accumulate=False)
+    ctx.synchronize()
+    L, S = post.samples(5, 1)
+    Lm = L[0].reshape(p, k)
+    want = Lm @ Lm.T + np.diag(S[0])
+    assert relerr_mat(psi[0].cpu().numpy().T, want) < 1e-12
+    post.close()

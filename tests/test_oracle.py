@@ -1,0 +1,260 @@
+"""CPU tests of the oracle (oracle/): frozen golden fixtures, analytic known answers
+(SURVEY.md App. A.6), control-flow replay of the bisection (reference
+src/updated-FABLE-functions.cpp:215-341), and the C twin against the numpy restatement.
+
+The reference ships no tests or golden vectors and cannot be built in this image, so these pin
+the oracle against drift and against implementation-independent identities ("parity unpinned"
+with respect to the R package itself -- see oracle/fable_oracle.py header).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import fable_oracle as orc
+from oracle import c_oracle
+from fable_b200 import synth
+from conftest import relerr_mat, relerr_vec, TOL
+
+CASES = ["a", "b", "c"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_golden(golden, name):
+    g = lambda key: golden[f"{name}_{key}"]
+    Y, u, d, v = g("Y"), g("u"), g("d"), g("v")
+    assert orc.kmax_rule(d, 0.5) == int(g("kMax50"))
+    assert orc.kmax_rule(d, 0.95) == int(g("kMax95"))
+    kMax95 = int(g("kMax95"))
+    crit = np.array([orc.criterion(k, Y, u, v, d) for k in range(1, kMax95 + 1)])
+    assert relerr_vec(crit, g("crit")) < 1e-13
+    assert orc.rank_estimator(Y, u, v, d, int(g("kMax50"))) == int(g("kEst50"))
+    kEst = orc.rank_estimator(Y, u, v, d, kMax95)
+    assert kEst == int(g("kEst95"))
+    hyp = orc.hyper_parameters(Y, u, v, d, kEst)
+    assert relerr_vec(hyp["SigmaSqEstimate"], g("hyp_sig")) < 1e-13
+    assert relerr_mat(hyp["G"], g("hyp_G")) < 1e-13
+    Bu = orc.cpp_cov_correct_matrix(hyp["SigmaSqEstimate"], hyp["G"])
+    assert relerr_vec(Bu, g("Bupper")) < 1e-13
+    pm = orc.post_mean(Y, 1.0, 1.0, u, v, d, int(g("kMax50")))
+    assert relerr_mat(pm["CovPostMean"], g("pm_cov")) < 1e-13
+    smp = orc.sampler(Y, 1.0, 1.0, 7, u, v, d, kEst, float(g("vi_wrapper")), g("gam"), g("z"))
+    assert relerr_mat(smp["LambdaSamples"], g("smp_L")) < 1e-13
+    assert relerr_vec(smp["SigmaSqSamples"], g("smp_S")) < 1e-13
+
+
+def test_golden_svd_is_a_decomposition_of_Y(golden):
+    for name in CASES:
+        Y, u, d, v = (golden[f"{name}_{key}"] for key in ("Y", "u", "d", "v"))
+        assert relerr_mat((u * d) @ v.T, Y) < 1e-12
+        assert np.all(np.diff(d) <= 0)
+        r = d.size
+        assert relerr_mat(u.T @ u, np.eye(r)) < 1e-12 and relerr_mat(v.T @ v, np.eye(r)) < 1e-12
+
+
+# ---- analytic known answers (independent of any implementation) ---------------------------------
+def _orthogonal_design(n=8, p=5, k=2):
+    """Y = U0 diag(d0) V0' + noise orthogonal to U0, with hand-computable c, q, s."""
+    rng = np.random.Generator(np.random.Philox(11))
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    W, _ = np.linalg.qr(rng.standard_normal((p, p)))
+    dfull = np.array([9.0, 6.0, 1.0, 0.7, 0.4])
+    Y = (Q[:, :p] * dfull) @ W.T
+    return Y, Q[:, :p], W, dfull
+
+
+def test_row_stats_known_answer():
+    Y, U, V, d = _orthogonal_design()
+    n, p = Y.shape
+    k = 2
+    c, q, s, sig, tausq = orc.row_stats(Y, U, V, d, k)
+    assert relerr_mat(c, V[:, :k] * d[:k]) == 0.0
+    # consistent SVD: the explicit residual equals the tail of the spectrum row by row
+    tail = ((V[:, k:] * d[k:]) ** 2).sum(axis=1)
+    assert relerr_vec(sig, tail / n) < 1e-12
+    assert relerr_vec(s, q + tail) < 1e-12
+    assert abs(tausq - np.mean(q / (tail / n)) / (n * k)) < 1e-15 * tausq * 10
+
+
+def test_criterion_formula_known_answer():
+    Y, U, V, d = _orthogonal_design()
+    n, p = Y.shape
+    for k in (1, 2, 3):
+        tail = ((V[:, k:] * d[k:]) ** 2).sum(axis=1) / n
+        want = n * p + n * np.sum(np.log(tail)) + k * max(n, p) * math.log(min(n, p))
+        assert abs(orc.criterion(k, Y, U, V, d) - want) < 1e-10 * abs(want)
+
+
+def test_post_mean_diagonal_quirk_Q4():
+    Y = synth.factor_data(50, 30, 2, rep=3)
+    u, d, v = orc.svd_thin(Y)
+    pm = orc.post_mean(Y, 1.0, 1.0, u, v, d, 5)
+    G = pm["G0"] @ pm["G0"].T
+    assert relerr_mat(pm["CovPostMean"] - G, np.diag(pm["SigmaHat"])) < 1e-12   # cpp:509-512
+
+
+def test_hyper_is_unshrunk_postmean_is_shrunk_Q3():
+    Y = synth.factor_data(50, 30, 2, rep=4)
+    u, d, v = orc.svd_thin(Y)
+    n = Y.shape[0]
+    hyp = orc.hyper_parameters(Y, u, v, d, 2)
+    assert relerr_mat(hyp["G0"], (v[:, :2] * d[:2]) / math.sqrt(n)) < 1e-15       # cpp:390
+    st = orc._shrunk_stats(Y, u, v, d, 2, 1.0, 1.0)
+    assert relerr_mat(st["G0"], math.sqrt(n) / (n + 1 / st["tausq"]) * (v[:, :2] * d[:2])) < 1e-15   # cpp:490
+
+
+def test_sampler_moments_known_answer():
+    """E[sigma2_j] = gnd_j/(gamma_n-2); Var[Lambda_jl] = a_n^2 E[sigma2_j]  (SURVEY A.6)."""
+    n, p, k, MC = 30, 12, 2, 40000
+    Y = synth.factor_data(n, p, k, rep=6)
+    u, d, v = orc.svd_thin(Y)
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=5)
+    o = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.7, gam, z, want_G=False)
+    S = o["SigmaSqSamples"]
+    a = 0.5 * o["gamma_n"]
+    want_mean = o["gnd"] / (o["gamma_n"] - 2.0)
+    assert relerr_vec(o["SigmaSqEstimatePostMean"], want_mean) < 1e-15
+    sd = np.sqrt((0.5 * o["gnd"]) ** 2 / ((a - 1) ** 2 * (a - 2)) / MC)
+    assert np.all(np.abs(S.mean(axis=0) - want_mean) < 5 * sd)
+    L = o["LambdaSamples"].reshape(MC, p, k)
+    assert np.all(np.abs(L.mean(axis=0) - o["G0"]) < 5 * np.sqrt(o["a_n"] ** 2 * want_mean / MC)[:, None])
+    var = L.var(axis=0)
+    assert np.all(np.abs(var / (o["a_n"] ** 2 * want_mean)[:, None] - 1.0) < 0.08)
+
+
+def test_sampler_layout_matches_reference_indexing():
+    """LambdaSamples(m, j*k + l) = Lambda_m[j, l]  (cpp:616: vectorise(LambdaSample.t()).t())."""
+    n, p, k, MC = 20, 7, 3, 4
+    Y = synth.factor_data(n, p, k, rep=7)
+    u, d, v = orc.svd_thin(Y)
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=9)
+    o = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.0, gam, z, want_G=False)
+    for m in range(MC):
+        s2 = 0.5 * o["gnd"] / gam[m]
+        Lam = o["G0"] + o["a_n"] * (z[m].T * np.sqrt(s2)[:, None])        # p x k, cpp:613-615
+        np.testing.assert_allclose(o["LambdaSamples"][m], Lam.reshape(-1), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(o["SigmaSqSamples"][m], s2, rtol=1e-15)
+
+
+# ---- bisection control flow (cpp:215-271, 314-337) ------------------------------------------------
+def _bisect_ref_recursive(lower, upper, f):
+    if upper - lower > 5:
+        mid = (lower + upper) // 2
+        if f(lower) < f(mid):
+            return _bisect_ref_recursive(lower, mid, f)
+        tq = (mid + upper) // 2
+        if f(mid) <= f(tq):
+            return _bisect_ref_recursive(lower, mid, f)
+        return _bisect_ref_recursive(mid, upper, f)
+    return lower, upper
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_bisection_iterative_equals_recursive(seed):
+    rng = np.random.default_rng(seed)
+    kMax = int(rng.integers(6, 400))
+    kstar = int(rng.integers(1, kMax + 1))
+    vals = {k: (k - kstar) ** 2 + 3.0 * rng.standard_normal() for k in range(1, kMax + 1)}
+    f = lambda k: vals[k]
+    assert orc.bisection(1, kMax, f) == _bisect_ref_recursive(1, kMax, f)
+
+
+def test_bisection_window_edges_and_ties():
+    assert orc.bisection(1, 6, lambda k: 0.0) == (1, 6)          # width 5: no shrink (cpp:223)
+    assert orc.bisection(1, 7, lambda k: 0.0) == (1, 4)          # tie: mid <= tq -> [lower, mid] (cpp:249)
+    assert orc.bisection(1, 100, lambda k: float(k)) == (1, 4)   # increasing: always left
+    lo, hi = orc.bisection(1, 100, lambda k: -float(k))          # decreasing: always right
+    assert hi == 100 and hi - lo <= 5
+
+
+def test_rank_first_minimum_wins():
+    Y = synth.factor_data(40, 60, 3, rep=8)
+    u, d, v = orc.svd_thin(Y)
+    trace = []
+    k = orc.rank_estimator(Y, u, v, d, 20, trace)
+    win = [(kk, val) for tag, kk, val in trace if tag == "win"]
+    assert k == min(win, key=lambda t: (t[1], t[0]))[0]
+
+
+# ---- cov-correct --------------------------------------------------------------------------------
+def test_cov_correct_forms_agree():
+    rng = np.random.default_rng(0)
+    p, k = 9, 2
+    G0 = rng.standard_normal((p, k)); sig = rng.uniform(0.5, 2.0, p)
+    G = G0 @ G0.T
+    B = orc.cov_correct_matrix_R(sig, G)
+    Bu = orc.cpp_cov_correct_matrix(sig, G)
+    iu = np.triu_indices(p)
+    # trimatu_ind is column-major: sort the (row, col) pairs by column then row
+    order = np.lexsort((iu[0], iu[1]))
+    np.testing.assert_array_equal(Bu, B[iu[0][order], iu[1][order]])
+    assert abs(B[0, 0] - math.sqrt(1 + G[0, 0] / (2 * sig[0]))) < 1e-15           # SURVEY a7 diagonal
+    assert B[1, 2] == pytest.approx(math.sqrt(1 + (G[1, 1] * G[2, 2] + G[1, 2] ** 2) / (G[1, 1] * sig[2] + sig[1] * G[2, 2])), rel=1e-15)
+    # D5: the two varInflation formulas differ (wrapper sums the FULL matrix)
+    assert orc.var_inflation_wrapper(B) > 3.0 * orc.var_inflation_script(Bu)
+
+
+# ---- quantile / post-processing -------------------------------------------------------------------
+def test_arma_quantile_definition5():
+    x = np.array([3.0, 1.0, 2.0, 4.0])
+    assert orc.arma_quantile(x, 0.5) == 2.5
+    assert orc.arma_quantile(x, 0.0) == 1.0 and orc.arma_quantile(x, 1.0) == 4.0
+    assert orc.arma_quantile(x, 0.125) == 1.0 and orc.arma_quantile(x, 0.25) == 1.5
+    for pr in (0.03, 0.2, 0.5, 0.77, 0.975):
+        y = np.random.default_rng(1).standard_normal(101)
+        assert orc.arma_quantile(y, pr) == pytest.approx(np.quantile(y, pr, method="hazen"), rel=1e-13)
+
+
+def test_post_processing_mean_matches_moments():
+    n, p, k, MC = 25, 6, 2, 11
+    Y = synth.factor_data(n, p, k, rep=9)
+    u, d, v = orc.svd_thin(Y)
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=3)
+    o = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.2, gam, z)
+    pp = orc.post_processing(o, 0.05)
+    s1, s2 = orc.psi_moments(o["LambdaSamples"], o["SigmaSqSamples"], k)
+    assert relerr_mat(pp["PostMeanMatrix"], s1 / MC) < 1e-13
+    assert np.all(pp["LowerQuantileMatrix"] <= pp["UpperQuantileMatrix"])
+    sub = orc.post_processing_submatrix(o, 0.05, [2, 5])
+    assert relerr_mat(sub["PostMeanMatrix"], pp["PostMeanMatrix"][np.ix_([1, 4], [1, 4])]) < 1e-14
+
+
+# ---- C twin ---------------------------------------------------------------------------------------
+def test_c_twin_matches_numpy_oracle(golden):
+    g = lambda key: golden[f"a_{key}"]
+    Y, u, d, v = g("Y"), g("u"), g("d"), g("v")
+    k = int(g("kEst95"))
+    assert relerr_vec(c_oracle.resid_sigsq(Y, u, v, d, k), orc._residual_sigsq(Y, u, v, d, k)) < 1e-12
+    st = orc._shrunk_stats(Y, u, v, d, k, 1.0, 1.0)
+    a_n = math.sqrt(float(g("vi_wrapper"))) / math.sqrt(st["w"])
+    L, S = c_oracle.sampler(7, Y.shape[1], k, st["G0"], st["gnd"], a_n, g("gam"), g("z"))
+    assert relerr_mat(L, g("smp_L")) < 1e-14 and relerr_vec(S, g("smp_S")) < 1e-14
+    s1, s2 = c_oracle.psi_moments(L, S, k)
+    assert relerr_mat(s1, g("psi_sum")) < 1e-13 and relerr_mat(s2, g("psi_sumsq")) < 1e-13
+    assert relerr_mat(c_oracle.psi_draw(L, S, k, 3), orc.psi_draw(g("smp_L")[3], g("smp_S")[3], k)) < 1e-14
+    sf, su = c_oracle.cov_correct_sums(g("hyp_sig"), g("hyp_G"))
+    p = Y.shape[1]
+    assert ((sf / (p * (p + 1) / 2)) ** 2) == pytest.approx(float(g("vi_wrapper")), rel=1e-12)
+    assert ((su / (p * (p + 1) / 2)) ** 2) == pytest.approx(float(g("vi_script")), rel=1e-12)
+
+
+# ---- fable-philox-v1 (the library's own RNG specification; CPU statement in the C twin) -----------
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    assert c_oracle.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert c_oracle.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert c_oracle.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_native_stream_moments_and_batch_invariance():
+    MC, p, k, shape = 4000, 16, 3, 15.5
+    gam, z = c_oracle.rng_fill(42, 0, MC, p, k, shape)
+    assert abs(gam.mean() - shape) < 5 * math.sqrt(shape / gam.size)
+    assert abs(gam.var() / shape - 1.0) < 0.05
+    assert abs(z.mean()) < 5 / math.sqrt(z.size) and abs(z.var() - 1.0) < 0.02
+    # a draw is a pure function of (seed, m, j, slot): any sub-range reproduces the same values
+    g2, z2 = c_oracle.rng_fill(42, 1000, 50, p, k, shape)
+    np.testing.assert_array_equal(g2, gam[1000:1050]); np.testing.assert_array_equal(z2, z[1000:1050])
+    g3, _ = c_oracle.rng_fill(43, 0, 10, p, k, shape, want_z=False)
+    assert not np.array_equal(g3, gam[:10])
