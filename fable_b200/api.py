@@ -113,6 +113,20 @@ class Context:
     def synchronize(self):
         self.check(_load().fable_ctx_synchronize(self._h))
 
+    def kernel_timing(self, enable=True):
+        """Start (and clear) / stop per-launch CUDA-event timing of the covariance kernel."""
+        self.check(_load().fable_ctx_kernel_timing(self._h, C.c_int(1 if enable else 0)))
+
+    def kernel_time(self):
+        """(summed device milliseconds, launches) of the covariance kernel since kernel_timing(True)."""
+        ms = C.c_double(); cnt = C.c_int64()
+        self.check(_load().fable_ctx_kernel_time(self._h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    def set_psi_ring(self, slots):
+        """slots > 0: the sampler's Psi pass also materialises every draw into a device ring."""
+        self.check(_load().fable_ctx_set_psi_ring(self._h, C.c_int(int(slots))))
+
 
 _default_ctx = None
 
@@ -281,7 +295,7 @@ def CPPFABLEPostMean(Y, gamma0, delta0sq, U_Y, V_Y, svalsY, kMax, ctx=None, want
 # a9
 # ------------------------------------------------------------------------------------------------
 def CPPFABLESampler(Y, gamma0, delta0sq, MC, U_Y, V_Y, svalsY, kEst, varInflation, ctx=None, gam=None, z=None,
-                    m0=0, want_G=True, want_samples=True, psi_moments=False):
+                    m0=0, want_G=True, want_samples=True, psi_moments=False, out=None):
     """Element names as cpp:620-627.  `gam`/`z`: injected draws (gam[m, j]; z[m, l, j]); default is
     the native Philox stream.  `psi_moments=True` adds PsiSum / PsiSumSq (entry-wise sums over the
     draws of Psi_m = Lambda_m Lambda_m' + diag(sigma2_m))."""
@@ -298,12 +312,23 @@ def CPPFABLESampler(Y, gamma0, delta0sq, MC, U_Y, V_Y, svalsY, kEst, varInflatio
             raise FableError(1, "injected draws need both gam and z")
         g = np.ascontiguousarray(gam, dtype=np.float64).reshape(MC, p)
         zz = np.ascontiguousarray(z, dtype=np.float64).reshape(MC, k, p)
-    L = np.empty((MC, k * p), order="F") if want_samples else None
-    S = np.empty((MC, p), order="F") if want_samples else None
-    pm = np.empty(p); pi = np.empty(p); tau = C.c_double()
-    G = np.empty((p, p), order="F") if want_G else None
-    s1 = np.empty((p, p), order="F") if psi_moments else None
-    s2 = np.empty((p, p), order="F") if psi_moments else None
+    out = out or {}
+
+    def _buf(name, shape, want):
+        if not want:
+            return None
+        a = out.get(name)
+        if a is None:
+            return np.empty(shape, order="F")
+        if a.shape != tuple(np.atleast_1d(shape)) or a.dtype != np.float64 or not (a.flags.f_contiguous or a.ndim == 1):
+            raise FableError(1, f"out[{name!r}] must be a column-major float64 array of shape {shape}")
+        return a
+    L = _buf("LambdaSamples", (MC, k * p), want_samples)
+    S = _buf("SigmaSqSamples", (MC, p), want_samples)
+    pm = _buf("SigmaSqEstimatePostMean", (p,), True); pi = _buf("SigmaSqEstimatePlugIn", (p,), True); tau = C.c_double()
+    G = _buf("G", (p, p), want_G)
+    s1 = _buf("PsiSum", (p, p), psi_moments)
+    s2 = _buf("PsiSumSq", (p, p), psi_moments)
     ctx.check(_load().fable_sampler(ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq),
                                     _i64(MC), _ptr(U), _ptr(V), _ptr(d), _i64(r), C.c_int(k),
                                     C.c_double(varInflation), _ptr(g), _ptr(zz), _i64(m0), _ptr(L), _ptr(S),
