@@ -672,10 +672,20 @@ int fable_dev_rankk_cov(fable_ctx* ctx, const double* dA, int64_t lda, const dou
   if (!ctx) return FABLE_ERR_INVALID;
   FB_REQUIRE(ctx, dA && dOut && p >= 1 && k >= 1 && lda >= p, "rankk_cov: bad arguments");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
-  PsiArgs a;
-  a.Lw = dA; a.s2w = ds; a.pp = lda; a.p = p; a.k = k; a.KP = k; a.B = 1;
-  a.psi = dOut; a.psi_slots = 1; a.slot0 = 0; a.acc_sum = nullptr; a.acc_sq = nullptr;
-  return fb_psi(ctx, a);
+  // the covariance kernel reads its operand through 16-byte cp.async from rows zero-padded to a
+  // multiple of 64: stage a padded copy (p x k doubles, negligible next to the p x p output)
+  const int64_t pp = round_up(p, 64);
+  double* padded = nullptr;
+  FB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&padded), static_cast<size_t>(pp) * k * sizeof(double), ctx->stream));
+  int rc = fb_pad_rows(ctx, dA, lda, p, pp, k, padded);
+  if (rc == FABLE_OK) {
+    PsiArgs a;
+    a.Lw = padded; a.s2w = ds; a.pp = pp; a.p = p; a.k = k; a.KP = k; a.B = 1;
+    a.psi = dOut; a.psi_slots = 1; a.slot0 = 0; a.acc_sum = nullptr; a.acc_sq = nullptr;
+    rc = fb_psi(ctx, a);
+  }
+  cudaFreeAsync(padded, ctx->stream);
+  return rc;
 }
 
 int fable_dev_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K, double alpha,

@@ -140,6 +140,8 @@ struct PsiArgs {
 };
 int fb_psi(fable_ctx* ctx, const PsiArgs& a);
 int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p);
+// dst (k rows of pp, zero-padded) <- src (k rows of lds, p valid)
+int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, double* dst);
 // sampler.cu
 struct SampleArgs {
   const double* G0;    // p x k shrunk loadings mean, leading dimension ldg

@@ -8,21 +8,28 @@
 // CovPostMean = G + diag(.) (:512).
 //
 // Roofline: k is small (10-20), so each 8-byte output costs only 2k flops: the kernel is bound by
-// HBM WRITE bandwidth (8 p^2 bytes per draw).  Only upper-triangle tiles are computed (halves the
-// FP64 work to ~25% of the DFMA pipe at full write bandwidth); the mirrored tile is transposed
-// through shared memory so that BOTH stores are full 256-byte coalesced runs, written once with
-// streaming (evict-first) stores.
-//
+// HBM WRITE bandwidth (8 p^2 bytes per draw).  Design for that bound:
+//   * only upper-triangle 64 x 64 tiles are computed (FP64 work ~25% of the DFMA pipe at full write
+//     bandwidth); one CTA owns a tile for the whole batch, so the sum / sumsq accumulators live in
+//     registers across the draw loop (one read-modify-write of the HBM accumulators per batch);
+//   * the rank-k operand rows of draw b+1 are prefetched with cp.async (LDGSTS) into a second
+//     shared-memory buffer while draw b is computed;
+//   * a finished tile is staged in shared memory in BOTH orientations (direct [v][u] and mirrored
+//     [u][v], padded row stride 66 so the transposed 16-byte stores are conflict-free) and leaves
+//     the SM as 128 asynchronous 512-byte bulk stores (cp.async.bulk.global.shared::cta -> UBLKCP),
+//     so HBM writes drain while the warps already compute the next draw; every global run is a
+//     full, aligned 512-byte line group written exactly once.
 // Tile = 64 x 64, 256 threads: lane -> row u (two rows, u = lane + 32*iu), warp -> 8 columns v.
-// Accumulators for the batch stay in registers across the draw loop (one read-modify-write of the
-// HBM accumulators per batch: 16*S*p^2/(2B) bytes per draw, upper tiles only).
 #include "common.cuh"
 
 namespace {
 
 constexpr int TILE = 64;
-constexpr int KC = 12;            // rank chunk staged in shared memory (static smem < 48 KB)
-constexpr int TSTRIDE = TILE + 1; // odd stride: conflict-free transposed 8-byte accesses
+constexpr int KC = 16;             // rank chunk per pipeline step
+constexpr int MSTR = TILE + 2;     // mirrored staging row stride (doubles): 66 = 2 mod 16 -> conflict-free STS.128
+constexpr int OP_DOUBLES = 2 * 2 * KC * TILE;                      // [buf][operand][l][row]
+constexpr size_t OP_BYTES = OP_DOUBLES * sizeof(double);           // 32 KB
+constexpr size_t STAGE_BYTES = (TILE * TILE + TILE * MSTR) * sizeof(double);   // 32 KB + 33 KB
 
 __device__ __forceinline__ void tile_of(int64_t t, int& I, int& J) {
   // column-major enumeration of the upper triangle: t = J(J+1)/2 + I, 0 <= I <= J
@@ -33,19 +40,56 @@ __device__ __forceinline__ void tile_of(int64_t t, int& I, int& J) {
   I = static_cast<int>(t - j * (j + 1) / 2);
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Lw must be zero-padded to pp rows (pp a multiple of TILE) and 16-byte aligned.
 template <bool MAT, bool ACC>
-__global__ void __launch_bounds__(256, ACC ? 2 : 3)
+__global__ void __launch_bounds__(256, 2)
 k_psi(PsiArgs a, int64_t tile_begin) {
-  __shared__ double As[KC][TILE];
-  __shared__ double Bs[KC][TILE];
-  __shared__ double T[MAT ? TILE * TSTRIDE : 1];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* op = reinterpret_cast<double*>(smem_raw);
+  double* D = reinterpret_cast<double*>(smem_raw + OP_BYTES);   // direct  [v][u], stride TILE
+  double* M = D + TILE * TILE;                                  // mirrored [u][v], stride MSTR
 
   int I, J;
   tile_of(tile_begin + blockIdx.x, I, J);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t u0 = static_cast<int64_t>(I) * TILE, v0 = static_cast<int64_t>(J) * TILE;
   const int64_t p = a.p;
   const bool diag = (I == J);
+  const bool bulk = MAT && ((p & 1) == 0);       // 16-byte aligned runs of even length
+  const uint32_t run_u = static_cast<uint32_t>((p - u0 < TILE ? p - u0 : TILE) * 8);   // bytes of one direct run
+  const uint32_t run_v = static_cast<uint32_t>((p - v0 < TILE ? p - v0 : TILE) * 8);   // bytes of one mirrored run
+  const int nch = (a.k + KC - 1) / KC;
+  const int nsteps = a.B * nch;
+
+  auto prefetch = [&](int s, int buf) {
+    const int b = s / nch, l0 = (s - b * nch) * KC;
+    const int kc = min(KC, a.k - l0);
+    const double* base = a.Lw + (static_cast<int64_t>(b) * a.KP + l0) * a.pp;
+    double* dst = op + buf * (2 * KC * TILE);
+    for (int idx = tid; idx < 2 * kc * (TILE / 2); idx += 256) {
+      const int o = idx / (kc * (TILE / 2)), rem = idx - o * kc * (TILE / 2);
+      const int l = rem >> 5, ch = rem & 31;
+      cp_async16(dst + (o * KC + l) * TILE + 2 * ch, base + static_cast<int64_t>(l) * a.pp + (o ? v0 : u0) + 2 * ch);
+    }
+    cp_async_commit();
+  };
 
   double acc_s[2][8], acc_q[2][8];
   if (ACC) {
@@ -54,39 +98,38 @@ k_psi(PsiArgs a, int64_t tile_begin) {
 #pragma unroll
       for (int iv = 0; iv < 8; ++iv) { acc_s[iu][iv] = 0.0; acc_q[iu][iv] = 0.0; }
   }
+  double c[2][8];
+#pragma unroll
+  for (int iu = 0; iu < 2; ++iu)
+#pragma unroll
+    for (int iv = 0; iv < 8; ++iv) c[iu][iv] = 0.0;
 
-  for (int b = 0; b < a.B; ++b) {
-    double c[2][8];
-#pragma unroll
-    for (int iu = 0; iu < 2; ++iu)
-#pragma unroll
-      for (int iv = 0; iv < 8; ++iv) c[iu][iv] = 0.0;
+  prefetch(0, 0);
+  for (int s = 0; s < nsteps; ++s) {
+    const int buf = s & 1;
+    const int b = s / nch, ch = s - b * nch;
+    const int kc = min(KC, a.k - ch * KC);
+    cp_async_wait_all();
+    __syncthreads();                     // operands of step s landed; buffer buf^1 is no longer read
+    if (s + 1 < nsteps) prefetch(s + 1, buf ^ 1);
 
-    const double* Lb = a.Lw + static_cast<int64_t>(b) * a.KP * a.pp;
-    for (int l0 = 0; l0 < a.k; l0 += KC) {
-      const int kc = min(KC, a.k - l0);
-      __syncthreads();  // previous chunk / previous draw's mirror reads are done
-      // stage kc x 64 rows of both operands (coalesced: 64 contiguous doubles per l)
-      for (int idx = threadIdx.x; idx < kc * TILE; idx += 256) {
-        const int l = idx >> 6, r = idx & 63;
-        const double* src = Lb + static_cast<int64_t>(l0 + l) * a.pp;
-        As[l][r] = (u0 + r < p) ? src[u0 + r] : 0.0;
-        Bs[l][r] = (v0 + r < p) ? src[v0 + r] : 0.0;
-      }
-      __syncthreads();
-#pragma unroll 4
-      for (int l = 0; l < kc; ++l) {
-        const double a0 = As[l][lane], a1 = As[l][lane + 32];
-        const double2* bp = reinterpret_cast<const double2*>(&Bs[l][warp * 8]);
-        const double2 b01 = bp[0], b23 = bp[1], b45 = bp[2], b67 = bp[3];
-        const double bv[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
+    const double* As = op + buf * (2 * KC * TILE);
+    const double* Bs = As + KC * TILE;
+#pragma unroll 2
+    for (int l = 0; l < kc; ++l) {
+      const double a0 = As[l * TILE + lane], a1 = As[l * TILE + lane + 32];
+      const double2* bp = reinterpret_cast<const double2*>(Bs + l * TILE + warp * 8);
+      const double2 b01 = bp[0], b23 = bp[1], b45 = bp[2], b67 = bp[3];
+      const double bv[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
 #pragma unroll
-        for (int iv = 0; iv < 8; ++iv) {
-          c[0][iv] = fma(a0, bv[iv], c[0][iv]);
-          c[1][iv] = fma(a1, bv[iv], c[1][iv]);
-        }
+      for (int iv = 0; iv < 8; ++iv) {
+        c[0][iv] = fma(a0, bv[iv], c[0][iv]);
+        c[1][iv] = fma(a1, bv[iv], c[1][iv]);
       }
     }
+    if (ch + 1 < nch) continue;          // more rank chunks of this draw to come
+
+    // ---- draw b of this tile is complete in registers ----------------------------------------
     if (diag && a.s2w) {
 #pragma unroll
       for (int iu = 0; iu < 2; ++iu)
@@ -108,40 +151,51 @@ k_psi(PsiArgs a, int64_t tile_begin) {
     }
     if (MAT) {
       double* out = a.psi + static_cast<int64_t>((a.slot0 + b) % a.psi_slots) * p * p;
-      // direct tile: column v, rows u -- 256-byte coalesced runs
+      if (bulk && tid < 2 * TILE) bulk_wait_read();   // the previous draw's bulk stores have read the staging
+      __syncthreads();
 #pragma unroll
-      for (int iv = 0; iv < 8; ++iv) {
-        const int64_t v = v0 + warp * 8 + iv;
-        if (v < p) {
+      for (int iu = 0; iu < 2; ++iu) {
 #pragma unroll
-          for (int iu = 0; iu < 2; ++iu) {
-            const int64_t u = u0 + lane + 32 * iu;
-            if (u < p) __stcs(out + v * p + u, c[iu][iv]);
-          }
+        for (int iv = 0; iv < 8; ++iv) D[(warp * 8 + iv) * TILE + lane + 32 * iu] = c[iu][iv];
+        if (!diag) {
+          double2* mp = reinterpret_cast<double2*>(M + (lane + 32 * iu) * MSTR + warp * 8);
+          mp[0] = make_double2(c[iu][0], c[iu][1]); mp[1] = make_double2(c[iu][2], c[iu][3]);
+          mp[2] = make_double2(c[iu][4], c[iu][5]); mp[3] = make_double2(c[iu][6], c[iu][7]);
         }
       }
-      if (!diag) {
-        // mirrored tile through shared memory: T[u][v], then columns u, rows v coalesced
-#pragma unroll
-        for (int iu = 0; iu < 2; ++iu)
-#pragma unroll
-          for (int iv = 0; iv < 8; ++iv) T[(lane + 32 * iu) * TSTRIDE + warp * 8 + iv] = c[iu][iv];
+      if (bulk) {
+        fence_async_smem();              // generic-proxy smem writes -> visible to the async (bulk copy) proxy
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int uc = warp * 8 + i;
-          const int64_t u = u0 + uc;
-          if (u < p) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int64_t v = v0 + lane + 32 * h;
-              if (v < p) __stcs(out + u * p + v, T[uc * TSTRIDE + lane + 32 * h]);
-            }
-          }
+        if (tid < TILE) {
+          if (v0 + tid < p)
+            bulk_store(out + (v0 + tid) * p + u0, D + tid * TILE, run_u);
+          bulk_commit();
+        } else if (tid < 2 * TILE) {
+          const int cidx = tid - TILE;
+          if (!diag && u0 + cidx < p)
+            bulk_store(out + (u0 + cidx) * p + v0, M + cidx * MSTR, run_v);
+          bulk_commit();
         }
+      } else {
+        __syncthreads();
+        // odd p: runs are not 16-byte aligned -> plain coalesced stores from the staging
+        for (int cidx = warp; cidx < TILE; cidx += 8) {
+          if (v0 + cidx < p)
+            for (int h = 0; h < 2; ++h)
+              if (u0 + lane + 32 * h < p) __stcs(out + (v0 + cidx) * p + u0 + lane + 32 * h, D[cidx * TILE + lane + 32 * h]);
+          if (!diag && u0 + cidx < p)
+            for (int h = 0; h < 2; ++h)
+              if (v0 + lane + 32 * h < p) __stcs(out + (u0 + cidx) * p + v0 + lane + 32 * h, M[cidx * MSTR + lane + 32 * h]);
+        }
+        __syncthreads();
       }
     }
+#pragma unroll
+    for (int iu = 0; iu < 2; ++iu)
+#pragma unroll
+      for (int iv = 0; iv < 8; ++iv) c[iu][iv] = 0.0;
   }
+  if (bulk && tid < 2 * TILE) bulk_wait_read();       // staging must stay valid until the last stores have read it
 
   if (ACC) {
 #pragma unroll
@@ -179,6 +233,27 @@ __global__ void __launch_bounds__(256) k_mirror_upper(double* __restrict__ A, in
   }
 }
 
+// dst[(l*pp) + j] = j < p ? src[l*lds + j] : 0   (zero-padded, 16-byte aligned operand layout)
+__global__ void __launch_bounds__(256) k_pad_rows(const double* __restrict__ src, int64_t lds, int64_t p, int64_t pp,
+                                                  int k, double* __restrict__ dst) {
+  const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (j >= pp) return;
+  for (int l = 0; l < k; ++l) dst[static_cast<int64_t>(l) * pp + j] = (j < p) ? src[static_cast<int64_t>(l) * lds + j] : 0.0;
+}
+
+template <bool MAT, bool ACC>
+int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned grid, int64_t t0) {
+  constexpr size_t smem = OP_BYTES + (MAT ? STAGE_BYTES : 0);
+  static bool attr = false;
+  if (!attr) {
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = true;
+  }
+  k_psi<MAT, ACC><<<grid, 256, smem, ctx->stream>>>(a, t0);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
 }  // namespace
 
 int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
@@ -187,6 +262,8 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
   const bool mat = a.psi != nullptr, acc = a.acc_sum != nullptr;
   FB_REQUIRE(ctx, mat || acc, "psi: nothing to do");
   FB_REQUIRE(ctx, !mat || a.psi_slots > 0, "psi: psi_slots must be positive");
+  FB_REQUIRE(ctx, a.pp % TILE == 0 && a.pp >= a.p && (reinterpret_cast<uintptr_t>(a.Lw) & 15) == 0,
+             "psi: operand rows must be zero-padded to a multiple of 64 and 16-byte aligned");
   const int64_t nT = ceil_div(a.p, TILE);
   const int64_t tiles = nT * (nT + 1) / 2;
   const int64_t chunk = 1 << 30;
@@ -203,12 +280,17 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
   }
   for (int64_t t0 = 0; t0 < tiles; t0 += chunk) {
     const unsigned g = static_cast<unsigned>(tiles - t0 < chunk ? tiles - t0 : chunk);
-    if (mat && acc) k_psi<true, true><<<g, 256, 0, ctx->stream>>>(a, t0);
-    else if (mat) k_psi<true, false><<<g, 256, 0, ctx->stream>>>(a, t0);
-    else k_psi<false, true><<<g, 256, 0, ctx->stream>>>(a, t0);
-    FB_LAUNCHED(ctx);
+    if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0)));
+    else if (mat) FB_TRY((launch_psi<true, false>(ctx, a, g, t0)));
+    else FB_TRY((launch_psi<false, true>(ctx, a, g, t0)));
   }
   if (ev1) FB_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+  return FABLE_OK;
+}
+
+int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, double* dst) {
+  k_pad_rows<<<static_cast<unsigned>(ceil_div(pp, 256)), 256, 0, ctx->stream>>>(src, lds, p, pp, k, dst);
+  FB_LAUNCHED(ctx);
   return FABLE_OK;
 }
 

@@ -1,0 +1,120 @@
+// store_lab: HBM write bandwidth of the access patterns the covariance kernel can choose from.
+// Pure stores (no arithmetic): a dense symmetric p x p FP64 matrix per "draw", written as square
+// T x T tiles of the upper triangle plus their mirrored tiles, B draws per CTA into a ring of slots.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/bin/store_lab tools/store_lab.cu
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ void tri_of(int64_t t, int& I, int& J) {
+  int64_t j = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while (j * (j + 1) / 2 > t) --j;
+  while ((j + 1) * (j + 2) / 2 <= t) ++j;
+  J = (int)j; I = (int)(t - j * (j + 1) / 2);
+}
+
+// order 0: column-major upper triangle.  order S>0: super-blocks of S x S tiles, the super-blocks
+// enumerated over their own upper triangle, tiles inside row-major; tiles below the diagonal skipped
+// (CTA exits).
+__device__ __forceinline__ bool tile_of(int64_t t, int nT, int S, int& I, int& J) {
+  if (S == 0) { tri_of(t, I, J); return true; }
+  const int64_t per = (int64_t)S * S;
+  int sI, sJ;
+  tri_of(t / per, sI, sJ);
+  const int r = (int)(t % per);
+  I = sI * S + r % S; J = sJ * S + r / S;
+  return I <= J && J < nT;
+}
+
+template <int T, int KIND>
+__global__ void __launch_bounds__(256) k_tiles(double* __restrict__ out, int64_t p, int nT, int S, int B, int slots,
+                                               int mirror) {
+  int I, J;
+  if (!tile_of(blockIdx.x, nT, S, I, J)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t u0 = (int64_t)I * T, v0 = (int64_t)J * T;
+  for (int b = 0; b < B; ++b) {
+    double* o = out + (int64_t)(b % slots) * p * p;
+    const double val = (double)(b + I + J);
+    // direct tile: columns v0..v0+T-1, rows u0.. (runs of T doubles)
+    for (int c = warp; c < T; c += 8) {
+      const int64_t v = v0 + c;
+      if (v >= p) break;
+      for (int r = lane; r < T; r += 32) {
+        const int64_t u = u0 + r;
+        if (u < p) {
+          if (KIND == 0) o[v * p + u] = val;
+          else __stcs(o + v * p + u, val);
+        }
+      }
+    }
+    if (mirror && I != J) {
+      for (int c = warp; c < T; c += 8) {
+        const int64_t u = u0 + c;
+        if (u >= p) break;
+        for (int r = lane; r < T; r += 32) {
+          const int64_t v = v0 + r;
+          if (v < p) {
+            if (KIND == 0) o[u * p + v] = val;
+            else __stcs(o + u * p + v, val);
+          }
+        }
+      }
+    }
+  }
+}
+
+// contiguous reference: grid-stride, one draw = p*p doubles
+__global__ void __launch_bounds__(256) k_contig(double* __restrict__ out, int64_t n, int B, int slots) {
+  for (int b = 0; b < B; ++b) {
+    double* o = out + (int64_t)(b % slots) * n;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) __stcs(o + i, (double)b);
+  }
+}
+
+template <int T, int KIND>
+float run_tiles(double* d, int64_t p, int S, int B, int slots, int mirror) {
+  const int nT = (int)((p + T - 1) / T);
+  int64_t grid;
+  if (S == 0) grid = (int64_t)nT * (nT + 1) / 2;
+  else { const int64_t nS = (nT + S - 1) / S; grid = nS * (nS + 1) / 2 * S * S; }
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_tiles<T, KIND><<<(unsigned)grid, 256>>>(d, p, nT, S, 2, slots, mirror);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  k_tiles<T, KIND><<<(unsigned)grid, 256>>>(d, p, nT, S, B, slots, mirror);
+  CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  return ms;
+}
+
+int main(int argc, char** argv) {
+  const int64_t p = argc > 1 ? atoll(argv[1]) : 20000;
+  const int B = argc > 2 ? atoi(argv[2]) : 8;
+  const int slots = 2;
+  double* d; CK(cudaMalloc(&d, sizeof(double) * p * p * slots));
+  CK(cudaMemset(d, 0, sizeof(double) * p * p * slots));
+  const double gb = 8.0 * p * p * B / 1e9;
+  {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_contig<<<148 * 8, 256>>>(d, p * p, 1, slots); CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0)); k_contig<<<148 * 8, 256>>>(d, p * p, B, slots); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("contig                                  %8.1f GB/s\n", gb / (ms * 1e-3));
+  }
+  const int orders[] = {0, 4, 8, 16};
+  for (int mirror = 0; mirror < 2; ++mirror)
+    for (int S : orders) {
+      // full-matrix bytes when mirror=1; upper triangle only (about half) when mirror=0
+      const double g = mirror ? gb : gb * 0.5;
+      printf("T=64  kind=cs  order=%2d mirror=%d        %8.1f GB/s\n", S, mirror, g / (run_tiles<64, 1>(d, p, S, B, slots, mirror) * 1e-3));
+      printf("T=128 kind=cs  order=%2d mirror=%d        %8.1f GB/s\n", S, mirror, g / (run_tiles<128, 1>(d, p, S, B, slots, mirror) * 1e-3));
+      printf("T=256 kind=cs  order=%2d mirror=%d        %8.1f GB/s\n", S, mirror, g / (run_tiles<256, 1>(d, p, S, B, slots, mirror) * 1e-3));
+      printf("T=64  kind=st  order=%2d mirror=%d        %8.1f GB/s\n", S, mirror, g / (run_tiles<64, 0>(d, p, S, B, slots, mirror) * 1e-3));
+    }
+  return 0;
+}
