@@ -34,9 +34,9 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # BASELINE.json configs; the metric is quoted on c3, which fits one B200 (3.2 GB per p x p)
-    "c1": dict(n=500, p=1000, k=10, batch=64, ring=8, e2e_mc=1000, ref_mc=256),
-    "c2": dict(n=1000, p=5000, k=10, batch=64, ring=8, e2e_mc=2000, ref_mc=128),
-    "c3": dict(n=1000, p=20000, k=10, batch=32, ring=4, e2e_mc=1000, ref_mc=16),
+    "c1": dict(n=500, p=1000, k=10, batch=64, e2e_mc=1000, ref_mc=256),
+    "c2": dict(n=1000, p=5000, k=10, batch=32, e2e_mc=2000, ref_mc=128),
+    "c3": dict(n=1000, p=20000, k=10, batch=16, e2e_mc=1000, ref_mc=16),
 }
 def metric_name(w):
     return f"posterior samples/sec (n={w['n']},p={w['p']},k={w['k']})"
@@ -193,7 +193,7 @@ def run_b200(args, w, wname):
     dev = torch.device("cuda", local)
     n, p, k = w["n"], w["p"], w["k"]
     B = args.batch or w["batch"]
-    slots = min(B, args.ring or w["ring"])
+    slots = B          # one dense p x p slot per draw of a batch (tile-major kernel order)
 
     def barrier():
         if world > 1:
@@ -320,7 +320,7 @@ def run_b200(args, w, wname):
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{wname}: n={n}, p={p}, k={kEst}; draws sharded over ranks" if world > 1 else
-                       f"{wname}: n={n}, p={p}, k={kEst}", "draws_per_step_per_gpu": B, "psi_ring_slots": slots,
+                       f"{wname}: n={n}, p={p}, k={kEst}", "draws_per_step_per_gpu": B, "psi_slots": slots,
                        "mode": "materialise every Psi draw (dense p x p FP64) + sum/sumsq accumulators",
                        "l2": "each step writes %.1f GB >> 126 MB L2; no flush needed" % (8e-9 * p * p * B),
                        "allreduce_ms_in_timed_region": round(allreduce_ms, 3)},
@@ -354,7 +354,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="draws per step per GPU (default: per workload)")
-    ap.add_argument("--ring", type=int, default=0, help="materialised-Psi ring slots")
     ap.add_argument("--e2e-mc", type=int, default=0, help="draws per end-to-end fable_sampler call")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

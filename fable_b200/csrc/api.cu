@@ -517,6 +517,9 @@ int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double*
   fable_ctx* ctx = post->ctx;
   FB_REQUIRE(ctx, B >= 1 && m0 >= 0, "draw_batch: need B >= 1 and m0 >= 0");
   FB_REQUIRE(ctx, dev_psi || accumulate, "draw_batch: nothing to do");
+  // one CTA owns a tile for the whole batch (tile-major order), so every draw of the launch needs
+  // its own slot: a shorter ring would be overwritten before anyone could read it
+  FB_REQUIRE(ctx, !dev_psi || psi_slots >= B, "draw_batch: psi_slots must be >= B (one p x p slot per draw of the batch)");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (B > post->Bcap) {
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -651,7 +654,7 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
         ctx->ring_bytes = need;
       }
     }
-    const int B = 32;
+    const int B = ctx->ring_slots > 0 ? (ctx->ring_slots < 32 ? ctx->ring_slots : 32) : 32;
     for (int64_t b0 = 0; b0 < MC; b0 += B) {
       const int nb = static_cast<int>(MC - b0 < B ? MC - b0 : B);
       FB_TRY(fable_posterior_draw_batch(post, m0 + b0, nb, ctx->ring_slots > 0 ? ctx->ring : nullptr,

@@ -43,14 +43,27 @@ __device__ __forceinline__ void tile_of(int64_t t, int& I, int& J) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// operand rows are re-read by every tile of a block row/column: keep them in L2 (evict_last)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "l"(pol)
+               : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
-               "r"(bytes)
+// the materialised draws are write-once streams: evict_first keeps them from displacing the operands
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -77,6 +90,7 @@ k_psi(PsiArgs a, int64_t tile_begin) {
   const uint32_t run_v = static_cast<uint32_t>((p - v0 < TILE ? p - v0 : TILE) * 8);   // bytes of one mirrored run
   const int nch = (a.k + KC - 1) / KC;
   const int nsteps = a.B * nch;
+  const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
 
   auto prefetch = [&](int s, int buf) {
     const int b = s / nch, l0 = (s - b * nch) * KC;
@@ -86,7 +100,7 @@ k_psi(PsiArgs a, int64_t tile_begin) {
     for (int idx = tid; idx < 2 * kc * (TILE / 2); idx += 256) {
       const int o = idx / (kc * (TILE / 2)), rem = idx - o * kc * (TILE / 2);
       const int l = rem >> 5, ch = rem & 31;
-      cp_async16(dst + (o * KC + l) * TILE + 2 * ch, base + static_cast<int64_t>(l) * a.pp + (o ? v0 : u0) + 2 * ch);
+      cp_async16(dst + (o * KC + l) * TILE + 2 * ch, base + static_cast<int64_t>(l) * a.pp + (o ? v0 : u0) + 2 * ch, pol_keep);
     }
     cp_async_commit();
   };
@@ -168,12 +182,12 @@ k_psi(PsiArgs a, int64_t tile_begin) {
         __syncthreads();
         if (tid < TILE) {
           if (v0 + tid < p)
-            bulk_store(out + (v0 + tid) * p + u0, D + tid * TILE, run_u);
+            bulk_store(out + (v0 + tid) * p + u0, D + tid * TILE, run_u, pol_stream);
           bulk_commit();
         } else if (tid < 2 * TILE) {
           const int cidx = tid - TILE;
           if (!diag && u0 + cidx < p)
-            bulk_store(out + (u0 + cidx) * p + v0, M + cidx * MSTR, run_v);
+            bulk_store(out + (u0 + cidx) * p + v0, M + cidx * MSTR, run_v, pol_stream);
           bulk_commit();
         }
       } else {
@@ -198,17 +212,27 @@ k_psi(PsiArgs a, int64_t tile_begin) {
   if (bulk && tid < 2 * TILE) bulk_wait_read();       // staging must stay valid until the last stores have read it
 
   if (ACC) {
+    // one read-modify-write of the HBM accumulators per batch; loads are batched ahead of the adds
+    // (c[] is free here) so the 16 independent requests per pass are all in flight together
 #pragma unroll
-    for (int iv = 0; iv < 8; ++iv) {
-      const int64_t v = v0 + warp * 8 + iv;
-      if (v < p) {
+    for (int pass = 0; pass < 2; ++pass) {
+      double* __restrict__ dst = pass == 0 ? a.acc_sum : a.acc_sq;
+#pragma unroll
+      for (int iv = 0; iv < 8; ++iv) {
+        const int64_t v = v0 + warp * 8 + iv;
 #pragma unroll
         for (int iu = 0; iu < 2; ++iu) {
           const int64_t u = u0 + lane + 32 * iu;
-          if (u < p) {
-            a.acc_sum[v * p + u] += acc_s[iu][iv];
-            a.acc_sq[v * p + u] += acc_q[iu][iv];
-          }
+          c[iu][iv] = (v < p && u < p) ? dst[v * p + u] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int iv = 0; iv < 8; ++iv) {
+        const int64_t v = v0 + warp * 8 + iv;
+#pragma unroll
+        for (int iu = 0; iu < 2; ++iu) {
+          const int64_t u = u0 + lane + 32 * iu;
+          if (v < p && u < p) dst[v * p + u] = c[iu][iv] + (pass == 0 ? acc_s[iu][iv] : acc_q[iu][iv]);
         }
       }
     }

@@ -64,7 +64,7 @@ void* fable_ctx_stream(fable_ctx* ctx);
 int fable_ctx_kernel_timing(fable_ctx* ctx, int enable);
 int fable_ctx_kernel_time(fable_ctx* ctx, double* total_ms, int64_t* launches);
 /* slots > 0: fable_sampler's Psi pass also MATERIALISES every draw Psi_m (dense p x p) into a device
- * ring of `slots` matrices owned by the context (draw m in slot m % slots), next to the sum / sumsq
+ * ring of `slots` matrices owned by the context (batches of min(slots, 32) draws, draw b of a batch in slot b), next to the sum / sumsq
  * accumulators -- the block-wise covariance formation named by the north star, left resident for
  * device-side consumers (fable_ctx_psi_ring).  slots == 0 (default): accumulate only. */
 int fable_ctx_set_psi_ring(fable_ctx* ctx, int slots);
@@ -141,8 +141,8 @@ void fable_posterior_destroy(fable_posterior* post);
 int fable_posterior_get(fable_posterior* post, double* G0s, double* gnd, double* sig, double* scalars);
 /* One batch of B draws m0..m0+B-1 entirely on the device:
  *   sampler kernel -> Lambda_m, sigma2_m (working layout) -> covariance kernel.
- * dev_psi: device buffer of `psi_slots` p x p matrices (NULL = do not materialise); draw m lands in
- * slot (m - m0) % psi_slots.  accumulate != 0 adds the batch into the posterior's own sum / sumsq
+ * dev_psi: device buffer of `psi_slots` >= B dense p x p matrices (NULL = do not materialise); draw m
+ * lands in slot m - m0 (tiles are processed batch-major, so every draw of a launch needs its own slot).  accumulate != 0 adds the batch into the posterior's own sum / sumsq
  * accumulators (upper tiles; mirrored on fetch).  gam/z: injected DEVICE buffers or NULL. */
 int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi,
                                int psi_slots, int accumulate, const double* dev_gam,

@@ -211,8 +211,10 @@ def test_posterior_batches_accumulate_like_one_pass(ctx, c1):
     assert relerr_mat(st["G0"], ref["G0"]) < TOL and relerr_vec(st["gnd"], ref["gnd"]) < TOL
     assert abs(st["tausq"] / ref["tausq"] - 1) < TOL
     MC = 24
-    slots = 3
+    slots = 16
     psi = torch.empty((slots, p, p), dtype=torch.float64, device="cuda")
+    with pytest.raises(fb.FableError):                 # one slot per draw of the batch
+        post.draw_batch(0, 17, dev_psi=psi.data_ptr(), psi_slots=slots, accumulate=False)
     for m0, B in ((0, 5), (5, 16), (21, 3)):          # ragged batches
         post.draw_batch(m0, B, dev_psi=psi.data_ptr(), psi_slots=slots, accumulate=True)
     ctx.synchronize()
