@@ -464,7 +464,7 @@ int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p
   FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kEst, in));
   fable_posterior* post = new (std::nothrow) fable_posterior();
   if (!post) return ctx->fail(FABLE_ERR_NOMEM, "out of host memory");
-  post->ctx = ctx; post->n = n; post->p = p; post->pp = round_up(p, 64); post->k = kEst; post->KP = kEst;
+  post->ctx = ctx; post->n = n; post->p = p; post->pp = round_up(p, 64); post->k = kEst; post->KP = static_cast<int>(round_up(kEst, 4));
   post->gamma0 = gamma0; post->delta0sq = delta0sq; post->varInflation = varInflation;
   int rc = row_posterior(ctx, in, kEst, gamma0, delta0sq, /*shrunk=*/1, post->rp);
   if (rc != FABLE_OK) { delete post; return rc; }
@@ -678,12 +678,13 @@ int fable_dev_rankk_cov(fable_ctx* ctx, const double* dA, int64_t lda, const dou
   // the covariance kernel reads its operand through 16-byte cp.async from rows zero-padded to a
   // multiple of 64: stage a padded copy (p x k doubles, negligible next to the p x p output)
   const int64_t pp = round_up(p, 64);
+  const int KP = static_cast<int>(round_up(k, 4));
   double* padded = nullptr;
-  FB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&padded), static_cast<size_t>(pp) * k * sizeof(double), ctx->stream));
-  int rc = fb_pad_rows(ctx, dA, lda, p, pp, k, padded);
+  FB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&padded), static_cast<size_t>(pp) * KP * sizeof(double), ctx->stream));
+  int rc = fb_pad_rows(ctx, dA, lda, p, pp, k, KP, padded);
   if (rc == FABLE_OK) {
     PsiArgs a;
-    a.Lw = padded; a.s2w = ds; a.pp = pp; a.p = p; a.k = k; a.KP = k; a.B = 1;
+    a.Lw = padded; a.s2w = ds; a.pp = pp; a.p = p; a.k = k; a.KP = KP; a.B = 1;
     a.psi = dOut; a.psi_slots = 1; a.slot0 = 0; a.acc_sum = nullptr; a.acc_sq = nullptr;
     rc = fb_psi(ctx, a);
   }

@@ -130,18 +130,18 @@ struct PsiArgs {
   const double* s2w;   // sigma^2 draws: s2w[b*pp + j]   (may be NULL: no diagonal term)
   int64_t pp;          // padded row count (multiple of the tile edge)
   int64_t p;
-  int k, KP;
+  int k, KP;           // rank and its zero-padded size (multiple of 4)
   int B;               // draws in this batch
   double* psi;         // materialised output, slot stride p*p (NULL: none)
   int psi_slots;
-  int slot0;           // slot of draw b is (slot0 + b) % psi_slots
+  int slot0;           // draw b goes to slot slot0 + b (< psi_slots)
   double* acc_sum;     // p x p accumulators (NULL: none); upper tiles only
   double* acc_sq;
 };
 int fb_psi(fable_ctx* ctx, const PsiArgs& a);
 int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p);
 // dst (k rows of pp, zero-padded) <- src (k rows of lds, p valid)
-int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, double* dst);
+int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, int KP, double* dst);
 // sampler.cu
 struct SampleArgs {
   const double* G0;    // p x k shrunk loadings mean, leading dimension ldg

@@ -15,21 +15,31 @@
 //   * the rank-k operand rows of draw b+1 are prefetched with cp.async (LDGSTS) into a second
 //     shared-memory buffer while draw b is computed;
 //   * a finished tile is staged in shared memory in BOTH orientations (direct [v][u] and mirrored
-//     [u][v], padded row stride 66 so the transposed 16-byte stores are conflict-free) and leaves
+//     [u][v], row strides padded so the fragment stores are bank-conflict-free) and leaves
 //     the SM as 128 asynchronous 512-byte bulk stores (cp.async.bulk.global.shared::cta -> UBLKCP),
 //     so HBM writes drain while the warps already compute the next draw; every global run is a
 //     full, aligned 512-byte line group written exactly once.
-// Tile = 64 x 64, 256 threads: lane -> row u (two rows, u = lane + 32*iu), warp -> 8 columns v.
+// Tile = 64 x 64, 256 threads = 8 warps as 2 (u) x 4 (v); warp tile 32 x 16 = 4 x 2 FP64 tensor-core
+// tiles (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no f64 kind), rank padded to a multiple
+// of 4 with zero rows.  DMMA runs at the DFMA rate on sm_100a but needs 6 fragment loads per 8 MMAs
+// (2048 FMAs) instead of 6 loads per 16 DFMAs (512 FMAs), which frees the issue slots and shared-memory
+// bandwidth that the staging and the asynchronous stores need.
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int TILE = 64;
-constexpr int KC = 16;             // rank chunk per pipeline step
-constexpr int MSTR = TILE + 2;     // mirrored staging row stride (doubles): 66 = 2 mod 16 -> conflict-free STS.128
-constexpr int OP_DOUBLES = 2 * 2 * KC * TILE;                      // [buf][operand][l][row]
-constexpr size_t OP_BYTES = OP_DOUBLES * sizeof(double);           // 32 KB
-constexpr size_t STAGE_BYTES = (TILE * TILE + TILE * MSTR) * sizeof(double);   // 32 KB + 33 KB
+constexpr int KC = 16;             // rank chunk per pipeline step (multiple of 4)
+constexpr int OSTR = TILE + 4;     // operand row stride: 68 = 4 mod 16 -> conflict-free DMMA fragment loads
+constexpr int DSTR = TILE;         // direct staging  [v][u] and mirrored staging [u][v]: dense 512-byte rows, the
+constexpr int MSTR = TILE;         // shared-memory box layout of the 64 x 64 TMA tensor stores
+constexpr int OP_DOUBLES = 2 * 2 * KC * OSTR;                      // [buf][operand][l][row]
+constexpr size_t OP_BYTES = OP_DOUBLES * sizeof(double);           // 34 KB
+constexpr size_t STAGE_BYTES = (TILE * DSTR + TILE * MSTR) * sizeof(double);   // 33 KB + 36 KB
 
 __device__ __forceinline__ void tile_of(int64_t t, int& I, int& J) {
   // column-major enumeration of the upper triangle: t = J(J+1)/2 + I, 0 <= I <= J
@@ -66,175 +76,231 @@ __device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uin
                "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol)
                : "memory");
 }
+// one 64 x 64 box of the p x p x slots output tensor (TMA clips the box at the matrix edge)
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, int c0, int c1, int c2, const double* ssrc,
+                                              uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(ssrc)), "l"(pol)
+               : "memory");
+}
+// 64 x 64 box added (FP64, in L2) into a p x p accumulator: each entry is touched by exactly one CTA
+// per launch, so the result is deterministic
+__device__ __forceinline__ void tma_reduce_add_box(const CUtensorMap* tmap, int c0, int c1, const double* ssrc) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1), "r"(0), "r"(smem_u32(ssrc))
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 
-// Lw must be zero-padded to pp rows (pp a multiple of TILE) and 16-byte aligned.
+// Lw: working-layout draws, rows zero-padded to pp (a multiple of TILE), rank zero-padded to KP (a
+// multiple of 4), 16-byte aligned.
 template <bool MAT, bool ACC>
 __global__ void __launch_bounds__(256, 2)
-k_psi(PsiArgs a, int64_t tile_begin) {
+k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_sum,
+      const __grid_constant__ CUtensorMap tmap_sq) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* op = reinterpret_cast<double*>(smem_raw);
-  double* D = reinterpret_cast<double*>(smem_raw + OP_BYTES);   // direct  [v][u], stride TILE
-  double* M = D + TILE * TILE;                                  // mirrored [u][v], stride MSTR
+  double* D = reinterpret_cast<double*>(smem_raw + OP_BYTES);   // direct   [v][u], stride DSTR
+  double* M = D + TILE * DSTR;                                  // mirrored [u][v], stride MSTR
 
   int I, J;
   tile_of(tile_begin + blockIdx.x, I, J);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wu = warp & 1, wv = warp >> 1;
   const int64_t u0 = static_cast<int64_t>(I) * TILE, v0 = static_cast<int64_t>(J) * TILE;
   const int64_t p = a.p;
   const bool diag = (I == J);
-  const bool bulk = MAT && ((p & 1) == 0);       // 16-byte aligned runs of even length
-  const uint32_t run_u = static_cast<uint32_t>((p - u0 < TILE ? p - u0 : TILE) * 8);   // bytes of one direct run
-  const uint32_t run_v = static_cast<uint32_t>((p - v0 < TILE ? p - v0 : TILE) * 8);   // bytes of one mirrored run
-  const int nch = (a.k + KC - 1) / KC;
+  const bool even = (p & 1) == 0;                // 16-byte aligned rows: TMA tensor maps exist
+  const bool bulk = MAT && even;
+  const int K4 = a.KP;
+  const int nch = (K4 + KC - 1) / KC;
   const int nsteps = a.B * nch;
   const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
 
+  // threads 0..127 stage the u-operand, 128..255 the v-operand: chunk column = tid & 31 (16 bytes),
+  // rank rows (tid >> 5) & 3, +4, +8, +12
+  const int pf_o = tid >> 7, pf_ch = tid & 31, pf_l0 = (tid >> 5) & 3;
+  const int64_t pf_col = (pf_o ? v0 : u0) + 2 * pf_ch;
   auto prefetch = [&](int s, int buf) {
     const int b = s / nch, l0 = (s - b * nch) * KC;
-    const int kc = min(KC, a.k - l0);
-    const double* base = a.Lw + (static_cast<int64_t>(b) * a.KP + l0) * a.pp;
-    double* dst = op + buf * (2 * KC * TILE);
-    for (int idx = tid; idx < 2 * kc * (TILE / 2); idx += 256) {
-      const int o = idx / (kc * (TILE / 2)), rem = idx - o * kc * (TILE / 2);
-      const int l = rem >> 5, ch = rem & 31;
-      cp_async16(dst + (o * KC + l) * TILE + 2 * ch, base + static_cast<int64_t>(l) * a.pp + (o ? v0 : u0) + 2 * ch, pol_keep);
-    }
+    const int kc = min(KC, K4 - l0);
+    const double* src = a.Lw + (static_cast<int64_t>(b) * a.KP + l0 + pf_l0) * a.pp + pf_col;
+    double* dst = op + buf * (2 * KC * OSTR) + (pf_o * KC + pf_l0) * OSTR + 2 * pf_ch;
+#pragma unroll
+    for (int l = 0; l < KC; l += 4)
+      if (pf_l0 + l < kc) cp_async16(dst + l * OSTR, src + static_cast<int64_t>(l) * a.pp, pol_keep);
     cp_async_commit();
   };
 
-  double acc_s[2][8], acc_q[2][8];
-  if (ACC) {
+  // fragment coordinates: c[i][j][e] is entry (u, v) = (wu*32 + i*8 + g, wv*16 + j*8 + 2t + e) of the tile
+  double acc_s[4][2][2], acc_q[4][2][2];
+  double c[4][2][2];
 #pragma unroll
-    for (int iu = 0; iu < 2; ++iu)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int iv = 0; iv < 8; ++iv) { acc_s[iu][iv] = 0.0; acc_q[iu][iv] = 0.0; }
-  }
-  double c[2][8];
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-  for (int iu = 0; iu < 2; ++iu)
-#pragma unroll
-    for (int iv = 0; iv < 8; ++iv) c[iu][iv] = 0.0;
+      for (int e = 0; e < 2; ++e) {
+        c[i][j][e] = 0.0;
+        if (ACC) { acc_s[i][j][e] = 0.0; acc_q[i][j][e] = 0.0; }
+      }
 
   prefetch(0, 0);
+  cp_async_wait_all();
+  __syncthreads();
   for (int s = 0; s < nsteps; ++s) {
     const int buf = s & 1;
     const int b = s / nch, ch = s - b * nch;
-    const int kc = min(KC, a.k - ch * KC);
-    cp_async_wait_all();
-    __syncthreads();                     // operands of step s landed; buffer buf^1 is no longer read
-    if (s + 1 < nsteps) prefetch(s + 1, buf ^ 1);
+    const int kc = min(KC, K4 - ch * KC);
+    if (s + 1 < nsteps) prefetch(s + 1, buf ^ 1);      // buf^1 was last read before the previous barrier
 
-    const double* As = op + buf * (2 * KC * TILE);
-    const double* Bs = As + KC * TILE;
-#pragma unroll 2
-    for (int l = 0; l < kc; ++l) {
-      const double a0 = As[l * TILE + lane], a1 = As[l * TILE + lane + 32];
-      const double2* bp = reinterpret_cast<const double2*>(Bs + l * TILE + warp * 8);
-      const double2 b01 = bp[0], b23 = bp[1], b45 = bp[2], b67 = bp[3];
-      const double bv[8] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y, b67.x, b67.y};
+    const double* As = op + buf * (2 * KC * OSTR) + wu * 32 + g + t * OSTR;
+    const double* Bs = op + buf * (2 * KC * OSTR) + KC * OSTR + wv * 16 + g + t * OSTR;
 #pragma unroll
-      for (int iv = 0; iv < 8; ++iv) {
-        c[0][iv] = fma(a0, bv[iv], c[0][iv]);
-        c[1][iv] = fma(a1, bv[iv], c[1][iv]);
+    for (int ks = 0; ks < KC / 4; ++ks) {
+      if (ks * 4 < kc) {
+        double af[4], bf[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = As[ks * 4 * OSTR + i * 8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) bf[j] = Bs[ks * 4 * OSTR + j * 8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) dmma(c[i][j], af[i], bf[j]);
       }
     }
-    if (ch + 1 < nch) continue;          // more rank chunks of this draw to come
+    if (ch + 1 < nch) {                  // more rank chunks of this draw to come
+      cp_async_wait_all();
+      __syncthreads();
+      continue;
+    }
 
     // ---- draw b of this tile is complete in registers ----------------------------------------
-    if (diag && a.s2w) {
+    if (diag && a.s2w && wu == (wv >> 1)) {
 #pragma unroll
-      for (int iu = 0; iu < 2; ++iu)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int iv = 0; iv < 8; ++iv)
-          if (lane + 32 * iu == warp * 8 + iv) {
-            const int64_t u = u0 + lane + 32 * iu;
-            if (u < p) c[iu][iv] += a.s2w[static_cast<int64_t>(b) * a.pp + u];
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ul = wu * 32 + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t + e;
+            if (ul == vl && u0 + ul < p) c[i][j][e] += a.s2w[static_cast<int64_t>(b) * a.pp + u0 + ul];
           }
     }
     if (ACC) {
 #pragma unroll
-      for (int iu = 0; iu < 2; ++iu)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int iv = 0; iv < 8; ++iv) {
-          acc_s[iu][iv] += c[iu][iv];
-          acc_q[iu][iv] = fma(c[iu][iv], c[iu][iv], acc_q[iu][iv]);
-        }
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            acc_s[i][j][e] += c[i][j][e];
+            acc_q[i][j][e] = fma(c[i][j][e], c[i][j][e], acc_q[i][j][e]);
+          }
     }
     if (MAT) {
-      double* out = a.psi + static_cast<int64_t>((a.slot0 + b) % a.psi_slots) * p * p;
-      if (bulk && tid < 2 * TILE) bulk_wait_read();   // the previous draw's bulk stores have read the staging
+      if (bulk && tid == 0) bulk_wait_read();         // the previous draw's TMA stores have read the staging
       __syncthreads();
 #pragma unroll
-      for (int iu = 0; iu < 2; ++iu) {
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int iv = 0; iv < 8; ++iv) D[(warp * 8 + iv) * TILE + lane + 32 * iu] = c[iu][iv];
-        if (!diag) {
-          double2* mp = reinterpret_cast<double2*>(M + (lane + 32 * iu) * MSTR + warp * 8);
-          mp[0] = make_double2(c[iu][0], c[iu][1]); mp[1] = make_double2(c[iu][2], c[iu][3]);
-          mp[2] = make_double2(c[iu][4], c[iu][5]); mp[3] = make_double2(c[iu][6], c[iu][7]);
+        for (int j = 0; j < 2; ++j) {
+          const int ul = wu * 32 + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
+          D[vl * DSTR + ul] = c[i][j][0];
+          D[(vl + 1) * DSTR + ul] = c[i][j][1];
+          if (!diag) *reinterpret_cast<double2*>(M + ul * MSTR + vl) = make_double2(c[i][j][0], c[i][j][1]);
         }
-      }
+      if (bulk) fence_async_smem();      // generic-proxy smem writes -> visible to the async (bulk copy) proxy
+    }
+    cp_async_wait_all();
+    __syncthreads();                     // staging complete; operands of step s+1 landed for every thread
+    if (MAT) {
       if (bulk) {
-        fence_async_smem();              // generic-proxy smem writes -> visible to the async (bulk copy) proxy
-        __syncthreads();
-        if (tid < TILE) {
-          if (v0 + tid < p)
-            bulk_store(out + (v0 + tid) * p + u0, D + tid * TILE, run_u, pol_stream);
-          bulk_commit();
-        } else if (tid < 2 * TILE) {
-          const int cidx = tid - TILE;
-          if (!diag && u0 + cidx < p)
-            bulk_store(out + (u0 + cidx) * p + v0, M + cidx * MSTR, run_v, pol_stream);
+        // two TMA tensor stores per draw (UTMASTG): the direct box at (u0, v0) and the mirrored box at
+        // (v0, u0) of slot b.  Issued by one thread, so back-pressure from HBM never blocks the warps
+        // at issue: it is absorbed at bulk_wait_read, after the next draw has been computed.
+        if (tid == 0) {
+          tma_store_box(&tmap, static_cast<int>(u0), static_cast<int>(v0), a.slot0 + b, D, pol_stream);
+          if (!diag) tma_store_box(&tmap, static_cast<int>(v0), static_cast<int>(u0), a.slot0 + b, M, pol_stream);
           bulk_commit();
         }
       } else {
-        __syncthreads();
-        // odd p: runs are not 16-byte aligned -> plain coalesced stores from the staging
+        // odd p: rows are not 16-byte aligned (no tensor map) -> plain coalesced stores from the staging
+        // (the barrier that opens the next draw's staging keeps it intact until these reads are done)
+        double* out = a.psi + static_cast<int64_t>(a.slot0 + b) * p * p;
         for (int cidx = warp; cidx < TILE; cidx += 8) {
           if (v0 + cidx < p)
             for (int h = 0; h < 2; ++h)
-              if (u0 + lane + 32 * h < p) __stcs(out + (v0 + cidx) * p + u0 + lane + 32 * h, D[cidx * TILE + lane + 32 * h]);
+              if (u0 + lane + 32 * h < p) __stcs(out + (v0 + cidx) * p + u0 + lane + 32 * h, D[cidx * DSTR + lane + 32 * h]);
           if (!diag && u0 + cidx < p)
             for (int h = 0; h < 2; ++h)
               if (v0 + lane + 32 * h < p) __stcs(out + (u0 + cidx) * p + v0 + lane + 32 * h, M[cidx * MSTR + lane + 32 * h]);
         }
-        __syncthreads();
       }
     }
 #pragma unroll
-    for (int iu = 0; iu < 2; ++iu)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int iv = 0; iv < 8; ++iv) c[iu][iv] = 0.0;
+      for (int j = 0; j < 2; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
   }
-  if (bulk && tid < 2 * TILE) bulk_wait_read();       // staging must stay valid until the last stores have read it
+  if (bulk && tid == 0) bulk_wait_read();             // staging must stay valid until the last stores have read it
 
-  if (ACC) {
-    // one read-modify-write of the HBM accumulators per batch; loads are batched ahead of the adds
-    // (c[] is free here) so the 16 independent requests per pass are all in flight together
+  if (ACC && even) {
+    // one update of the HBM accumulators per batch (upper tiles only): the register accumulators are
+    // staged as two dense 64 x 64 boxes and added in L2 by TMA reduce stores, so no warp waits for a
+    // DRAM read behind the write stream
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ul = wu * 32 + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
+        D[vl * DSTR + ul] = acc_s[i][j][0];
+        D[(vl + 1) * DSTR + ul] = acc_s[i][j][1];
+        M[vl * DSTR + ul] = acc_q[i][j][0];
+        M[(vl + 1) * DSTR + ul] = acc_q[i][j][1];
+      }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tma_reduce_add_box(&tmap_sum, static_cast<int>(u0), static_cast<int>(v0), D);
+      tma_reduce_add_box(&tmap_sq, static_cast<int>(u0), static_cast<int>(v0), M);
+      bulk_commit();
+      bulk_wait_read();
+    }
+  } else if (ACC) {
+    // odd p (no tensor maps): read-modify-write from the registers; loads are batched ahead of the adds
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       double* __restrict__ dst = pass == 0 ? a.acc_sum : a.acc_sq;
 #pragma unroll
-      for (int iv = 0; iv < 8; ++iv) {
-        const int64_t v = v0 + warp * 8 + iv;
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int iu = 0; iu < 2; ++iu) {
-          const int64_t u = u0 + lane + 32 * iu;
-          c[iu][iv] = (v < p && u < p) ? dst[v * p + u] : 0.0;
-        }
-      }
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int iv = 0; iv < 8; ++iv) {
-        const int64_t v = v0 + warp * 8 + iv;
+          for (int e = 0; e < 2; ++e) {
+            const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+            c[i][j][e] = (v < p && u < p) ? dst[v * p + u] : 0.0;
+          }
 #pragma unroll
-        for (int iu = 0; iu < 2; ++iu) {
-          const int64_t u = u0 + lane + 32 * iu;
-          if (v < p && u < p) dst[v * p + u] = c[iu][iv] + (pass == 0 ? acc_s[iu][iv] : acc_q[iu][iv]);
-        }
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+            if (v < p && u < p) dst[v * p + u] = c[i][j][e] + (pass == 0 ? acc_s[i][j][e] : acc_q[i][j][e]);
+          }
     }
   }
 }
@@ -257,23 +323,49 @@ __global__ void __launch_bounds__(256) k_mirror_upper(double* __restrict__ A, in
   }
 }
 
-// dst[(l*pp) + j] = j < p ? src[l*lds + j] : 0   (zero-padded, 16-byte aligned operand layout)
+// dst[(l*pp) + j] = (j < p && l < k) ? src[l*lds + j] : 0, l < KP   (zero-padded operand layout)
 __global__ void __launch_bounds__(256) k_pad_rows(const double* __restrict__ src, int64_t lds, int64_t p, int64_t pp,
-                                                  int k, double* __restrict__ dst) {
+                                                  int k, int KP, double* __restrict__ dst) {
   const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (j >= pp) return;
-  for (int l = 0; l < k; ++l) dst[static_cast<int64_t>(l) * pp + j] = (j < p) ? src[static_cast<int64_t>(l) * lds + j] : 0.0;
+  for (int l = 0; l < KP; ++l)
+    dst[static_cast<int64_t>(l) * pp + j] = (j < p && l < k) ? src[static_cast<int64_t>(l) * lds + j] : 0.0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// p x p x slots FP64 tensor (column-major matrices: dimension 0 = row index, contiguous), 64 x 64 x 1 boxes
+int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorMap* out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    FB_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return ctx->fail(FABLE_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(slots)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(p) * 8, static_cast<cuuint64_t>(p) * p * 8};
+  const cuuint32_t box[3] = {TILE, TILE, 1}, estr[3] = {1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, psi, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ctx->fail(FABLE_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return FABLE_OK;
 }
 
 template <bool MAT, bool ACC>
-int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned grid, int64_t t0) {
-  constexpr size_t smem = OP_BYTES + (MAT ? STAGE_BYTES : 0);
+int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned grid, int64_t t0, const CUtensorMap& tmap,
+               const CUtensorMap& tsum, const CUtensorMap& tsq) {
+  constexpr size_t smem = OP_BYTES + STAGE_BYTES;
   static bool attr = false;
   if (!attr) {
     FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = true;
   }
-  k_psi<MAT, ACC><<<grid, 256, smem, ctx->stream>>>(a, t0);
+  k_psi<MAT, ACC><<<grid, 256, smem, ctx->stream>>>(a, t0, tmap, tsum, tsq);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
 }
@@ -288,6 +380,8 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
   FB_REQUIRE(ctx, !mat || a.psi_slots > 0, "psi: psi_slots must be positive");
   FB_REQUIRE(ctx, a.pp % TILE == 0 && a.pp >= a.p && (reinterpret_cast<uintptr_t>(a.Lw) & 15) == 0,
              "psi: operand rows must be zero-padded to a multiple of 64 and 16-byte aligned");
+  FB_REQUIRE(ctx, a.KP % 4 == 0 && a.KP >= a.k, "psi: operand rank must be zero-padded to a multiple of 4");
+  FB_REQUIRE(ctx, !mat || a.psi_slots >= a.slot0 + a.B, "psi: one output slot per draw of the batch");
   const int64_t nT = ceil_div(a.p, TILE);
   const int64_t tiles = nT * (nT + 1) / 2;
   const int64_t chunk = 1 << 30;
@@ -302,18 +396,32 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
     ctx->ev_used += 2;
     FB_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
   }
+  CUtensorMap tmap, tsum, tsq;
+  memset(&tmap, 0, sizeof(tmap)); memset(&tsum, 0, sizeof(tsum)); memset(&tsq, 0, sizeof(tsq));
+  if ((a.p & 1) == 0) {
+    if (mat) {
+      FB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(a.psi) & 15) == 0, "psi: the output buffer must be 16-byte aligned");
+      FB_TRY(make_output_map(ctx, a.psi, a.p, a.psi_slots, &tmap));
+    }
+    if (acc) {
+      FB_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(a.acc_sum) | reinterpret_cast<uintptr_t>(a.acc_sq)) & 15) == 0,
+                 "psi: the accumulators must be 16-byte aligned");
+      FB_TRY(make_output_map(ctx, a.acc_sum, a.p, 1, &tsum));
+      FB_TRY(make_output_map(ctx, a.acc_sq, a.p, 1, &tsq));
+    }
+  }
   for (int64_t t0 = 0; t0 < tiles; t0 += chunk) {
     const unsigned g = static_cast<unsigned>(tiles - t0 < chunk ? tiles - t0 : chunk);
-    if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0)));
-    else if (mat) FB_TRY((launch_psi<true, false>(ctx, a, g, t0)));
-    else FB_TRY((launch_psi<false, true>(ctx, a, g, t0)));
+    if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0, tmap, tsum, tsq)));
+    else if (mat) FB_TRY((launch_psi<true, false>(ctx, a, g, t0, tmap, tsum, tsq)));
+    else FB_TRY((launch_psi<false, true>(ctx, a, g, t0, tmap, tsum, tsq)));
   }
   if (ev1) FB_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
   return FABLE_OK;
 }
 
-int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, double* dst) {
-  k_pad_rows<<<static_cast<unsigned>(ceil_div(pp, 256)), 256, 0, ctx->stream>>>(src, lds, p, pp, k, dst);
+int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, int KP, double* dst) {
+  k_pad_rows<<<static_cast<unsigned>(ceil_div(pp, 256)), 256, 0, ctx->stream>>>(src, lds, p, pp, k, KP, dst);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
 }

@@ -68,6 +68,61 @@ __global__ void __launch_bounds__(256) k_tiles(double* __restrict__ out, int64_t
   }
 }
 
+// bulk (TMA) stores from shared memory: T x T tile, direct + mirrored runs of T doubles each, issued
+// either by lane 0 of each of the 8 warps (2T/8 runs per warp) or spread over 2T threads.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int T, int SPREAD>
+__global__ void __launch_bounds__(256) k_bulk(double* __restrict__ out, int64_t p, int nT, int B) {
+  extern __shared__ __align__(128) double sm[];   // [2][T][T+2]
+  int I, J;
+  tri_of(blockIdx.x, I, J);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t u0 = (int64_t)I * T, v0 = (int64_t)J * T;
+  for (int i = threadIdx.x; i < 2 * T * (T + 2); i += 256) sm[i] = (double)i;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const uint32_t ru = (uint32_t)((p - u0 < T ? p - u0 : T) * 8), rv = (uint32_t)((p - v0 < T ? p - v0 : T) * 8);
+  for (int b = 0; b < B; ++b) {
+    double* o = out + (int64_t)b * p * p;
+    if (SPREAD) {
+      if (threadIdx.x < 2 * T && (T == 64 || threadIdx.x < 256)) {
+        for (int r = threadIdx.x; r < 2 * T; r += 256) {
+          const int c = r % T; const bool mir = r >= T;
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (!mir) { if (v0 + c < p) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o + (v0 + c) * p + u0), "r"(smem_u32(sm + c * (T + 2))), "r"(ru) : "memory"); }
+          else if (I != J && u0 + c < p) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o + (u0 + c) * p + v0), "r"(smem_u32(sm + (T + c) * (T + 2))), "r"(rv) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    } else if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      for (int r = warp * (2 * T / 8); r < (warp + 1) * (2 * T / 8); ++r) {
+        const int c = r % T; const bool mir = r >= T;
+        if (!mir) { if (v0 + c < p) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o + (v0 + c) * p + u0), "r"(smem_u32(sm + c * (T + 2))), "r"(ru) : "memory"); }
+        else if (I != J && u0 + c < p) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o + (u0 + c) * p + v0), "r"(smem_u32(sm + (T + c) * (T + 2))), "r"(rv) : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <int T, int SPREAD>
+float run_bulk(double* d, int64_t p, int B) {
+  const int nT = (int)((p + T - 1) / T);
+  const int64_t grid = (int64_t)nT * (nT + 1) / 2;
+  const size_t smem = sizeof(double) * 2 * T * (T + 2);
+  CK(cudaFuncSetAttribute(k_bulk<T, SPREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_bulk<T, SPREAD><<<(unsigned)grid, 256, smem>>>(d, p, nT, 2);
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  k_bulk<T, SPREAD><<<(unsigned)grid, 256, smem>>>(d, p, nT, B);
+  CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  return ms;
+}
+
 // contiguous reference: grid-stride, one draw = p*p doubles
 __global__ void __launch_bounds__(256) k_contig(double* __restrict__ out, int64_t n, int B, int slots) {
   for (int b = 0; b < B; ++b) {
@@ -106,7 +161,10 @@ int main(int argc, char** argv) {
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("contig                                  %8.1f GB/s\n", gb / (ms * 1e-3));
   }
-  const int orders[] = {0, 4, 8, 16};
+  printf("bulk T=64  (512 B runs) lane0/warp       %8.1f GB/s\n", gb / (run_bulk<64, 0>(d, p, B) * 1e-3));
+  printf("bulk T=64  (512 B runs) spread            %8.1f GB/s\n", gb / (run_bulk<64, 1>(d, p, B) * 1e-3));
+  printf("bulk T=128 (1 KB runs)  lane0/warp        %8.1f GB/s\n", gb / (run_bulk<128, 0>(d, p, B) * 1e-3));
+  const int orders[] = {0, 16};
   for (int mirror = 0; mirror < 2; ++mirror)
     for (int S : orders) {
       // full-matrix bytes when mirror=1; upper triangle only (about half) when mirror=0
