@@ -18,7 +18,7 @@ import time
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libfable_b200.so")
+_SO = os.environ.get("FABLE_B200_LIB") or os.path.join(_HERE, "libfable_b200.so")
 _lib = None
 _dp = C.POINTER(C.c_double)
 _i64 = C.c_int64

@@ -137,6 +137,7 @@ struct PsiArgs {
   int slot0;           // draw b goes to slot slot0 + b (< psi_slots)
   double* acc_sum;     // p x p accumulators (NULL: none); upper tiles only
   double* acc_sq;
+  int tma_mode = 0;    // set by fb_psi: 1 = 4-D whole-tile TMA boxes, 2 = 3-D sub-boxes, 0 = plain stores
 };
 int fb_psi(fable_ctx* ctx, const PsiArgs& a);
 int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p);

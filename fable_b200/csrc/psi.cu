@@ -14,11 +14,11 @@
 //     registers across the draw loop (one read-modify-write of the HBM accumulators per batch);
 //   * the rank-k operand rows of draw b+1 are prefetched with cp.async (LDGSTS) into a second
 //     shared-memory buffer while draw b is computed;
-//   * a finished tile is staged in shared memory in BOTH orientations (direct [v][u] and mirrored
-//     [u][v], row strides padded so the fragment stores are bank-conflict-free) and leaves
-//     the SM as 128 asynchronous 512-byte bulk stores (cp.async.bulk.global.shared::cta -> UBLKCP),
-//     so HBM writes drain while the warps already compute the next draw; every global run is a
-//     full, aligned 512-byte line group written exactly once.
+//   * a finished tile is staged in shared memory in BOTH orientations (direct and mirrored, as
+//     128-byte-swizzled TMA boxes) and leaves the SM as two asynchronous TMA tensor stores
+//     (cp.async.bulk.tensor -> UTMASTG), so HBM writes drain while the warps already compute the
+//     next draw; every global run is a full, aligned 512-byte line group written exactly once;
+//   * the register accumulators reach HBM as TMA reduce-add stores (UTMAREDG), once per batch.
 // Tile = 64 x 64, 256 threads = 8 warps as 2 (u) x 4 (v); warp tile 32 x 16 = 4 x 2 FP64 tensor-core
 // tiles (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no f64 kind), rank padded to a multiple
 // of 4 with zero rows.  DMMA runs at the DFMA rate on sm_100a but needs 6 fragment loads per 8 MMAs
@@ -35,19 +35,49 @@ namespace {
 constexpr int TILE = 64;
 constexpr int KC = 16;             // rank chunk per pipeline step (multiple of 4)
 constexpr int OSTR = TILE + 4;     // operand row stride: 68 = 4 mod 16 -> conflict-free DMMA fragment loads
-constexpr int DSTR = TILE;         // direct staging  [v][u] and mirrored staging [u][v]: dense 512-byte rows, the
-constexpr int MSTR = TILE;         // shared-memory box layout of the 64 x 64 TMA tensor stores
+constexpr int BOXW = 16;           // TMA box row: 16 doubles = 128 bytes = one swizzle row
+constexpr int BOX_DOUBLES = BOXW * TILE;   // 16 x 64 sub-box, 8 KB; 4 sub-boxes per orientation
 constexpr int OP_DOUBLES = 2 * 2 * KC * OSTR;                      // [buf][operand][l][row]
 constexpr size_t OP_BYTES = OP_DOUBLES * sizeof(double);           // 34 KB
-constexpr size_t STAGE_BYTES = (TILE * DSTR + TILE * MSTR) * sizeof(double);   // 33 KB + 36 KB
+constexpr size_t STAGE_BYTES = 2 * TILE * TILE * sizeof(double);   // direct + mirrored, 32 KB each
+constexpr size_t SMEM_BYTES = OP_BYTES + STAGE_BYTES + 1024;       // + slack to align the boxes to 1024 bytes
 
-__device__ __forceinline__ void tile_of(int64_t t, int& I, int& J) {
-  // column-major enumeration of the upper triangle: t = J(J+1)/2 + I, 0 <= I <= J
+// Staging layouts = the shared-memory image of 128-byte-swizzled TMA boxes: sub-box q holds 16
+// consecutive rows-of-the-matrix (the contiguous index) for 64 columns; inside a sub-box, row r is 8
+// chunks of 16 bytes and chunk c sits at position c ^ (r & 7).
+//   direct   orientation: sub-box q = u in [16q, 16q+16), row = v
+//   mirrored orientation: sub-box q = v in [16q, 16q+16), row = u
+// With the DMMA accumulator layout (u = g, v = 2t+e per 8 x 8 tile) the direct 8-byte stores are
+// bank-conflict-free and the mirrored 16-byte stores are 2-way conflicted (dense 512-byte rows
+// would be 4-way / 2-way).
+__device__ __forceinline__ int d_off(int u, int v) {
+  return (u >> 4) * BOX_DOUBLES + v * BOXW + ((((u & 15) >> 1) ^ (v & 7)) << 1) + (u & 1);
+}
+__device__ __forceinline__ int m_off(int u, int v) {
+  return (v >> 4) * BOX_DOUBLES + u * BOXW + ((((v & 15) >> 1) ^ (u & 7)) << 1) + (v & 1);
+}
+
+__device__ __forceinline__ void tri_of(int64_t t, int& I, int& J) {
+  // column-major enumeration of an upper triangle: t = J(J+1)/2 + I, 0 <= I <= J
   int64_t j = static_cast<int64_t>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
   while (j * (j + 1) / 2 > t) --j;
   while ((j + 1) * (j + 2) / 2 <= t) ++j;
   J = static_cast<int>(j);
   I = static_cast<int>(t - j * (j + 1) / 2);
+}
+
+// Tile order: super-blocks of SB x SB tiles (the super-blocks enumerated over their own upper triangle,
+// tiles column-major inside).  The CTAs resident at any time then share 2*SB operand row blocks, which
+// are re-read after ~SB tiles instead of after a whole block column, so the operand rows stay in L2
+// under the write stream.  Returns false for the padding slots (below the diagonal / past the edge).
+constexpr int SB = 16;
+__device__ __forceinline__ bool tile_of(int64_t t, int nT, int& I, int& J) {
+  int sI, sJ;
+  tri_of(t / (SB * SB), sI, sJ);
+  const int r = static_cast<int>(t % (SB * SB));
+  I = sI * SB + (r % SB);
+  J = sJ * SB + (r / SB);
+  return I <= J && J < nT;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -76,20 +106,37 @@ __device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uin
                "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol)
                : "memory");
 }
-// one 64 x 64 box of the p x p x slots output tensor (TMA clips the box at the matrix edge)
-__device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, int c0, int c1, int c2, const double* ssrc,
-                                              uint64_t pol) {
+// The p x p x slots output is described to TMA as a 4-D tensor (r_lo = 16 contiguous rows, column,
+// r_hi = row block of 16, slot) so that ONE store moves a whole 64 x 64 tile as a {16, 64, 4, 1} box whose
+// shared-memory image is the four swizzled sub-boxes above (TMA clips the box at the matrix edge).
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* tmap, int col, int rowblk, int slot, const double* ssrc,
+                                               uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4}], [%5], %6;" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(0), "r"(col), "r"(rowblk), "r"(slot), "r"(smem_u32(ssrc)), "l"(pol)
+               : "memory");
+}
+// Fallback when p is even but not a multiple of 16: the plain 3-D map (row, column, slot) and one
+// {16, 64, 1} store per swizzled sub-box (four per orientation).
+__device__ __forceinline__ void tma_store_subbox(const CUtensorMap* tmap, int row, int col, int slot, const double* ssrc,
+                                                 uint64_t pol) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(
                    reinterpret_cast<uint64_t>(tmap)),
-               "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(ssrc)), "l"(pol)
+               "r"(row), "r"(col), "r"(slot), "r"(smem_u32(ssrc)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_subbox(const CUtensorMap* tmap, int row, int col, const double* ssrc) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(row), "r"(col), "r"(0), "r"(smem_u32(ssrc))
                : "memory");
 }
 // 64 x 64 box added (FP64, in L2) into a p x p accumulator: each entry is touched by exactly one CTA
 // per launch, so the result is deterministic
-__device__ __forceinline__ void tma_reduce_add_box(const CUtensorMap* tmap, int c0, int c1, const double* ssrc) {
-  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+__device__ __forceinline__ void tma_reduce_add_tile(const CUtensorMap* tmap, int col, int rowblk, const double* ssrc) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
                    reinterpret_cast<uint64_t>(tmap)),
-               "r"(c0), "r"(c1), "r"(0), "r"(smem_u32(ssrc))
+               "r"(0), "r"(col), "r"(rowblk), "r"(0), "r"(smem_u32(ssrc))
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -106,20 +153,21 @@ template <bool MAT, bool ACC>
 __global__ void __launch_bounds__(256, 2)
 k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_sum,
       const __grid_constant__ CUtensorMap tmap_sq) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms: 1 KB aligned
   double* op = reinterpret_cast<double*>(smem_raw);
-  double* D = reinterpret_cast<double*>(smem_raw + OP_BYTES);   // direct   [v][u], stride DSTR
-  double* M = D + TILE * DSTR;                                  // mirrored [u][v], stride MSTR
+  double* D = reinterpret_cast<double*>(smem_raw + OP_BYTES);   // direct   staging (4 swizzled sub-boxes)
+  double* M = D + TILE * TILE;                                  // mirrored staging (4 swizzled sub-boxes)
 
   int I, J;
-  tile_of(tile_begin + blockIdx.x, I, J);
+  if (!tile_of(tile_begin + blockIdx.x, static_cast<int>((a.p + TILE - 1) / TILE), I, J)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wu = warp & 1, wv = warp >> 1;
   const int64_t u0 = static_cast<int64_t>(I) * TILE, v0 = static_cast<int64_t>(J) * TILE;
   const int64_t p = a.p;
   const bool diag = (I == J);
-  const bool even = (p & 1) == 0;                // 16-byte aligned rows: TMA tensor maps exist
+  const bool even = a.tma_mode != 0;             // TMA tensor maps exist (1: 4-D whole-tile boxes, 2: 3-D sub-boxes)
   const bool bulk = MAT && even;
   const int K4 = a.KP;
   const int nch = (K4 + KC - 1) / KC;
@@ -216,9 +264,9 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int ul = wu * 32 + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
-          D[vl * DSTR + ul] = c[i][j][0];
-          D[(vl + 1) * DSTR + ul] = c[i][j][1];
-          if (!diag) *reinterpret_cast<double2*>(M + ul * MSTR + vl) = make_double2(c[i][j][0], c[i][j][1]);
+          D[d_off(ul, vl)] = c[i][j][0];
+          D[d_off(ul, vl + 1)] = c[i][j][1];
+          if (!diag) *reinterpret_cast<double2*>(M + m_off(ul, vl)) = make_double2(c[i][j][0], c[i][j][1]);
         }
       if (bulk) fence_async_smem();      // generic-proxy smem writes -> visible to the async (bulk copy) proxy
     }
@@ -226,25 +274,35 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
     __syncthreads();                     // staging complete; operands of step s+1 landed for every thread
     if (MAT) {
       if (bulk) {
-        // two TMA tensor stores per draw (UTMASTG): the direct box at (u0, v0) and the mirrored box at
-        // (v0, u0) of slot b.  Issued by one thread, so back-pressure from HBM never blocks the warps
-        // at issue: it is absorbed at bulk_wait_read, after the next draw has been computed.
+        // two TMA tensor stores per draw (UTMASTG): the direct tile (columns v0.., row blocks u0/16..)
+        // and the mirrored tile (columns u0.., row blocks v0/16..) of slot b.  Issued by one thread, so
+        // back-pressure from HBM never blocks the warps at issue: it is absorbed at bulk_wait_read,
+        // after the next draw has been computed.
         if (tid == 0) {
-          tma_store_box(&tmap, static_cast<int>(u0), static_cast<int>(v0), a.slot0 + b, D, pol_stream);
-          if (!diag) tma_store_box(&tmap, static_cast<int>(v0), static_cast<int>(u0), a.slot0 + b, M, pol_stream);
+          if (a.tma_mode == 1) {
+            tma_store_tile(&tmap, static_cast<int>(v0), static_cast<int>(u0 >> 4), a.slot0 + b, D, pol_stream);
+            if (!diag) tma_store_tile(&tmap, static_cast<int>(u0), static_cast<int>(v0 >> 4), a.slot0 + b, M, pol_stream);
+          } else {
+            for (int q = 0; q < TILE / BOXW; ++q) {
+              if (u0 + q * BOXW < p)
+                tma_store_subbox(&tmap, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), a.slot0 + b, D + q * BOX_DOUBLES, pol_stream);
+              if (!diag && v0 + q * BOXW < p)
+                tma_store_subbox(&tmap, static_cast<int>(v0) + q * BOXW, static_cast<int>(u0), a.slot0 + b, M + q * BOX_DOUBLES, pol_stream);
+            }
+          }
           bulk_commit();
         }
       } else {
-        // odd p: rows are not 16-byte aligned (no tensor map) -> plain coalesced stores from the staging
+        // odd p (rows not 16-byte aligned, no tensor map) -> plain coalesced stores from the staging
         // (the barrier that opens the next draw's staging keeps it intact until these reads are done)
         double* out = a.psi + static_cast<int64_t>(a.slot0 + b) * p * p;
         for (int cidx = warp; cidx < TILE; cidx += 8) {
           if (v0 + cidx < p)
             for (int h = 0; h < 2; ++h)
-              if (u0 + lane + 32 * h < p) __stcs(out + (v0 + cidx) * p + u0 + lane + 32 * h, D[cidx * DSTR + lane + 32 * h]);
+              if (u0 + lane + 32 * h < p) __stcs(out + (v0 + cidx) * p + u0 + lane + 32 * h, D[d_off(lane + 32 * h, cidx)]);
           if (!diag && u0 + cidx < p)
             for (int h = 0; h < 2; ++h)
-              if (v0 + lane + 32 * h < p) __stcs(out + (u0 + cidx) * p + v0 + lane + 32 * h, M[cidx * MSTR + lane + 32 * h]);
+              if (v0 + lane + 32 * h < p) __stcs(out + (u0 + cidx) * p + v0 + lane + 32 * h, M[m_off(cidx, lane + 32 * h)]);
         }
       }
     }
@@ -265,21 +323,29 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int ul = wu * 32 + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
-        D[vl * DSTR + ul] = acc_s[i][j][0];
-        D[(vl + 1) * DSTR + ul] = acc_s[i][j][1];
-        M[vl * DSTR + ul] = acc_q[i][j][0];
-        M[(vl + 1) * DSTR + ul] = acc_q[i][j][1];
+        D[d_off(ul, vl)] = acc_s[i][j][0];
+        D[d_off(ul, vl + 1)] = acc_s[i][j][1];
+        M[d_off(ul, vl)] = acc_q[i][j][0];      // both accumulators use the direct orientation
+        M[d_off(ul, vl + 1)] = acc_q[i][j][1];
       }
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-      tma_reduce_add_box(&tmap_sum, static_cast<int>(u0), static_cast<int>(v0), D);
-      tma_reduce_add_box(&tmap_sq, static_cast<int>(u0), static_cast<int>(v0), M);
+      if (a.tma_mode == 1) {
+        tma_reduce_add_tile(&tmap_sum, static_cast<int>(v0), static_cast<int>(u0 >> 4), D);
+        tma_reduce_add_tile(&tmap_sq, static_cast<int>(v0), static_cast<int>(u0 >> 4), M);
+      } else {
+        for (int q = 0; q < TILE / BOXW; ++q)
+          if (u0 + q * BOXW < p) {
+            tma_reduce_add_subbox(&tmap_sum, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), D + q * BOX_DOUBLES);
+            tma_reduce_add_subbox(&tmap_sq, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), M + q * BOX_DOUBLES);
+          }
+      }
       bulk_commit();
       bulk_wait_read();
     }
   } else if (ACC) {
-    // odd p (no tensor maps): read-modify-write from the registers; loads are batched ahead of the adds
+    // odd p (no tensor maps): read-modify-write from the registers; loads batched ahead of the adds
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       double* __restrict__ dst = pass == 0 ? a.acc_sum : a.acc_sq;
@@ -336,7 +402,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// p x p x slots FP64 tensor (column-major matrices: dimension 0 = row index, contiguous), 64 x 64 x 1 boxes
+// p x p x slots FP64 tensor of column-major matrices, 128-byte swizzle.
+//   p % 16 == 0: 4-D (r_lo 16, column p, r_hi p/16, slot), box {16, 64, 4, 1} = a whole tile per store
+//   p %  2 == 0: 3-D (row p, column p, slot),              box {16, 64, 1}    = one sub-box per store
 int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorMap* out) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
@@ -346,12 +414,22 @@ int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorM
     if (!fn || q != cudaDriverEntryPointSuccess) return ctx->fail(FABLE_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(p), static_cast<cuuint64_t>(slots)};
-  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(p) * 8, static_cast<cuuint64_t>(p) * p * 8};
-  const cuuint32_t box[3] = {TILE, TILE, 1}, estr[3] = {1, 1, 1};
-  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, psi, dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const cuuint64_t up = static_cast<cuuint64_t>(p);
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r;
+  if (p % BOXW == 0) {
+    const cuuint64_t dims[4] = {BOXW, up, up / BOXW, static_cast<cuuint64_t>(slots)};
+    const cuuint64_t strides[3] = {up * 8, BOXW * 8, up * up * 8};
+    const cuuint32_t box[4] = {BOXW, TILE, TILE / BOXW, 1};
+    r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, psi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[3] = {up, up, static_cast<cuuint64_t>(slots)};
+    const cuuint64_t strides[2] = {up * 8, up * up * 8};
+    const cuuint32_t box[3] = {BOXW, TILE, 1};
+    r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, psi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) return ctx->fail(FABLE_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
   return FABLE_OK;
 }
@@ -359,7 +437,7 @@ int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorM
 template <bool MAT, bool ACC>
 int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned grid, int64_t t0, const CUtensorMap& tmap,
                const CUtensorMap& tsum, const CUtensorMap& tsq) {
-  constexpr size_t smem = OP_BYTES + STAGE_BYTES;
+  constexpr size_t smem = SMEM_BYTES;
   static bool attr = false;
   if (!attr) {
     FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -372,7 +450,9 @@ int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned grid, int64_t t0, cons
 
 }  // namespace
 
-int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
+int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
+  PsiArgs a = a_in;
+  a.tma_mode = (a.p % BOXW == 0) ? 1 : ((a.p & 1) == 0 ? 2 : 0);
   FB_REQUIRE(ctx, a.p > 0 && a.k > 0 && a.B > 0, "psi: empty problem");
   FB_REQUIRE(ctx, (a.acc_sum == nullptr) == (a.acc_sq == nullptr), "psi: need both accumulators");
   const bool mat = a.psi != nullptr, acc = a.acc_sum != nullptr;
@@ -382,8 +462,8 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
              "psi: operand rows must be zero-padded to a multiple of 64 and 16-byte aligned");
   FB_REQUIRE(ctx, a.KP % 4 == 0 && a.KP >= a.k, "psi: operand rank must be zero-padded to a multiple of 4");
   FB_REQUIRE(ctx, !mat || a.psi_slots >= a.slot0 + a.B, "psi: one output slot per draw of the batch");
-  const int64_t nT = ceil_div(a.p, TILE);
-  const int64_t tiles = nT * (nT + 1) / 2;
+  const int64_t nT = ceil_div(a.p, TILE), nSB = ceil_div(nT, SB);
+  const int64_t tiles = nSB * (nSB + 1) / 2 * SB * SB;    // super-block order, padding slots exit at once
   const int64_t chunk = 1 << 30;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->timing) {
@@ -398,7 +478,7 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a) {
   }
   CUtensorMap tmap, tsum, tsq;
   memset(&tmap, 0, sizeof(tmap)); memset(&tsum, 0, sizeof(tsum)); memset(&tsq, 0, sizeof(tsq));
-  if ((a.p & 1) == 0) {
+  if (a.tma_mode != 0) {
     if (mat) {
       FB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(a.psi) & 15) == 0, "psi: the output buffer must be 16-byte aligned");
       FB_TRY(make_output_map(ctx, a.psi, a.p, a.psi_slots, &tmap));
