@@ -1,0 +1,82 @@
+"""CPU tests of the multi-GPU host logic (fable_b200/parallel.py) with world_size-2 gloo:
+draw sharding + sum all-reduce of the accumulators reproduces the single-process result, sample row
+ranges are disjoint and complete, tile ranges partition the upper triangle.  The per-rank arithmetic
+is done by the oracle's C twin here (no GPU in this container); on the GPU box the same helpers drive
+libfable_b200 (bench.py under torchrun)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from fable_b200 import parallel  # noqa: E402
+
+
+def test_draw_range_partitions_the_mc_axis():
+    for MC in (0, 1, 7, 10, 1000, 10001):
+        for world in (1, 2, 3, 8):
+            r = [parallel.draw_range(MC, g, world) for g in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == MC
+            assert all(r[g][1] == r[g + 1][0] for g in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.draw_range(10, 2, 2)
+
+
+def test_tile_range_partitions_the_upper_triangle():
+    for p in (1, 64, 65, 1000, 20000, 50000):
+        nT = -(-p // 64)
+        total = nT * (nT + 1) // 2
+        for world in (1, 2, 8):
+            r = [parallel.tile_range(p, g, world) for g in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(r[g][1] == r[g + 1][0] for g in range(world - 1))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
+def _worker(rank, world, port, MC, p, k, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import c_oracle
+    rng = np.random.default_rng(0)                       # same posterior on every rank
+    G0 = rng.standard_normal((p, k)); gnd = rng.uniform(20.0, 60.0, p)
+    a_n, shape, seed = 0.07, 15.5, 99
+    lo, hi = parallel.draw_range(MC, rank, world)
+    gam, z = c_oracle.rng_fill(seed, lo, hi - lo, p, k, shape)        # counter-based: draw m is the same on any rank
+    L, S = c_oracle.sampler(hi - lo, p, k, G0, gnd, a_n, gam, z)
+    s1, s2 = c_oracle.psi_moments(L, S, k)
+    t1, t2 = torch.from_numpy(np.ascontiguousarray(s1)), torch.from_numpy(np.ascontiguousarray(s2))
+    parallel.allreduce_moments([t1, t2])
+    Lall = parallel.gather_sample_rows(L, MC, rank, world)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "multi.npz"), s1=t1.numpy(), s2=t2.numpy(), L=Lall)
+    dist.destroy_process_group()
+
+
+def test_sharded_draws_and_allreduce_match_single_process(tmp_path):
+    from oracle import c_oracle
+    MC, p, k, world = 11, 37, 3, 2
+    port = _free_port()
+    mp.start_processes(_worker, args=(world, port, MC, p, k, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    got = np.load(tmp_path / "multi.npz")
+    rng = np.random.default_rng(0)
+    G0 = rng.standard_normal((p, k)); gnd = rng.uniform(20.0, 60.0, p)
+    gam, z = c_oracle.rng_fill(99, 0, MC, p, k, 15.5)
+    L, S = c_oracle.sampler(MC, p, k, G0, gnd, 0.07, gam, z)
+    s1, s2 = c_oracle.psi_moments(L, S, k)
+    np.testing.assert_array_equal(got["L"], L)                     # samples: bit-identical, disjoint row ranges
+    assert np.max(np.abs(got["s1"] - s1)) <= 1e-12 * np.max(np.abs(s1))   # sums: order of addition differs
+    assert np.max(np.abs(got["s2"] - s2)) <= 1e-12 * np.max(np.abs(s2))
