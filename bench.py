@@ -36,7 +36,7 @@ WORKLOADS = {
     # BASELINE.json configs; the metric is quoted on c3, which fits one B200 (3.2 GB per p x p)
     "c1": dict(n=500, p=1000, k=10, batch=64, e2e_mc=1000, ref_mc=256),
     "c2": dict(n=1000, p=5000, k=10, batch=32, e2e_mc=2000, ref_mc=128),
-    "c3": dict(n=1000, p=20000, k=10, batch=32, e2e_mc=1024, ref_mc=16),
+    "c3": dict(n=1000, p=20000, k=10, batch=32, e2e_mc=4096, ref_mc=16),
 }
 def metric_name(w):
     return f"posterior samples/sec (n={w['n']},p={w['p']},k={w['k']})"
@@ -186,6 +186,7 @@ def run_b200(args, w, wname):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("FABLE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:

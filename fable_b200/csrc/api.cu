@@ -637,9 +637,11 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
   FB_TRY(download(ctx, SigmaPlugIn, post->rp.sig.d(), p));                     // cpp:623
   if (tausq) *tausq = post->rp.tausq;                                          // cpp:626
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  FB_TRY(fable_posterior_samples(post, m0, MC, MC, LambdaSamples, SigmaSqSamples, gam_inj, z_inj));
+  // The Psi pass (draw loop on the main stream) is enqueued first; the reference-layout samples are
+  // then generated and copied out on the copy stream, so their D2H traffic (8 p (k+1) bytes per draw)
+  // overlaps the covariance kernels.  Both read the same immutable row posterior.
+  DevBuf dgam, dz;
   if (psi_sum) {
-    DevBuf dgam, dz;
     if (gam_inj) {
       FB_TRY(upload(ctx, dgam, gam_inj, static_cast<size_t>(MC) * p));
       FB_TRY(upload(ctx, dz, z_inj, static_cast<size_t>(MC) * p * kEst));
@@ -661,10 +663,22 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
                                         ctx->ring_slots, 1,
                                         gam_inj ? dgam.d() + b0 * p : nullptr,
                                         gam_inj ? dz.d() + b0 * p * kEst : nullptr));
-      if (ctx->poll && ctx->poll(ctx->poll_user)) return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");
+      if (ctx->poll && ctx->poll(ctx->poll_user)) {
+        cudaStreamSynchronize(ctx->stream);
+        return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");
+      }
     }
-    FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
   }
+  {
+    struct StreamSwap {      // run the sample kernels + copies on the copy stream
+      fable_ctx* c; cudaStream_t main;
+      explicit StreamSwap(fable_ctx* cx) : c(cx), main(cx->stream) { c->stream = c->copy_stream; }
+      ~StreamSwap() { c->stream = main; }
+    } swap(ctx);
+    const int rc = fable_posterior_samples(post, m0, MC, MC, LambdaSamples, SigmaSqSamples, gam_inj, z_inj);
+    if (rc != FABLE_OK) { cudaStreamSynchronize(swap.main); return rc; }
+  }
+  if (psi_sum) FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
   if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), p, nullptr, p, kEst, G));   // cpp:627
   return FABLE_OK;
 }
