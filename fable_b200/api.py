@@ -415,6 +415,11 @@ def dev_gemm(ctx, a_kfast, b_kfast, M, N, K, alpha, dA, lda, dB, ldb, dC, ldc):
                                      C.c_void_p(dC), _i64(ldc)))
 
 
+def dev_syrk(ctx, a_kfast, M, K, alpha, dA, lda, dC):
+    ctx.check(_load().fable_dev_syrk(ctx._h, C.c_int(a_kfast), _i64(M), _i64(K), C.c_double(alpha), C.c_void_p(dA),
+                                     _i64(lda), C.c_void_p(dC)))
+
+
 def dev_syevj(ctx, dG, m, dW, dQ):
     sweeps = C.c_int()
     ctx.check(_load().fable_dev_syevj(ctx._h, C.c_void_p(dG), _i64(m), C.c_void_p(dW), C.c_void_p(dQ),

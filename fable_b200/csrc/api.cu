@@ -237,6 +237,7 @@ void fable_ctx_destroy(fable_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ring) cudaFree(ctx->ring);
+  if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -712,6 +713,14 @@ int fable_dev_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t 
   FB_REQUIRE(ctx, dA && dB && dC, "gemm: NULL pointer");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   return fb_gemm(ctx, a_kfast != 0, b_kfast != 0, M, N, K, alpha, dA, lda, dB, ldb, dC, ldc);
+}
+
+int fable_dev_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alpha, const double* dA, int64_t lda,
+                   double* dC) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, dA && dC, "syrk: NULL pointer");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return fb_syrk(ctx, a_kfast != 0, M, K, alpha, dA, lda, dC, M);
 }
 
 int fable_dev_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps) {

@@ -23,6 +23,8 @@ struct fable_ctx {
   std::vector<cudaEvent_t> ev_pool;     // pairs: [2i] before, [2i+1] after the launch
   size_t ev_used = 0;
   // optional device ring of materialised Psi draws kept by fable_sampler (fable_ctx_set_psi_ring)
+  double* gemm_ws = nullptr;    // grow-only split-K workspace of the DMMA GEMM
+  size_t gemm_ws_bytes = 0;
   int ring_slots = 0;
   double* ring = nullptr;
   size_t ring_bytes = 0;
@@ -117,6 +119,8 @@ int fb_sum_partials(fable_ctx* ctx, const double* d_part, int64_t nparts, int64_
 // gemm.cu
 int fb_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K, double alpha,
             const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc);
+int fb_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alpha, const double* dA, int64_t lda,
+            double* dC, int64_t ldc);
 // residual column sums of squares: d_resid[j] = sum_i (Y[i,j] - sum_l U[i,l] C[j,l])^2, l < k.
 int fb_gemm_resid(fable_ctx* ctx, int64_t n, int64_t p, int k, const double* dY, int64_t ldy,
                   const double* dU, int64_t ldu, const double* dC, int64_t ldc, double* d_resid);

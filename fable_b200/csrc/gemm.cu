@@ -61,7 +61,9 @@ __device__ __forceinline__ void store_tile_smem(double* __restrict__ S, const do
 
 // RESID = false: C[z] = alpha * partial product (z = split index, partial stride M*N when split)
 // RESID = true : out[blockIdx.x * N + n] = sum_{m in tile} (Yres[m + ldy*n] - acc)^2
-template <bool AKF, bool BKF, bool RESID>
+// SYRK: B == A and only the tiles with block row <= block column are computed (blockIdx.x enumerates
+// the upper triangle of the tile grid column-major); the caller mirrors the result.
+template <bool AKF, bool BKF, bool RESID, bool SYRK = false>
 __global__ void __launch_bounds__(256)
 k_gemm(int64_t M, int64_t N, int64_t K, int64_t kper, double alpha, const double* __restrict__ A, int64_t lda,
        const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc, int64_t split_stride,
@@ -73,7 +75,15 @@ k_gemm(int64_t M, int64_t N, int64_t K, int64_t kper, double alpha, const double
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp & 1, wn = warp >> 1;
-  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM, n0 = static_cast<int64_t>(blockIdx.y) * BN;
+  int64_t bi = blockIdx.x, bj = blockIdx.y;
+  if (SYRK) {
+    const int64_t t = blockIdx.x;
+    int64_t j = static_cast<int64_t>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
+    while (j * (j + 1) / 2 > t) --j;
+    while ((j + 1) * (j + 2) / 2 <= t) ++j;
+    bj = j; bi = t - j * (j + 1) / 2;
+  }
+  const int64_t m0 = bi * BM, n0 = bj * BN;
   const int64_t kbeg = static_cast<int64_t>(blockIdx.z) * kper;
   const int64_t kend = (kbeg + kper < K) ? kbeg + kper : K;
 
@@ -170,17 +180,17 @@ k_gemm(int64_t M, int64_t N, int64_t K, int64_t kper, double alpha, const double
 
 constexpr size_t kSmemBytes = 4 * STAGE_DOUBLES * sizeof(double);
 
-template <bool AKF, bool BKF, bool RESID>
+template <bool AKF, bool BKF, bool RESID, bool SYRK = false>
 int launch(fable_ctx* ctx, dim3 grid, int64_t M, int64_t N, int64_t K, int64_t kper, double alpha, const double* A,
            int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t split_stride,
            const double* Yres, int64_t ldy) {
   static bool attr = false;
   if (!attr) {
-    FB_CUDA(ctx, cudaFuncSetAttribute(k_gemm<AKF, BKF, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_gemm<AKF, BKF, RESID, SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(kSmemBytes)));
     attr = true;
   }
-  k_gemm<AKF, BKF, RESID><<<grid, 256, kSmemBytes, ctx->stream>>>(M, N, K, kper, alpha, A, lda, B, ldb, C, ldc,
+  k_gemm<AKF, BKF, RESID, SYRK><<<grid, 256, kSmemBytes, ctx->stream>>>(M, N, K, kper, alpha, A, lda, B, ldb, C, ldc,
                                                                  split_stride, Yres, ldy);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
@@ -188,29 +198,70 @@ int launch(fable_ctx* ctx, dim3 grid, int64_t M, int64_t N, int64_t K, int64_t k
 
 }  // namespace
 
+namespace {
+// split K so that the grid covers the 148 SMs about twice
+int64_t choose_splits(const fable_ctx* ctx, int64_t tiles, int64_t K, int64_t* kper) {
+  int64_t splits = 1;
+  const int64_t ktiles = ceil_div(K, BK);
+  if (tiles < 2 * ctx->sms) {
+    splits = ceil_div(2 * static_cast<int64_t>(ctx->sms), tiles);
+    if (splits > ktiles / 4) splits = ktiles / 4 > 0 ? ktiles / 4 : 1;
+    if (splits > 64) splits = 64;
+  }
+  *kper = round_up(ceil_div(K, splits), BK);
+  return ceil_div(K, *kper);
+}
+// grow-only split-K workspace owned by the context (no allocation or synchronisation per call)
+int workspace(fable_ctx* ctx, size_t bytes, double** out) {
+  if (bytes > ctx->gemm_ws_bytes) {
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+    ctx->gemm_ws = nullptr; ctx->gemm_ws_bytes = 0;
+    FB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->gemm_ws), bytes));
+    ctx->gemm_ws_bytes = bytes;
+  }
+  *out = ctx->gemm_ws;
+  return FABLE_OK;
+}
+}  // namespace
+
+// C (M x M, upper triangle + mirrored) = alpha * A A',  A: M x K (K-slow or K-fast)
+int fb_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alpha, const double* dA, int64_t lda,
+            double* dC, int64_t ldc) {
+  FB_REQUIRE(ctx, M > 0 && K > 0 && ldc == M, "syrk: need M, K > 0 and a dense output");
+  const int64_t gm = ceil_div(M, BM), tiles = gm * (gm + 1) / 2;
+  int64_t kper = 0;
+  const int64_t splits = choose_splits(ctx, tiles, K, &kper);
+  dim3 grid(static_cast<unsigned>(tiles), 1, static_cast<unsigned>(splits));
+  double* out = dC;
+  int64_t stride = 0;
+  double a_eff = alpha;
+  if (splits > 1) {
+    FB_TRY(workspace(ctx, static_cast<size_t>(splits) * M * M * sizeof(double), &out));
+    stride = M * M; a_eff = 1.0;
+    // lower tiles of the partial buffers are never written: zero them once so the sum is defined
+    FB_CUDA(ctx, cudaMemsetAsync(out, 0, static_cast<size_t>(splits) * M * M * sizeof(double), ctx->stream));
+  }
+  if (a_kfast) FB_TRY((launch<true, true, false, true>(ctx, grid, M, M, K, kper, a_eff, dA, lda, dA, lda, out, M, stride, nullptr, 0)));
+  else FB_TRY((launch<false, false, false, true>(ctx, grid, M, M, K, kper, a_eff, dA, lda, dA, lda, out, M, stride, nullptr, 0)));
+  if (splits > 1) FB_TRY(fb_sum_partials(ctx, out, splits, M * M, M * M, alpha, dC));
+  return fb_mirror_upper(ctx, dC, M);
+}
+
 int fb_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K, double alpha,
             const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc) {
   FB_REQUIRE(ctx, M > 0 && N > 0 && K > 0, "gemm: empty problem");
   const int64_t gm = ceil_div(M, BM), gn = ceil_div(N, BN);
   FB_REQUIRE(ctx, gn <= 65535, "gemm: N too large for one launch");
-  // split K so that the grid covers the 148 SMs about twice
-  int64_t splits = 1;
-  const int64_t ktiles = ceil_div(K, BK);
-  if (gm * gn < 2 * ctx->sms) {
-    splits = ceil_div(2 * static_cast<int64_t>(ctx->sms), gm * gn);
-    if (splits > ktiles / 4) splits = ktiles / 4 > 0 ? ktiles / 4 : 1;
-    if (splits > 64) splits = 64;
-  }
-  const int64_t kper = round_up(ceil_div(K, splits), BK);
-  splits = ceil_div(K, kper);
+  int64_t kper = 0;
+  const int64_t splits = choose_splits(ctx, gm * gn, K, &kper);
   dim3 grid(static_cast<unsigned>(gm), static_cast<unsigned>(gn), static_cast<unsigned>(splits));
-  DevBuf part;
   double* out = dC;
   int64_t out_ld = ldc, stride = 0;
   double a_eff = alpha;
   if (splits > 1) {
-    FB_CUDA(ctx, part.alloc(static_cast<size_t>(splits) * M * N * sizeof(double)));
-    out = part.d(); out_ld = M; stride = M * N; a_eff = 1.0;
+    FB_TRY(workspace(ctx, static_cast<size_t>(splits) * M * N * sizeof(double), &out));
+    out_ld = M; stride = M * N; a_eff = 1.0;
   }
 #define FB_GEMM_CASE(AK, BKF_)                                                                                \
   if (a_kfast == AK && b_kfast == BKF_)                                                                       \
@@ -220,12 +271,11 @@ int fb_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int6
 #undef FB_GEMM_CASE
   if (splits > 1) {
     if (ldc == M) {
-      FB_TRY(fb_sum_partials(ctx, part.d(), splits, M * N, M * N, alpha, dC));
+      FB_TRY(fb_sum_partials(ctx, out, splits, M * N, M * N, alpha, dC));
     } else {
       for (int64_t n = 0; n < N; ++n)  // rare: strided output
-        FB_TRY(fb_sum_partials(ctx, part.d() + n * M, splits, M, M * N, alpha, dC + n * ldc));
+        FB_TRY(fb_sum_partials(ctx, out + n * M, splits, M, M * N, alpha, dC + n * ldc));
     }
-    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // partial buffer is freed on return
   }
   return FABLE_OK;
 }
@@ -234,12 +284,10 @@ int fb_gemm_resid(fable_ctx* ctx, int64_t n, int64_t p, int k, const double* dY,
                   int64_t ldu, const double* dC, int64_t ldc, double* d_resid) {
   const int64_t gm = ceil_div(n, BM), gn = ceil_div(p, BN);
   FB_REQUIRE(ctx, gn <= 65535, "gemm_resid: p too large for one launch");
-  DevBuf part;
-  FB_CUDA(ctx, part.alloc(static_cast<size_t>(gm) * p * sizeof(double)));
+  double* part = nullptr;
+  FB_TRY(workspace(ctx, static_cast<size_t>(gm) * p * sizeof(double), &part));
   dim3 grid(static_cast<unsigned>(gm), static_cast<unsigned>(gn), 1);
-  FB_TRY((launch<false, false, true>(ctx, grid, n, p, k, round_up(k, BK), 1.0, dU, ldu, dC, ldc, part.d(), 0, 0,
+  FB_TRY((launch<false, false, true>(ctx, grid, n, p, k, round_up(k, BK), 1.0, dU, ldu, dC, ldc, part, 0, 0,
                                      dY, ldy)));
-  FB_TRY(fb_sum_partials(ctx, part.d(), gm, p, p, 1.0, d_resid));
-  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return FABLE_OK;
+  return fb_sum_partials(ctx, part, gm, p, p, 1.0, d_resid);
 }

@@ -77,13 +77,13 @@ int fb_svd(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, double* dU, d
   FB_CUDA(ctx, W.alloc(static_cast<size_t>(r) * sizeof(double)));
   int sweeps = 0;
   if (n <= p) {
-    FB_TRY(fb_gemm(ctx, 0, 0, n, n, p, 1.0, dY, n, dY, n, G.d(), n));        // Y Y'
+    FB_TRY(fb_syrk(ctx, 0, n, p, 1.0, dY, n, G.d(), n));                        // Y Y' (upper tiles + mirror)
     FB_TRY(fb_syevj(ctx, G.d(), n, W.d(), dU, &sweeps));                        // U (n x n)
     FB_TRY(fb_gemm(ctx, 1, 1, p, r, n, 1.0, dY, n, dU, n, dV, p));             // T = Y'U
     k_norm_scale<<<static_cast<unsigned>(r), ST, 0, ctx->stream>>>(dV, p, p, dd);
     FB_LAUNCHED(ctx);
   } else {
-    FB_TRY(fb_gemm(ctx, 1, 1, p, p, n, 1.0, dY, n, dY, n, G.d(), p));        // Y'Y
+    FB_TRY(fb_syrk(ctx, 1, p, n, 1.0, dY, n, G.d(), p));                        // Y'Y (upper tiles + mirror)
     FB_TRY(fb_syevj(ctx, G.d(), p, W.d(), dV, &sweeps));                        // V (p x p)
     FB_TRY(fb_gemm(ctx, 0, 1, n, r, p, 1.0, dY, n, dV, p, dU, n));             // T = Y V
     k_norm_scale<<<static_cast<unsigned>(r), ST, 0, ctx->stream>>>(dU, n, n, dd);

@@ -169,6 +169,11 @@ int fable_dev_rankk_cov(fable_ctx* ctx, const double* dA, int64_t lda, const dou
 int fable_dev_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K,
                    double alpha, const double* dA, int64_t lda, const double* dB, int64_t ldb,
                    double* dC, int64_t ldc);
+/* C (M x M dense, both triangles) = alpha * A A', A: M x K stored K-slow (column-major M x K, lda) or K-fast
+ * (a_kfast: K x M with leading dimension lda).  Only the upper tile triangle is computed on the FP64
+ * tensor cores (SYRK: M(M+1)K flops), then mirrored: the Gram step Y Y' / Y'Y of fable_svd. */
+int fable_dev_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alpha, const double* dA,
+                   int64_t lda, double* dC);
 /* symmetric eigen-decomposition of the m x m matrix dG (destroyed): eigenvalues descending in
  * dW (m), eigenvectors in the columns of dQ (m x m). */
 int fable_dev_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps);
