@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     CPPRankEstimator, CPPCriterionFunction, CPPBisectionRecursion,
     FABLEHyperParameters, CPPcov_correct_matrix, cov_correct_matrix, var_inflation,
     CPPFABLEPostMean, CPPFABLESampler, CPPsvd, svd, kmax_rule,
+    CPPCCFABLEPostProcessing, CCFABLEPostProcessingSubmatrix, CCFABLEPostProcessingSubmatrix_Optimized,
     default_context, library_path,
 )
 from . import synth  # noqa: F401
@@ -20,5 +21,6 @@ __all__ = [
     "FableError", "Context", "Posterior", "FABLEPosteriorMean", "FABLEPosteriorSampler",
     "CPPRankEstimator", "CPPCriterionFunction", "CPPBisectionRecursion", "FABLEHyperParameters",
     "CPPcov_correct_matrix", "cov_correct_matrix", "var_inflation", "CPPFABLEPostMean",
-    "CPPFABLESampler", "CPPsvd", "svd", "kmax_rule", "default_context", "library_path", "synth",
+    "CPPFABLESampler", "CPPsvd", "svd", "kmax_rule", "CPPCCFABLEPostProcessing",
+    "CCFABLEPostProcessingSubmatrix", "CCFABLEPostProcessingSubmatrix_Optimized", "default_context", "library_path", "synth",
 ]

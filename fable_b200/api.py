@@ -340,6 +340,39 @@ def CPPFABLESampler(Y, gamma0, delta0sq, MC, U_Y, V_Y, svalsY, kEst, varInflatio
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# f1: post-processing of stored draws (R/RcppExports.R:77-87)
+# ------------------------------------------------------------------------------------------------
+def _post(FABLEOutput, alpha, sel, ctx):
+    ctx = _ctx(ctx)
+    L = _F(FABLEOutput["LambdaSamples"]); S = _F(FABLEOutput["SigmaSqSamples"]); k = int(FABLEOutput["EstimatedRank"])
+    MC, p = S.shape
+    if L.shape != (MC, k * p):
+        raise FableError(1, "LambdaSamples must be MC x (k p)")
+    if sel is None:
+        n = p; sp = None
+    else:
+        sel = np.ascontiguousarray(sel, dtype=np.int64); n = sel.size
+        sp = sel.ctypes.data_as(C.POINTER(C.c_int64))
+    M = np.empty((n, n), order="F"); Lo = np.empty((n, n), order="F"); Up = np.empty((n, n), order="F")
+    ctx.check(_load().fable_post_processing(ctx._h, _ptr(L), _ptr(S), _i64(MC), _i64(p), C.c_int(k), C.c_double(alpha), sp,
+                                            _i64(n), _ptr(M), _ptr(Lo), _ptr(Up)))
+    return {"PostMeanMatrix": M, "LowerQuantileMatrix": Lo, "UpperQuantileMatrix": Up}
+
+
+def CPPCCFABLEPostProcessing(FABLEOutput, alpha, ctx=None):
+    """cpp:631-713: mean and (alpha/2, 1-alpha/2) quantiles of every entry of Psi over the draws."""
+    return _post(FABLEOutput, alpha, None, ctx)
+
+
+def CCFABLEPostProcessingSubmatrix(FABLEOutput, alpha, SelectedIndices, ctx=None):
+    """cpp:716-818: the same on the sub-matrix of the (1-based) SelectedIndices."""
+    return _post(FABLEOutput, alpha, SelectedIndices, ctx)
+
+
+CCFABLEPostProcessingSubmatrix_Optimized = CCFABLEPostProcessingSubmatrix   # cpp:821-893: same results
+
+
 class Posterior:
     """fable_posterior: the row posterior resident in HBM + batched draw / covariance kernels."""
 
@@ -374,6 +407,15 @@ class Posterior:
         self.ctx.check(_load().fable_posterior_draw_batch(self._h, _i64(m0), C.c_int(B), C.c_void_p(dev_psi or None),
                                                           C.c_int(psi_slots), C.c_int(1 if accumulate else 0),
                                                           C.c_void_p(dev_gam or None), C.c_void_p(dev_z or None)))
+
+    def tile_slots(self):
+        n = C.c_int64()
+        self.ctx.check(_load().fable_posterior_tile_slots(self._h, C.byref(n)))
+        return n.value
+
+    def set_tile_range(self, t_begin, t_end):
+        """Partition B: restrict draw_batch to a slice of the tile enumeration (0, 0 = everything)."""
+        self.ctx.check(_load().fable_posterior_set_tile_range(self._h, _i64(t_begin), _i64(t_end)))
 
     def samples(self, m0, MC, gam=None, z=None, want_lambda=True, want_sigma=True):
         L = np.empty((MC, self.k * self.p), order="F") if want_lambda else None

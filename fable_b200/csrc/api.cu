@@ -194,6 +194,7 @@ struct fable_posterior {
   int Bcap = 0;
   DevBuf acc_sum, acc_sq;
   bool mirrored = false;
+  int64_t tile_begin = 0, tile_end = 0;
 };
 
 extern "C" {
@@ -535,7 +536,22 @@ int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double*
   a.Lw = post->Lw.d(); a.s2w = post->s2w.d(); a.pp = post->pp; a.p = post->p; a.k = post->k; a.KP = post->KP;
   a.B = B; a.psi = dev_psi; a.psi_slots = psi_slots; a.slot0 = 0;
   a.acc_sum = accumulate ? post->acc_sum.d() : nullptr; a.acc_sq = accumulate ? post->acc_sq.d() : nullptr;
+  a.tile_begin = post->tile_begin; a.tile_end = post->tile_end;
   return fb_psi(ctx, a);
+}
+
+int fable_posterior_tile_slots(fable_posterior* post, int64_t* slots) {
+  if (!post || !slots) return FABLE_ERR_INVALID;
+  *slots = fb_psi_tile_slots(post->p);
+  return FABLE_OK;
+}
+
+int fable_posterior_set_tile_range(fable_posterior* post, int64_t t_begin, int64_t t_end) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, t_begin >= 0 && t_begin <= t_end && t_end <= fb_psi_tile_slots(post->p), "tile range out of bounds");
+  post->tile_begin = t_begin; post->tile_end = t_end;
+  return FABLE_OK;
 }
 
 int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64_t ldm, double* LambdaSamples,
@@ -681,6 +697,44 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
   }
   if (psi_sum) FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
   if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), p, nullptr, p, kEst, G));   // cpp:627
+  return FABLE_OK;
+}
+
+// ---- f1: post-processing of the stored draws -------------------------------------------------------
+int fable_post_processing(fable_ctx* ctx, const double* LambdaSamples, const double* SigmaSqSamples, int64_t MC,
+                          int64_t p, int k, double alpha, const int64_t* selected, int64_t S, double* PostMean,
+                          double* Lower, double* Upper) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, LambdaSamples && SigmaSqSamples && PostMean && Lower && Upper, "post_processing: NULL pointer");
+  FB_REQUIRE(ctx, MC >= 1 && p >= 1 && k >= 1, "post_processing: need MC, p, k >= 1");
+  if (!selected) S = p;
+  FB_REQUIRE(ctx, S >= 1, "post_processing: empty selection");
+  std::vector<int64_t> idx(S);
+  for (int64_t i = 0; i < S; ++i) {
+    idx[i] = selected ? selected[i] - 1 : i;                          // cpp:721: 1-based R indices
+    FB_REQUIRE(ctx, idx[i] >= 0 && idx[i] < p, "post_processing: SelectedIndices out of range");   // arma bounds error
+  }
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf dL, dS, dI, dM, dLo, dUp;
+  FB_CUDA(ctx, dL.alloc(static_cast<size_t>(S) * k * MC * sizeof(double)));
+  FB_CUDA(ctx, dS.alloc(static_cast<size_t>(S) * MC * sizeof(double)));
+  FB_CUDA(ctx, dI.alloc(static_cast<size_t>(S) * sizeof(int64_t)));
+  for (auto* b : {&dM, &dLo, &dUp}) FB_CUDA(ctx, b->alloc(static_cast<size_t>(S) * S * sizeof(double)));
+  if (!selected) {
+    FB_CUDA(ctx, cudaMemcpyAsync(dL.ptr, LambdaSamples, static_cast<size_t>(p) * k * MC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(ctx, cudaMemcpyAsync(dS.ptr, SigmaSqSamples, static_cast<size_t>(p) * MC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    for (int64_t i = 0; i < S; ++i) {   // the k factor columns of one variable are contiguous in the reference layout
+      FB_CUDA(ctx, cudaMemcpyAsync(dL.d() + i * k * MC, LambdaSamples + idx[i] * k * MC, static_cast<size_t>(k) * MC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      FB_CUDA(ctx, cudaMemcpyAsync(dS.d() + i * MC, SigmaSqSamples + idx[i] * MC, static_cast<size_t>(MC) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  FB_CUDA(ctx, cudaMemcpyAsync(dI.ptr, idx.data(), static_cast<size_t>(S) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  FB_TRY(fb_post_processing(ctx, dL.d(), dS.d(), static_cast<const int64_t*>(dI.ptr), MC, k, S, alpha, dM.d(), dLo.d(), dUp.d()));
+  FB_TRY(download(ctx, PostMean, dM.d(), static_cast<size_t>(S) * S));
+  FB_TRY(download(ctx, Lower, dLo.d(), static_cast<size_t>(S) * S));
+  FB_TRY(download(ctx, Upper, dUp.d(), static_cast<size_t>(S) * S));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FABLE_OK;
 }
 

@@ -141,12 +141,17 @@ struct PsiArgs {
   int slot0;           // draw b goes to slot slot0 + b (< psi_slots)
   double* acc_sum;     // p x p accumulators (NULL: none); upper tiles only
   double* acc_sq;
+  int64_t tile_begin = 0, tile_end = 0;   // slice of the tile enumeration (tile_end == 0: all tiles)
   int tma_mode = 0;    // set by fb_psi: 1 = 4-D whole-tile TMA boxes, 2 = 3-D sub-boxes, 0 = plain stores
 };
 int fb_psi(fable_ctx* ctx, const PsiArgs& a);
+int64_t fb_psi_tile_slots(int64_t p);   // length of the (super-block padded) tile enumeration
 int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p);
 // dst (k rows of pp, zero-padded) <- src (k rows of lds, p valid)
 int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, int KP, double* dst);
+// post.cu: Lsel [S][k][MC], Ssel [S][MC], idx [S] (0-based selected variables); outputs S x S column-major
+int fb_post_processing(fable_ctx* ctx, const double* dLsel, const double* dSsel, const int64_t* d_idx, int64_t MC, int k,
+                       int64_t S, double alpha, double* d_mean, double* d_lower, double* d_upper);
 // sampler.cu
 struct SampleArgs {
   const double* G0;    // p x k shrunk loadings mean, leading dimension ldg

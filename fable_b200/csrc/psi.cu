@@ -490,8 +490,15 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
       FB_TRY(make_output_map(ctx, a.acc_sq, a.p, 1, &tsq));
     }
   }
-  for (int64_t t0 = 0; t0 < tiles; t0 += chunk) {
-    const unsigned g = static_cast<unsigned>(tiles - t0 < chunk ? tiles - t0 : chunk);
+  // optional slice of the tile enumeration (multi-GPU partition B: every rank processes all draws for
+  // its own tiles; no collective)
+  int64_t t_lo = 0, t_hi = tiles;
+  if (a.tile_end > 0) {
+    FB_REQUIRE(ctx, a.tile_begin >= 0 && a.tile_begin <= a.tile_end && a.tile_end <= tiles, "psi: tile range out of bounds");
+    t_lo = a.tile_begin; t_hi = a.tile_end;
+  }
+  for (int64_t t0 = t_lo; t0 < t_hi; t0 += chunk) {
+    const unsigned g = static_cast<unsigned>(t_hi - t0 < chunk ? t_hi - t0 : chunk);
     if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0, tmap, tsum, tsq)));
     else if (mat) FB_TRY((launch_psi<true, false>(ctx, a, g, t0, tmap, tsum, tsq)));
     else FB_TRY((launch_psi<false, true>(ctx, a, g, t0, tmap, tsum, tsq)));
@@ -504,6 +511,11 @@ int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64
   k_pad_rows<<<static_cast<unsigned>(ceil_div(pp, 256)), 256, 0, ctx->stream>>>(src, lds, p, pp, k, KP, dst);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
+}
+
+int64_t fb_psi_tile_slots(int64_t p) {
+  const int64_t nT = ceil_div(p, TILE), nSB = ceil_div(nT, SB);
+  return nSB * (nSB + 1) / 2 * SB * SB;
 }
 
 int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p) {

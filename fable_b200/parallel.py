@@ -27,11 +27,21 @@ def draw_range(MC, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def tile_range(p, rank, world, tile=64):
-    """Contiguous [t_begin, t_end) of the upper-triangle tile list (t = J(J+1)/2 + I, I <= J)
-    owned by `rank`, balanced by tile count."""
+def tile_slots(p, tile=64, sb=16):
+    """Length of the covariance kernel's tile enumeration: upper-triangle 64 x 64 tiles in 16 x 16
+    super-block order, padding slots included (same count as fable_posterior_tile_slots)."""
     nT = -(-int(p) // tile)
-    return draw_range(nT * (nT + 1) // 2, rank, world)
+    nSB = -(-nT // sb)
+    return nSB * (nSB + 1) // 2 * sb * sb
+
+
+def tile_range(p, rank, world, tile=64, sb=16):
+    """Contiguous [t_begin, t_end) of the tile enumeration owned by `rank` (multiples of a super-block
+    so every rank keeps the operand locality of the kernel's order)."""
+    total = tile_slots(p, tile, sb)
+    blocks = total // (sb * sb)
+    lo, hi = draw_range(blocks, rank, world)
+    return lo * sb * sb, hi * sb * sb
 
 
 class _DevArray:

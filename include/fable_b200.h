@@ -130,6 +130,14 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
                   double* SigmaPostMean, double* SigmaPlugIn, double* tausq, double* G,
                   double* psi_sum, double* psi_sumsq);
 
+/* ---- f1: CPPCCFABLEPostProcessing (:631-713) / CCFABLEPostProcessingSubmatrix(_Optimized) (:716-893) ---
+ * Entry-wise posterior mean and (alpha/2, 1-alpha/2) sample quantiles (Armadillo quantile, type 5) of
+ * Psi over the stored draws, on the variables `selected` (1-based R indices, length S; NULL = all p).
+ * LambdaSamples MC x (k p), SigmaSqSamples MC x p as CPPFABLESampler returns them.  Outputs S x S. */
+int fable_post_processing(fable_ctx* ctx, const double* LambdaSamples, const double* SigmaSqSamples,
+                          int64_t MC, int64_t p, int k, double alpha, const int64_t* selected, int64_t S,
+                          double* PostMean, double* Lower, double* Upper);
+
 /* ---- resident-in-HBM posterior object (what fable_sampler is built from) ---------------------- */
 /* Uploads Y, U_k, V_k, d_k, runs the row-posterior kernels, keeps G0 / gnd / a_n on the device. */
 int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
@@ -147,6 +155,13 @@ int fable_posterior_get(fable_posterior* post, double* G0s, double* gnd, double*
 int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi,
                                int psi_slots, int accumulate, const double* dev_gam,
                                const double* dev_z);
+/* Multi-GPU partition B (tiles): restrict draw_batch to the slice [t_begin, t_end) of the kernel's tile
+ * enumeration (64 x 64 upper-triangle tiles in 16 x 16 super-block order; fable_posterior_tile_slots
+ * gives its length, padding slots included).  Ranks owning disjoint slices and processing the same
+ * draws produce disjoint parts of every Psi_m and of the accumulators: no collective is needed.
+ * t_end == 0 restores the full range.  (Only upper tiles are written; mirror / fetch as usual.) */
+int fable_posterior_tile_slots(fable_posterior* post, int64_t* slots);
+int fable_posterior_set_tile_range(fable_posterior* post, int64_t t_begin, int64_t t_end);
 /* reference-layout samples for draws m0..m0+MC-1 into HOST arrays with leading dimension ldm
  * (>= MC; rows m-m0) -- NULL to skip either. */
 int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64_t ldm,

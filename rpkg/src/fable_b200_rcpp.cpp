@@ -161,6 +161,34 @@ Rcpp::List FABLESamplerMoments(Rcpp::NumericMatrix Y, double gamma0, double delt
   return Rcpp::List::create(Rcpp::Named("PsiSum") = s1, Rcpp::Named("PsiSumSq") = s2, Rcpp::Named("MC") = MC);
 }
 
+// reference cpp:631-713 and cpp:716-818 / 821-893 (f1): mean + (alpha/2, 1-alpha/2) sample quantiles
+static Rcpp::List post_processing(Rcpp::List FABLEOutput, double alpha, const int64_t* sel, int64_t S) {
+  Rcpp::NumericMatrix L = FABLEOutput["LambdaSamples"], Sg = FABLEOutput["SigmaSqSamples"];
+  const int k = FABLEOutput["EstimatedRank"];
+  const int64_t MC = Sg.nrow(), p = Sg.ncol();
+  if (!sel) S = p;
+  Rcpp::NumericMatrix M(S, S), Lo(S, S), Up(S, S);
+  check(fable_post_processing(ctx(), L.begin(), Sg.begin(), MC, p, k, alpha, sel, S, M.begin(), Lo.begin(), Up.begin()));
+  return Rcpp::List::create(Rcpp::Named("PostMeanMatrix") = M, Rcpp::Named("LowerQuantileMatrix") = Lo,
+                            Rcpp::Named("UpperQuantileMatrix") = Up);
+}
+
+// [[Rcpp::export]]
+Rcpp::List CPPCCFABLEPostProcessing(Rcpp::List FABLEOutput, double alpha) {
+  return post_processing(FABLEOutput, alpha, nullptr, 0);
+}
+
+// [[Rcpp::export]]
+Rcpp::List CCFABLEPostProcessingSubmatrix(Rcpp::List FABLEOutput, double alpha, Rcpp::IntegerVector SelectedIndices) {
+  std::vector<int64_t> sel(SelectedIndices.begin(), SelectedIndices.end());      // 1-based, as in R (cpp:721)
+  return post_processing(FABLEOutput, alpha, sel.data(), static_cast<int64_t>(sel.size()));
+}
+
+// [[Rcpp::export]]
+Rcpp::List CCFABLEPostProcessingSubmatrix_Optimized(Rcpp::List FABLEOutput, double alpha, Rcpp::IntegerVector SelectedIndices) {
+  return CCFABLEPostProcessingSubmatrix(FABLEOutput, alpha, SelectedIndices);
+}
+
 // reference cpp:40-74 (exported, unused by the wrappers); `flag` chose a LAPACK driver there
 // [[Rcpp::export]]
 Rcpp::List CPPsvd(Rcpp::NumericMatrix X, int flag) {

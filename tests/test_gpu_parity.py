@@ -235,7 +235,69 @@ def test_posterior_batches_accumulate_like_one_pass(ctx, c1):
     post.close()
 
 
-@pytest.mark.parametrize("p,k", [(1, 1), (63, 1), (64, 2), (65, 3), (130, 13), (200, 20), (257, 33)])
+@pytest.mark.parametrize("n,p,k,B", [(120, 640, 20, 3), (90, 333, 17, 2), (50, 64, 1, 5)])
+def test_c4_like_ranks_above_one_chunk(ctx, n, p, k, B):
+    """BASELINE configs[3] in miniature (k = 20 > the 16-row rank chunk; p on / off the TMA paths):
+    materialised draws and accumulators against the oracle rebuilt from the returned samples."""
+    import torch
+    Y, u, d, v = _svd_inputs(n, p, k, 51)
+    post = fb.Posterior(Y, 1.0, 1.0, u, v, d, k, 2.0, ctx=ctx)
+    psi = torch.zeros((B, p, p), dtype=torch.float64, device="cuda")
+    post.draw_batch(7, B, dev_psi=psi.data_ptr(), psi_slots=B, accumulate=True)
+    s1, s2 = post.accum_fetch()
+    L, S = post.samples(7, B)
+    r1, r2 = c_oracle.psi_moments(L, S, k)
+    assert relerr_mat(s1, r1) < TOL and relerr_mat(s2, r2) < TOL
+    for b in range(B):
+        assert relerr_mat(psi[b].cpu().numpy().T, c_oracle.psi_draw(L, S, k, b)) < TOL
+    post.close()
+
+
+def test_tile_partition_needs_no_collective(ctx):
+    """Partition B: two 'ranks' owning disjoint tile slices and processing the same draws fill disjoint
+    parts of the accumulators and of every Psi_m; their union is the single-GPU result (p % 16 == 0:
+    the whole-tile TMA path)."""
+    import torch
+    from fable_b200 import parallel
+    n, p, k, B = 60, 1600, 3, 4
+    Y, u, d, v = _svd_inputs(n, p, k, 31)
+    post = fb.Posterior(Y, 1.0, 1.0, u, v, d, k, 1.4, ctx=ctx)
+    assert post.tile_slots() == parallel.tile_slots(p)
+    full = torch.zeros((B, p, p), dtype=torch.float64, device="cuda")
+    post.draw_batch(0, B, dev_psi=full.data_ptr(), psi_slots=B, accumulate=True)
+    f1, f2 = post.accum_fetch()
+    parts = torch.zeros((B, p, p), dtype=torch.float64, device="cuda")
+    post.accum_reset()
+    for rank in range(2):
+        post.set_tile_range(*parallel.tile_range(p, rank, 2))
+        post.draw_batch(0, B, dev_psi=parts.data_ptr(), psi_slots=B, accumulate=True)
+    post.set_tile_range(0, 0)
+    g1, g2 = post.accum_fetch()
+    ctx.synchronize()
+    assert torch.equal(full, parts)
+    np.testing.assert_array_equal(g1, f1); np.testing.assert_array_equal(g2, f2)
+    L, S = post.samples(0, B)
+    r1, r2 = c_oracle.psi_moments(L, S, k)
+    assert relerr_mat(f1, r1) < TOL and relerr_mat(f2, r2) < TOL
+    assert relerr_mat(full[2].cpu().numpy().T, c_oracle.psi_draw(L, S, k, 2)) < TOL
+    post.close()
+
+
+@pytest.mark.parametrize("M,K,akf", [(1, 1, 0), (130, 77, 0), (130, 77, 1), (300, 4000, 0), (257, 1000, 1)])
+def test_syrk_gram(ctx, M, K, akf):
+    import torch
+    rng = np.random.default_rng(M + K)
+    A = rng.standard_normal((M, K))
+    dA = torch.from_numpy(A.copy() if akf else A.T.copy()).cuda()
+    dC = torch.empty((M, M), dtype=torch.float64, device="cuda")
+    fb.api.dev_syrk(ctx, akf, M, K, 2.0, dA.data_ptr(), K if akf else M, dC.data_ptr())
+    ctx.synchronize()
+    got = dC.cpu().numpy()
+    assert relerr_mat(got, 2.0 * A @ A.T) < 1e-13
+    assert np.array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("p,k", [(1, 1), (63, 1), (64, 2), (65, 3), (130, 13), (200, 20), (257, 33), (320, 10)])
 def test_rankk_cov_ragged_shapes(ctx, p, k):
     """dense A A' + diag(s) (G = G0 G0', CovPostMean) at tile-edge sizes and ranks above one chunk."""
     import torch
@@ -248,6 +310,45 @@ def test_rankk_cov_ragged_shapes(ctx, p, k):
     ctx.synchronize()
     want = A @ A.T + np.diag(s)
     assert relerr_mat(out.cpu().numpy().T, want) < 1e-13
+
+
+# ---- f1: post-processing (mean + exact type-5 sample quantiles) -------------------------------------
+@pytest.mark.parametrize("MC", [1, 2, 7, 100, 1000, 1025])
+def test_post_processing_against_oracle(ctx, MC):
+    n, p, k = 40, 9, 2
+    Y, u, d, v = _svd_inputs(n, p, k, 41)
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=MC)
+    o = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.3, gam, z)
+    ref = orc.post_processing(o, 0.05)
+    got = fb.CPPCCFABLEPostProcessing(o, 0.05, ctx=ctx)
+    for key in ("PostMeanMatrix", "LowerQuantileMatrix", "UpperQuantileMatrix"):
+        assert relerr_mat(got[key], ref[key]) < TOL, key
+        assert np.array_equal(got[key], got[key].T)
+    sel = [3, 1, 9, 3]                     # 1-based, unsorted, with a repeated variable (index equality, cpp:770)
+    refs = orc.post_processing_submatrix(o, 0.1, sel)
+    gots = fb.CCFABLEPostProcessingSubmatrix(o, 0.1, sel, ctx=ctx)
+    for key in refs:
+        assert relerr_mat(gots[key], refs[key]) < TOL, key
+    with pytest.raises(fb.FableError):
+        fb.CCFABLEPostProcessingSubmatrix(o, 0.1, [0, 2], ctx=ctx)
+    with pytest.raises(fb.FableError):
+        fb.CCFABLEPostProcessingSubmatrix(o, 0.1, [2, p + 1], ctx=ctx)
+
+
+def test_coverage_pattern_of_the_replication_script(ctx):
+    """extras/replicationCodes/coverage_FABLE.R:95-130 in miniature: entry-wise 95% intervals from the GPU
+    sampler + post-processing cover the true covariance on a random sub-matrix at roughly the nominal rate."""
+    n, p, k, MC = 400, 300, 3, 600
+    Lambda0, Sigma0 = synth.truth(p, k, seed=1)
+    Psi0 = Lambda0 @ Lambda0.T + np.diag(Sigma0)
+    Y = synth.factor_data(n, p, k, rep=0)
+    out = fb.FABLEPosteriorSampler(Y, MC=MC, ctx=ctx)
+    assert out["estRank"] == k
+    sel = np.sort(np.random.default_rng(3).choice(p, 40, replace=False)) + 1
+    pp_ = fb.CCFABLEPostProcessingSubmatrix(out["CCFABLESamples"], 0.05, sel, ctx=ctx)
+    truth = Psi0[np.ix_(sel - 1, sel - 1)]
+    cover = np.mean((pp_["LowerQuantileMatrix"] <= truth) & (truth <= pp_["UpperQuantileMatrix"]))
+    assert 0.85 <= cover <= 1.0, cover
 
 
 # ---- DMMA GEMM + eigensolver primitives -------------------------------------------------------------
