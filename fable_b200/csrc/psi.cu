@@ -18,7 +18,8 @@
 //     128-byte-swizzled TMA boxes) and leaves the SM as two asynchronous TMA tensor stores
 //     (cp.async.bulk.tensor -> UTMASTG), so HBM writes drain while the warps already compute the
 //     next draw; every global run is a full, aligned 512-byte line group written exactly once;
-//   * the register accumulators reach HBM as TMA reduce-add stores (UTMAREDG), once per batch.
+//   * the HBM accumulators are read into the register accumulators when the CTA starts (latency hidden
+//     behind the first draw) and written back once per batch by TMA tensor stores.
 // Tile = 64 x 64, 256 threads = 8 warps as 2 (u) x 4 (v); warp tile 32 x 16 = 4 x 2 FP64 tensor-core
 // tiles (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no f64 kind), rank padded to a multiple
 // of 4 with zero rows.  DMMA runs at the DFMA rate on sm_100a but needs 6 fragment loads per 8 MMAs
@@ -199,7 +200,17 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         c[i][j][e] = 0.0;
-        if (ACC) { acc_s[i][j][e] = 0.0; acc_q[i][j][e] = 0.0; }
+        if (ACC) {
+          // the running HBM accumulators are loaded into the register accumulators up front: the loads
+          // are first needed when draw 0 is folded in, so their latency hides behind its math, and the
+          // batch ends with a plain store (no read-modify-write, no L2 atomics)
+          // (materialising kernels only: there the batch is store-bound and the loads are free; the
+          // accumulate-only kernel is FP64-bound and keeps zero-init + one TMA reduce-add per batch)
+          const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+          const bool in = MAT && u < p && v < p;
+          acc_s[i][j][e] = in ? __ldcs(a.acc_sum + v * p + u) : 0.0;
+          acc_q[i][j][e] = in ? __ldcs(a.acc_sq + v * p + u) : 0.0;
+        }
       }
 
   prefetch(0, 0);
@@ -314,9 +325,8 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   if (bulk && tid == 0) bulk_wait_read();             // staging must stay valid until the last stores have read it
 
   if (ACC && even) {
-    // one update of the HBM accumulators per batch (upper tiles only): the register accumulators are
-    // staged as two dense 64 x 64 boxes and added in L2 by TMA reduce stores, so no warp waits for a
-    // DRAM read behind the write stream
+    // one update of the HBM accumulators per batch (upper tiles only): the register accumulators
+    // (old value + batch) are staged as two swizzled tiles and leave as plain TMA tensor stores
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -332,42 +342,42 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
     __syncthreads();
     if (tid == 0) {
       if (a.tma_mode == 1) {
-        tma_reduce_add_tile(&tmap_sum, static_cast<int>(v0), static_cast<int>(u0 >> 4), D);
-        tma_reduce_add_tile(&tmap_sq, static_cast<int>(v0), static_cast<int>(u0 >> 4), M);
+        if (MAT) {
+          tma_store_tile(&tmap_sum, static_cast<int>(v0), static_cast<int>(u0 >> 4), 0, D, pol_stream);
+          tma_store_tile(&tmap_sq, static_cast<int>(v0), static_cast<int>(u0 >> 4), 0, M, pol_stream);
+        } else {
+          tma_reduce_add_tile(&tmap_sum, static_cast<int>(v0), static_cast<int>(u0 >> 4), D);
+          tma_reduce_add_tile(&tmap_sq, static_cast<int>(v0), static_cast<int>(u0 >> 4), M);
+        }
       } else {
         for (int q = 0; q < TILE / BOXW; ++q)
           if (u0 + q * BOXW < p) {
-            tma_reduce_add_subbox(&tmap_sum, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), D + q * BOX_DOUBLES);
-            tma_reduce_add_subbox(&tmap_sq, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), M + q * BOX_DOUBLES);
+            if (MAT) {
+              tma_store_subbox(&tmap_sum, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), 0, D + q * BOX_DOUBLES, pol_stream);
+              tma_store_subbox(&tmap_sq, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), 0, M + q * BOX_DOUBLES, pol_stream);
+            } else {
+              tma_reduce_add_subbox(&tmap_sum, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), D + q * BOX_DOUBLES);
+              tma_reduce_add_subbox(&tmap_sq, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), M + q * BOX_DOUBLES);
+            }
           }
       }
       bulk_commit();
       bulk_wait_read();
     }
   } else if (ACC) {
-    // odd p (no tensor maps): read-modify-write from the registers; loads batched ahead of the adds
+    // odd p (no tensor maps): the register accumulators hold old + batch (MAT) or the batch alone
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      double* __restrict__ dst = pass == 0 ? a.acc_sum : a.acc_sq;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
-            c[i][j][e] = (v < p && u < p) ? dst[v * p + u] : 0.0;
+        for (int e = 0; e < 2; ++e) {
+          const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+          if (v < p && u < p) {
+            if (MAT) { a.acc_sum[v * p + u] = acc_s[i][j][e]; a.acc_sq[v * p + u] = acc_q[i][j][e]; }
+            else { a.acc_sum[v * p + u] += acc_s[i][j][e]; a.acc_sq[v * p + u] += acc_q[i][j][e]; }
           }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
-            if (v < p && u < p) dst[v * p + u] = c[i][j][e] + (pass == 0 ? acc_s[i][j][e] : acc_q[i][j][e]);
-          }
-    }
+        }
   }
 }
 
