@@ -472,27 +472,79 @@ def dev_syevj(ctx, dG, m, dW, dQ):
 # ------------------------------------------------------------------------------------------------
 # a11: the two public wrappers (R/FABLE_wrapper.R)
 # ------------------------------------------------------------------------------------------------
-def FABLEPosteriorMean(Y, gamma0=1.0, delta0sq=1.0, maxProp=0.5, ctx=None):
+def FABLEPosteriorMean(Y, gamma0=1.0, delta0sq=1.0, maxProp=0.5, ctx=None, composed=False):
+    """R/FABLE_wrapper.R:80-128.  Default: one C-ABI call (fable_wrapper_posterior_mean: Y uploaded once,
+    everything resident); composed=True replays the wrapper's own sequence of exports."""
     t0 = time.perf_counter()                                             # wrapper:85
     Y = _F(Y, "Y")                                                       # as.matrix, wrapper:87
-    svdY = svd(Y, ctx)                                                   # wrapper:90
-    kMax = kmax_rule(svdY["d"], maxProp)                                 # wrapper:94
-    mod = CPPFABLEPostMean(Y, gamma0, delta0sq, svdY["u"], svdY["v"], svdY["d"], kMax, ctx)   # wrapper:102
-    return {"FABLEPostMean": mod["CovPostMean"], "svdY": svdY, "estRank": mod["kEst"],
+    if composed:
+        svdY = svd(Y, ctx)                                               # wrapper:90
+        kMax = kmax_rule(svdY["d"], maxProp)                             # wrapper:94
+        mod = CPPFABLEPostMean(Y, gamma0, delta0sq, svdY["u"], svdY["v"], svdY["d"], kMax, ctx)   # wrapper:102
+        Cov, kEst = mod["CovPostMean"], mod["kEst"]
+    else:
+        ctx = _ctx(ctx)
+        n, p = Y.shape
+        r = min(n, p)
+        U = np.empty((n, r), order="F"); d = np.empty(r); V = np.empty((p, r), order="F")
+        Cov = np.empty((p, p), order="F"); k = C.c_int(); kM = C.c_int()
+        ctx.check(_load().fable_wrapper_posterior_mean(ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0),
+                                                       C.c_double(delta0sq), C.c_double(maxProp), _ptr(Cov), C.byref(k),
+                                                       C.byref(kM), _ptr(U), _ptr(d), _ptr(V)))
+        svdY = {"d": d, "u": U, "v": V}; kEst = k.value
+    return {"FABLEPostMean": Cov, "svdY": svdY, "estRank": kEst,
             "runTime": time.perf_counter() - t0}                         # wrapper:121-124
 
 
-def FABLEPosteriorSampler(Y, gamma0=1.0, delta0sq=1.0, maxProp=0.95, MC=1000, ctx=None, gam=None, z=None):
+def FABLEPosteriorSampler(Y, gamma0=1.0, delta0sq=1.0, maxProp=0.95, MC=1000, ctx=None, gam=None, z=None,
+                          composed=False, want_G=True):
+    """R/FABLE_wrapper.R:12-68.  Default: fable_wrapper_sampler_begin + fable_posterior_sampler_outputs (Y
+    uploaded once, every intermediate resident).  Injected draws
+    (gam, z -- z may be a callable (MC, k, p) -> array because k is only known after the rank search) or
+    composed=True replay the wrapper's own sequence of exports."""
     t0 = time.perf_counter()                                             # wrapper:18
     Y = _F(Y, "Y")
-    svdY = svd(Y, ctx)                                                   # wrapper:23
-    U, V, d = svdY["u"], svdY["v"], svdY["d"]
-    kMax = kmax_rule(d, maxProp)                                         # wrapper:27
-    kEst = CPPRankEstimator(Y, U, V, d, kMax, ctx)                       # wrapper:29
-    hyp = FABLEHyperParameters(Y, U, V, d, kEst, ctx)                    # wrapper:35
-    # wrapper:41-44 -- cov_correct_matrix + (sum(B)/(p(p+1)/2))^2, fused: B is never stored
-    varInfl = var_inflation(hyp["SigmaSqEstimate"], hyp["G0"], "wrapper", ctx)
-    zz = z(MC, kEst, Y.shape[1]) if callable(z) else z
-    smp = CPPFABLESampler(Y, gamma0, delta0sq, MC, U, V, d, kEst, varInfl, ctx, gam=gam, z=zz)   # wrapper:46
+    if composed or gam is not None or z is not None:
+        svdY = svd(Y, ctx)                                               # wrapper:23
+        U, V, d = svdY["u"], svdY["v"], svdY["d"]
+        kMax = kmax_rule(d, maxProp)                                     # wrapper:27
+        kEst = CPPRankEstimator(Y, U, V, d, kMax, ctx)                   # wrapper:29
+        hyp = FABLEHyperParameters(Y, U, V, d, kEst, ctx, want_G=want_G)  # wrapper:35
+        # wrapper:41-44 -- cov_correct_matrix + (sum(B)/(p(p+1)/2))^2, fused: B is never stored
+        varInfl = var_inflation(hyp["SigmaSqEstimate"], hyp["G0"], "wrapper", ctx)
+        zz = z(MC, kEst, Y.shape[1]) if callable(z) else z
+        smp = CPPFABLESampler(Y, gamma0, delta0sq, MC, U, V, d, kEst, varInfl, ctx, gam=gam, z=zz, want_G=want_G)   # wrapper:46
+    else:
+        ctx = _ctx(ctx)
+        n, p = Y.shape
+        r = min(n, p)
+        MC = int(MC)
+        if MC < 1:
+            raise FableError(1, "MC must be >= 1")
+        U = np.empty((n, r), order="F"); d = np.empty(r); V = np.empty((p, r), order="F")
+        k = C.c_int(); kM = C.c_int(); htau = C.c_double(); vi = C.c_double(); tau = C.c_double()
+        hsig = np.empty(p); hG0 = np.empty((p, r), order="F")            # first kEst columns are written
+        hG = np.empty((p, p), order="F") if want_G else None
+        G = np.empty((p, p), order="F") if want_G else None
+        # step 1 (wrapper:20-44): everything up to varInflation, row posterior left resident
+        ph = C.c_void_p()
+        ctx.check(_load().fable_wrapper_sampler_begin(
+            ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq), C.c_double(maxProp),
+            _ptr(U), _ptr(d), _ptr(V), C.byref(kM), C.byref(k), _ptr(hsig), _ptr(hG0), C.byref(htau), _ptr(hG), C.byref(vi),
+            C.byref(ph)))
+        kEst = k.value; varInfl = vi.value
+        hyp = {"SigmaSqEstimate": hsig, "G": hG, "EstimatedRank": kEst,
+               "G0": np.asfortranarray(hG0.reshape(-1, order="F")[: p * kEst].reshape((p, kEst), order="F")),
+               "tauSqEstimate": htau.value}
+        svdY = {"d": d, "u": U, "v": V}
+        # step 2 (wrapper:46-54): the caller sizes LambdaSamples now that k is known
+        L = np.empty((MC, kEst * p), order="F"); S = np.empty((MC, p), order="F"); pm = np.empty(p); pi = np.empty(p)
+        try:
+            ctx.check(_load().fable_posterior_sampler_outputs(ph, _i64(MC), _i64(0), None, None, _ptr(L), _ptr(S), _ptr(pm),
+                                                              _ptr(pi), C.byref(tau), _ptr(G), None, None))
+        finally:
+            _load().fable_posterior_destroy(ph)
+        smp = {"LambdaSamples": L, "SigmaSqSamples": S, "SigmaSqEstimatePostMean": pm, "SigmaSqEstimatePlugIn": pi,
+               "EstimatedRank": kEst, "VarianceInflation": varInfl, "tauSqEstimate": tau.value, "G": G}
     return {"CCFABLESamples": smp, "FABLEHyperParameters": hyp, "svdY": svdY, "estRank": kEst,
             "varInflation": varInfl, "runTime": time.perf_counter() - t0}   # wrapper:59-64

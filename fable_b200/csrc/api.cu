@@ -197,6 +197,27 @@ struct fable_posterior {
   int64_t tile_begin = 0, tile_end = 0;
 };
 
+// row posterior (shrunk G0, cpp:564-597) from inputs already resident in HBM
+static int posterior_from_inputs(fable_ctx* ctx, const Inputs& in, double gamma0, double delta0sq, int kEst,
+                                 double varInflation, fable_posterior** out) {
+  FB_REQUIRE(ctx, varInflation >= 0.0 && std::isfinite(varInflation), "varInflation must be finite and >= 0");
+  FB_REQUIRE(ctx, gamma0 + static_cast<double>(in.n) > 2.0, "gamma0 + n must exceed 2");
+  fable_posterior* post = new (std::nothrow) fable_posterior();
+  if (!post) return ctx->fail(FABLE_ERR_NOMEM, "out of host memory");
+  post->ctx = ctx; post->n = in.n; post->p = in.p; post->pp = round_up(in.p, 64); post->k = kEst;
+  post->KP = static_cast<int>(round_up(kEst, 4));
+  post->gamma0 = gamma0; post->delta0sq = delta0sq; post->varInflation = varInflation;
+  const int rc = row_posterior(ctx, in, kEst, gamma0, delta0sq, /*shrunk=*/1, post->rp);
+  if (rc != FABLE_OK) { delete post; return rc; }
+  post->a_n = std::sqrt(varInflation) / std::sqrt(post->rp.w);                 // cpp:597
+  *out = post;
+  return FABLE_OK;
+}
+
+static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_inj, const double* z_inj, int64_t m0,
+                           double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
+                           double* tausq, double* G, double* psi_sum, double* psi_sumsq);
+
 extern "C" {
 
 int fable_abi_version(void) { return FABLE_B200_ABI_VERSION; }
@@ -460,19 +481,9 @@ int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p
   FB_REQUIRE(ctx, out, "posterior_create: NULL out");
   *out = nullptr;
   FB_REQUIRE(ctx, kEst >= 1 && kEst <= r, "kEst must be in 1..length(svalsY)");
-  FB_REQUIRE(ctx, varInflation >= 0.0 && std::isfinite(varInflation), "varInflation must be finite and >= 0");
-  FB_REQUIRE(ctx, gamma0 + static_cast<double>(n) > 2.0, "gamma0 + n must exceed 2");
   Inputs in;
   FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kEst, in));
-  fable_posterior* post = new (std::nothrow) fable_posterior();
-  if (!post) return ctx->fail(FABLE_ERR_NOMEM, "out of host memory");
-  post->ctx = ctx; post->n = n; post->p = p; post->pp = round_up(p, 64); post->k = kEst; post->KP = static_cast<int>(round_up(kEst, 4));
-  post->gamma0 = gamma0; post->delta0sq = delta0sq; post->varInflation = varInflation;
-  int rc = row_posterior(ctx, in, kEst, gamma0, delta0sq, /*shrunk=*/1, post->rp);
-  if (rc != FABLE_OK) { delete post; return rc; }
-  post->a_n = std::sqrt(varInflation) / std::sqrt(post->rp.w);                 // cpp:597
-  *out = post;
-  return FABLE_OK;
+  return posterior_from_inputs(ctx, in, gamma0, delta0sq, kEst, varInflation, out);
 }
 
 void fable_posterior_destroy(fable_posterior* post) {
@@ -650,6 +661,19 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
   fable_posterior* post = nullptr;
   FB_TRY(fable_posterior_create(ctx, Y, n, p, gamma0, delta0sq, U, V, d, r, kEst, varInflation, &post));
   struct Guard { fable_posterior* p; ~Guard() { fable_posterior_destroy(p); } } guard{post};
+  return sampler_outputs(post, MC, gam_inj, z_inj, m0, LambdaSamples, SigmaSqSamples, SigmaPostMean, SigmaPlugIn, tausq, G,
+                         psi_sum, psi_sumsq);
+}
+
+}  // extern "C"
+
+// everything CPPFABLESampler returns (cpp:599-627) from a resident row posterior
+static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_inj, const double* z_inj, int64_t m0,
+                           double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
+                           double* tausq, double* G, double* psi_sum, double* psi_sumsq) {
+  fable_ctx* ctx = post->ctx;
+  const int64_t p = post->p;
+  const int kEst = post->k;
   FB_TRY(download(ctx, SigmaPostMean, post->rp.sigmahat.d(), p));              // cpp:622
   FB_TRY(download(ctx, SigmaPlugIn, post->rp.sig.d(), p));                     // cpp:623
   if (tausq) *tausq = post->rp.tausq;                                          // cpp:626
@@ -697,6 +721,109 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
   }
   if (psi_sum) FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
   if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), p, nullptr, p, kEst, G));   // cpp:627
+  return FABLE_OK;
+}
+
+// ---- a11: the two R wrappers as single calls (Y crosses PCIe once, nothing round-trips) -------------
+namespace {
+struct Pipeline {
+  Inputs in;          // Y plus the FULL thin SVD, resident
+  std::vector<double> d;
+  int kMax = 0;
+};
+
+// R/FABLE_wrapper.R:20-27 == :87-94: as.matrix, svd(Y), kMax rule
+int pipeline_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double maxProp, Pipeline& pl, double* U,
+                 double* dOut, double* V) {
+  FB_REQUIRE(ctx, Y && n >= 1 && p >= 1, "Y must be a non-empty matrix");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t r = n < p ? n : p;
+  Inputs& in = pl.in;
+  in.n = n; in.p = p; in.r = r; in.kcols = static_cast<int>(r);
+  FB_TRY(upload(ctx, in.Y, Y, static_cast<size_t>(n) * p));
+  FB_CUDA(ctx, in.U.alloc(static_cast<size_t>(n) * r * sizeof(double)));
+  FB_CUDA(ctx, in.V.alloc(static_cast<size_t>(p) * r * sizeof(double)));
+  FB_CUDA(ctx, in.d.alloc(static_cast<size_t>(r) * sizeof(double)));
+  FB_TRY(fb_svd(ctx, in.Y.d(), n, p, in.U.d(), in.d.d(), in.V.d()));
+  pl.d.resize(r);
+  FB_TRY(download(ctx, pl.d.data(), in.d.d(), r));
+  FB_TRY(download(ctx, U, in.U.d(), static_cast<size_t>(n) * r));
+  FB_TRY(download(ctx, V, in.V.d(), static_cast<size_t>(p) * r));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (dOut) std::memcpy(dOut, pl.d.data(), r * sizeof(double));
+  if (fable_kmax(pl.d.data(), r, maxProp, &pl.kMax) != FABLE_OK)
+    return ctx->fail(FABLE_ERR_INVALID, "kMax rule: no index reaches maxProp");       // R: min(integer(0)) -> Inf
+  return FABLE_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
+                                 double maxProp, double* Cov, int* kEst, int* kMaxOut, double* U, double* d, double* V) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, kEst, "posterior_mean: NULL kEst");
+  Pipeline pl;
+  FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:87-94
+  if (kMaxOut) *kMaxOut = pl.kMax;
+  int k = 1;
+  FB_TRY(rank_dev(ctx, pl.in, pl.kMax, &k));                                     // cpp:457
+  RowPosterior rp;
+  FB_TRY(row_posterior(ctx, pl.in, k, gamma0, delta0sq, /*shrunk=*/1, rp));
+  *kEst = k;
+  if (Cov) FB_TRY(rankk_cov_to_host(ctx, rp.G0.d(), p, rp.sigmahat.d(), p, k, Cov));   // cpp:491, 509-512
+  return FABLE_OK;
+}
+
+// wrapper:20-44 on the device: SVD, kMax, rank search, hyper-parameters, varInflation; leaves the (shrunk) row
+// posterior of wrapper:46-54 resident in *out
+int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
+                                double maxProp, double* U, double* d, double* V, int* kMaxOut, int* kEstOut,
+                                double* hypSigma, double* hypG0, double* hypTau, double* hypG, double* varInflationOut,
+                                fable_posterior** out) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, out, "sampler_begin: NULL out");
+  *out = nullptr;
+  Pipeline pl;
+  FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:20-27
+  if (kMaxOut) *kMaxOut = pl.kMax;
+  int k = 1;
+  FB_TRY(rank_dev(ctx, pl.in, pl.kMax, &k));                                     // wrapper:29-33
+  if (kEstOut) *kEstOut = k;
+  double vi = 0.0;
+  {
+    RowPosterior hyp;                                                            // wrapper:35-39 (unshrunk G0, cpp:390)
+    FB_TRY(row_posterior(ctx, pl.in, k, 1.0, 1.0, /*shrunk=*/0, hyp));
+    FB_TRY(download(ctx, hypSigma, hyp.sig.d(), p));
+    FB_TRY(download(ctx, hypG0, hyp.G0.d(), static_cast<size_t>(p) * k));
+    if (hypTau) *hypTau = hyp.tausq;
+    double su, sd;                                                               // wrapper:41-44, B never stored
+    FB_TRY(fb_var_inflation(ctx, hyp.sig.d(), hyp.G0.d(), p, p, k, &su, &sd));
+    FB_TRY(var_inflation_from_sums(su, sd, p, /*variant=*/0, &vi));
+    if (hypG) FB_TRY(rankk_cov_to_host(ctx, hyp.G0.d(), p, nullptr, p, k, hypG));     // cpp:391
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (varInflationOut) *varInflationOut = vi;
+  return posterior_from_inputs(ctx, pl.in, gamma0, delta0sq, k, vi, out);        // wrapper:46-54, cpp:553-597
+}
+
+int fable_posterior_sampler_outputs(fable_posterior* post, int64_t MC, int64_t m0, const double* gam_inj,
+                                    const double* z_inj, double* LambdaSamples, double* SigmaSqSamples,
+                                    double* SigmaPostMean, double* SigmaPlugIn, double* tausq, double* G, double* psi_sum,
+                                    double* psi_sumsq) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, MC >= 1, "MC must be >= 1");
+  FB_REQUIRE(ctx, (gam_inj == nullptr) == (z_inj == nullptr), "injected draws need both gam and z");
+  FB_REQUIRE(ctx, (psi_sum == nullptr) == (psi_sumsq == nullptr), "psi_sum and psi_sumsq go together");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sampler_outputs(post, MC, gam_inj, z_inj, m0, LambdaSamples, SigmaSqSamples, SigmaPostMean, SigmaPlugIn, tausq, G,
+                         psi_sum, psi_sumsq);
+}
+
+int fable_posterior_rank(fable_posterior* post, int* k) {
+  if (!post || !k) return FABLE_ERR_INVALID;
+  *k = post->k;
   return FABLE_OK;
 }
 

@@ -130,6 +130,31 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
                   double* SigmaPostMean, double* SigmaPlugIn, double* tausq, double* G,
                   double* psi_sum, double* psi_sumsq);
 
+/* ---- a11: the two R wrappers as single calls -----------------------------------------------------------
+ * FABLEPosteriorMean (R/FABLE_wrapper.R:80-128) and FABLEPosteriorSampler (:12-68) run svd(Y) -> kMax rule ->
+ * CPP* exports, passing Y, U, V back and forth.  These entry points run the same sequence with Y uploaded
+ * once and every intermediate resident in HBM; the Rcpp layer unpacks the outputs into the wrappers'
+ * unchanged return lists.  U n x r, d r, V p x r (r = min(n,p)) are the `svdY` element; any output pointer
+ * may be NULL to skip it (kEst is required).  varInflation follows the wrapper's formula (:41-44).
+ * hyp* = FABLEHyperParameters' list (unshrunk G0; hypG0 must hold p x min(n,p) doubles, the first
+ * kEst columns are written). */
+int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
+                                 double delta0sq, double maxProp, double* Cov, int* kEst, int* kMax,
+                                 double* U, double* d, double* V);
+/* FABLEPosteriorSampler in two steps, because R must size LambdaSamples (MC x k p) after the rank is
+ * known: begin = wrapper:20-44 (svd, kMax, rank, FABLEHyperParameters, varInflation) and leaves the row
+ * posterior of CPPFABLESampler (:553-597) resident; fable_posterior_sampler_outputs then produces
+ * everything CPPFABLESampler returns (:599-627) -- same outputs as fable_sampler -- from that handle. */
+int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
+                                double delta0sq, double maxProp, double* U, double* d, double* V, int* kMax,
+                                int* kEst, double* hypSigma, double* hypG0, double* hypTau, double* hypG,
+                                double* varInflation, fable_posterior** post);
+int fable_posterior_sampler_outputs(fable_posterior* post, int64_t MC, int64_t m0, const double* gam_inj,
+                                    const double* z_inj, double* LambdaSamples, double* SigmaSqSamples,
+                                    double* SigmaPostMean, double* SigmaPlugIn, double* tausq, double* G,
+                                    double* psi_sum, double* psi_sumsq);
+int fable_posterior_rank(fable_posterior* post, int* k);
+
 /* ---- f1: CPPCCFABLEPostProcessing (:631-713) / CCFABLEPostProcessingSubmatrix(_Optimized) (:716-893) ---
  * Entry-wise posterior mean and (alpha/2, 1-alpha/2) sample quantiles (Armadillo quantile, type 5) of
  * Psi over the stored draws, on the variables `selected` (1-based R indices, length S; NULL = all p).

@@ -199,6 +199,48 @@ Rcpp::List CPPsvd(Rcpp::NumericMatrix X, int flag) {
   return Rcpp::List::create(Rcpp::Named("U") = U, Rcpp::Named("d") = d, Rcpp::Named("V") = V);
 }
 
+// NEW: FABLEPosteriorSampler / FABLEPosteriorMean as pipelines with Y uploaded once (a11).  The R wrappers
+// may call these instead of the export sequence; the returned lists have the wrappers' element names.
+// [[Rcpp::export]]
+Rcpp::List FABLEPosteriorSamplerB200(Rcpp::NumericMatrix Y, double gamma0, double delta0sq, double maxProp, int MC) {
+  const int64_t n = Y.nrow(), p = Y.ncol(), r = n < p ? n : p;
+  reseed();
+  Rcpp::NumericMatrix U(n, r), V(p, r), hG0full(p, r), hG(p, p), G(p, p);
+  Rcpp::NumericVector d(r), hsig(p), pm(p), plug(p);
+  int kMax = 0, k = 0;
+  double htau = 0.0, vi = 0.0, tau = 0.0;
+  fable_posterior* post = nullptr;
+  check(fable_wrapper_sampler_begin(ctx(), Y.begin(), n, p, gamma0, delta0sq, maxProp, U.begin(), d.begin(), V.begin(), &kMax,
+                                    &k, hsig.begin(), hG0full.begin(), &htau, hG.begin(), &vi, &post));
+  Rcpp::NumericMatrix L(MC, static_cast<int>(k * p)), S(MC, static_cast<int>(p));   // sized now that k is known
+  const int rc = fable_posterior_sampler_outputs(post, MC, 0, nullptr, nullptr, L.begin(), S.begin(), pm.begin(), plug.begin(),
+                                                 &tau, G.begin(), nullptr, nullptr);
+  fable_posterior_destroy(post);
+  check(rc);
+  Rcpp::NumericMatrix hG0 = hG0full(Rcpp::_, Rcpp::Range(0, k - 1));
+  Rcpp::List samples = Rcpp::List::create(Rcpp::Named("LambdaSamples") = L, Rcpp::Named("SigmaSqSamples") = S,
+                                          Rcpp::Named("SigmaSqEstimatePostMean") = pm, Rcpp::Named("SigmaSqEstimatePlugIn") = plug,
+                                          Rcpp::Named("EstimatedRank") = k, Rcpp::Named("VarianceInflation") = vi,
+                                          Rcpp::Named("tauSqEstimate") = tau, Rcpp::Named("G") = G);
+  Rcpp::List hyp = Rcpp::List::create(Rcpp::Named("SigmaSqEstimate") = hsig, Rcpp::Named("G") = hG, Rcpp::Named("EstimatedRank") = k,
+                                      Rcpp::Named("G0") = hG0, Rcpp::Named("tauSqEstimate") = htau);
+  Rcpp::List svdY = Rcpp::List::create(Rcpp::Named("d") = d, Rcpp::Named("u") = U, Rcpp::Named("v") = V);
+  return Rcpp::List::create(Rcpp::Named("CCFABLESamples") = samples, Rcpp::Named("FABLEHyperParameters") = hyp,
+                            Rcpp::Named("svdY") = svdY, Rcpp::Named("estRank") = k, Rcpp::Named("varInflation") = vi);
+}
+
+// [[Rcpp::export]]
+Rcpp::List FABLEPosteriorMeanB200(Rcpp::NumericMatrix Y, double gamma0, double delta0sq, double maxProp) {
+  const int64_t n = Y.nrow(), p = Y.ncol(), r = n < p ? n : p;
+  Rcpp::NumericMatrix U(n, r), V(p, r), Cov(p, p);
+  Rcpp::NumericVector d(r);
+  int k = 0, kMax = 0;
+  check(fable_wrapper_posterior_mean(ctx(), Y.begin(), n, p, gamma0, delta0sq, maxProp, Cov.begin(), &k, &kMax, U.begin(),
+                                     d.begin(), V.begin()));
+  Rcpp::List svdY = Rcpp::List::create(Rcpp::Named("d") = d, Rcpp::Named("u") = U, Rcpp::Named("v") = V);
+  return Rcpp::List::create(Rcpp::Named("FABLEPostMean") = Cov, Rcpp::Named("svdY") = svdY, Rcpp::Named("estRank") = k);
+}
+
 // NEW: drop-in for base-R svd(Y) as the wrappers use it (R/FABLE_wrapper.R:23-26, 90-93): list(d, u, v)
 // [[Rcpp::export]]
 Rcpp::List FABLEsvd(Rcpp::NumericMatrix Y) {

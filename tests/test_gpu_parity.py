@@ -134,6 +134,19 @@ def test_c1_wrappers_end_to_end(ctx, c1):
     gam, zfull = synth.injected_draws(MC, p, 10, 0.5 * (1.0 + Y.shape[0]), seed=777)
     refs = orc.FABLEPosteriorSampler(Y, MC=MC, gam=gam, z=zfull)
     gots = fb.FABLEPosteriorSampler(Y, MC=MC, ctx=ctx, gam=gam, z=zfull)
+    # the single-upload pipeline (native draws) returns the same estimation outputs as the composed wrapper
+    pipe = fb.FABLEPosteriorSampler(Y, MC=50, ctx=ctx)
+    assert pipe["estRank"] == gots["estRank"] and abs(pipe["varInflation"] / gots["varInflation"] - 1) < 1e-13
+    assert relerr_vec(pipe["svdY"]["d"], gots["svdY"]["d"]) < 1e-14
+    for key in ("SigmaSqEstimate", "G0", "G"):
+        assert relerr_mat(pipe["FABLEHyperParameters"][key], gots["FABLEHyperParameters"][key]) < 1e-13, key
+    assert relerr_mat(pipe["CCFABLESamples"]["G"], a_G := gots["CCFABLESamples"]["G"]) < 1e-13
+    ctx.set_seed(12345)
+    nat = fb.CPPFABLESampler(Y, 1.0, 1.0, 50, pipe["svdY"]["u"], pipe["svdY"]["v"], pipe["svdY"]["d"], 10, pipe["varInflation"], ctx=ctx, want_G=False)
+    np.testing.assert_array_equal(pipe["CCFABLESamples"]["SigmaSqSamples"], nat["SigmaSqSamples"])
+    assert relerr_mat(pipe["CCFABLESamples"]["LambdaSamples"], nat["LambdaSamples"]) < 1e-12
+    pm1 = fb.FABLEPosteriorMean(Y, ctx=ctx); pm2 = fb.FABLEPosteriorMean(Y, ctx=ctx, composed=True)
+    assert pm1["estRank"] == pm2["estRank"] and relerr_mat(pm1["FABLEPostMean"], pm2["FABLEPostMean"]) < 1e-13
     assert gots["estRank"] == refs["estRank"] == 10
     assert abs(gots["varInflation"] / refs["varInflation"] - 1) < TOL
     a, b = gots["CCFABLESamples"], refs["CCFABLESamples"]
