@@ -6,7 +6,8 @@
  *   (2) as the timed CPU baseline ("port", all host threads via OpenMP) in bench.py.
  * The product library (libfable_b200.so) never links or calls this file.
  *
- * PARITY UNPINNED: the reference has no tests / golden vectors and cannot be compiled here.
+ * Pinning: see oracle/fable_oracle.py (this twin is checked against it, and it against the reference's
+ * own translation unit compiled with the stand-ins of oracle/shim/).
  *
  * It also holds the CPU statement of the library's OWN random-number specification
  * ("fable-philox-v1"): the reference's R/Armadillo stream cannot be reproduced, so

@@ -6,10 +6,16 @@ every function cites the reference file:line it follows.  Only `tests/`,
 `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import it.
 The product (`fable_b200`) never does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures and
-cannot be built in this image (no R / Rcpp / Armadillo / system LAPACK), so this oracle is pinned
-only by (i) the analytic known answers of SURVEY.md App. A.6 (tests/test_oracle.py) and (ii) the
-self-generated frozen fixtures under tests/golden/ (made by tests/golden/make_golden.py).
+PINNING.  The reference ships no tests, golden vectors or fixtures and cannot be built
+as an R package in this image (no R / Rcpp / Armadillo / system LAPACK).  Its single translation unit,
+src/updated-FABLE-functions.cpp, IS however compiled here where it lies, against a minimal stand-in for the
+Armadillo/Rcpp subset it uses (oracle/shim/, oracle/ref_bridge.cpp -> oracle/_ref/libfable_ref.so), and
+tests/test_reference_source.py checks this restatement and the frozen fixtures against it to 1e-12:
+formulas, index conventions, bisection control flow, list layouts, quantile interpolation and the
+random-draw consumption order are therefore pinned to the reference's own function bodies.  What remains
+UNPINNED is the third-party arithmetic under them (Armadillo expression evaluation order, LAPACK dgesdd,
+R's RNG streams), restated from published definitions.  Further anchors: the analytic known answers of
+SURVEY.md App. A.6 (tests/test_oracle.py) and the frozen fixtures under tests/golden/.
 
 Third-party arithmetic the reference delegates and that is restated here from its published
 definition (none of it is under /root/reference, versions unpinned in DESCRIPTION:10-11):

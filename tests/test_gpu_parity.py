@@ -74,6 +74,34 @@ def test_golden_sampler_injected(ctx, golden, name):
     assert out["EstimatedRank"] == kEst and out["VarianceInflation"] == float(g("vi_wrapper"))
 
 
+def test_gpu_against_the_reference_source(ctx):
+    """The CUDA path against the reference's OWN translation unit (oracle/_ref, compiled with the shim):
+    rank, hyper-parameters, posterior mean and the sampler with injected draws."""
+    from oracle import ref_oracle as ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libfable_ref.so not present")
+    n, p, k, MC = 70, 150, 3, 9
+    Y, u, d, v = _svd_inputs(n, p, k, 61)
+    kMax = orc.kmax_rule(d, 0.95)
+    assert fb.CPPRankEstimator(Y, u, v, d, kMax, ctx=ctx) == ref.rank_estimator(Y, u, v, d, kMax)
+    for kk in (1, 7, 40):
+        assert abs(fb.CPPCriterionFunction(kk, Y, u, v, d, ctx=ctx) / ref.criterion(kk, Y, u, v, d) - 1) < TOL
+    hg, hr = fb.FABLEHyperParameters(Y, u, v, d, k, ctx=ctx), ref.hyper_parameters(Y, u, v, d, k)
+    assert relerr_mat(hg["G"], hr["G"]) < TOL and relerr_vec(hg["SigmaSqEstimate"], hr["SigmaSqEstimate"]) < TOL
+    assert relerr_vec(fb.CPPcov_correct_matrix(hr["SigmaSqEstimate"], hr["G"], ctx=ctx), ref.cov_correct_matrix(hr["SigmaSqEstimate"], hr["G"])) < TOL
+    pg, pr = fb.CPPFABLEPostMean(Y, 1.5, 0.7, u, v, d, kMax, ctx=ctx), ref.post_mean(Y, 1.5, 0.7, u, v, d, kMax)
+    assert pg["kEst"] == pr["kEst"] and relerr_mat(pg["CovPostMean"], pr["CovPostMean"]) < TOL
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.5 + n), seed=8)
+    sg = fb.CPPFABLESampler(Y, 1.5, 0.7, MC, u, v, d, k, 1.31, ctx=ctx, gam=gam, z=z)
+    sr = ref.sampler(Y, 1.5, 0.7, MC, u, v, d, k, 1.31, gam, z)
+    for key in ("LambdaSamples", "SigmaSqSamples", "SigmaSqEstimatePostMean", "SigmaSqEstimatePlugIn", "G"):
+        assert relerr_mat(sg[key], sr[key]) < TOL, key
+    ppg = fb.CCFABLEPostProcessingSubmatrix(sg, 0.05, [2, 9, 9, 40], ctx=ctx)
+    ppr = ref.post_processing(sr, 0.05, [2, 9, 9, 40])
+    for key in ppr:
+        assert relerr_mat(ppg[key], ppr[key]) < TOL, key
+
+
 # ---- SVD replacement (a1): sign-invariant comparison + decomposition properties -------------------
 @pytest.mark.parametrize("n,p,k", [(40, 120, 3), (64, 48, 2), (33, 77, 4), (200, 1000, 5), (300, 130, 4), (1, 5, 1), (5, 1, 1)])
 def test_svd_against_lapack(ctx, n, p, k):
