@@ -329,7 +329,7 @@ def run_b200(args, w, wname):
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(wname)
+                traffic = json.load(open(tpath)).get(wname)      # GB per launch, from the committed ncu capture
             except Exception:
                 traffic = None
         line = {
@@ -346,8 +346,8 @@ def run_b200(args, w, wname):
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
             "roofline": {"bound": "hbm", "kernel": "k_psi<MAT,ACC>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu)", "peak_source": peak_src,
+                         "algorithmic_gb_per_launch": alg_bytes_per_launch / 1e9, "avg_launch_ms": avg_launch_s * 1e3,
                          "launches_timed": int(kern_launches), "kernel_share_of_step": kern_ms / max(dev_ms - allreduce_ms, 1e-9)},
             "accumulate_only_samples_per_s_per_gpu": acc_only,
             "stages": stages,
