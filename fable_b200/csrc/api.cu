@@ -4,9 +4,11 @@
 // src/updated-FABLE-functions.cpp:215-341) is replayed here verbatim on criterion values computed
 // on the device.  No CPU arithmetic fallback exists for any matrix-sized quantity.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
+#include <thread>
 
 #include "common.cuh"
 
@@ -165,9 +167,68 @@ int row_posterior(fable_ctx* ctx, const Inputs& in, int k, double gamma0, double
   return FABLE_OK;
 }
 
+// Device -> host.  Results land in caller memory, which under R is PAGEABLE: a plain cudaMemcpy then runs
+// at ~6 GB/s (the driver stages through one pinned buffer on one thread).  Large copies into pageable
+// memory are therefore pipelined by hand: 64 MB chunks go D2H into two pinned staging buffers on the
+// context's stream while host threads copy the previous chunk out in parallel.  Pinned destinations
+// (bench.py's e2e buffers) and small copies take the plain asynchronous path.
+constexpr size_t kStageBytes = size_t(64) << 20;
+constexpr size_t kFastCopyMin = size_t(16) << 20;
+
+void parallel_memcpy(char* dst, const char* src, size_t bytes, int nthreads) {
+  if (nthreads <= 1 || bytes < (size_t(4) << 20)) { std::memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((bytes + nthreads - 1) / nthreads + 4095) & ~size_t(4095);
+  for (int t = 0; t < nthreads; ++t) {
+    const size_t off = per * t;
+    if (off >= bytes) break;
+    const size_t len = bytes - off < per ? bytes - off : per;
+    th.emplace_back([=] { std::memcpy(dst + off, src + off, len); });
+  }
+  for (auto& x : th) x.join();
+}
+
+bool is_pageable(const void* h) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
 int download(fable_ctx* ctx, double* h, const double* dptr, size_t count) {
   if (!h) return FABLE_OK;
-  FB_CUDA(ctx, cudaMemcpyAsync(h, dptr, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t bytes = count * sizeof(double);
+  if (bytes < kFastCopyMin || !is_pageable(h)) {
+    FB_CUDA(ctx, cudaMemcpyAsync(h, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return FABLE_OK;
+  }
+  for (int s = 0; s < 2; ++s)
+    if (!ctx->stage[s]) {
+      FB_CUDA(ctx, cudaHostAlloc(&ctx->stage[s], kStageBytes, cudaHostAllocDefault));
+      FB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[s], cudaEventDisableTiming));
+    }
+  unsigned hw = std::thread::hardware_concurrency();
+  int nthreads = hw >= 16 ? 8 : (hw >= 4 ? static_cast<int>(hw / 2) : 1);
+  if (const char* e = getenv("FABLE_B200_COPY_THREADS")) nthreads = atoi(e);
+  if (nthreads <= 0) {                 // 0: leave the copy to the driver
+    FB_CUDA(ctx, cudaMemcpyAsync(h, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return FABLE_OK;
+  }
+  const char* src = reinterpret_cast<const char*>(dptr);
+  char* dst = reinterpret_cast<char*>(h);
+  const size_t nchunks = (bytes + kStageBytes - 1) / kStageBytes;
+  auto issue = [&](size_t i) -> cudaError_t {
+    const size_t off = i * kStageBytes, len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+    cudaError_t e = cudaMemcpyAsync(ctx->stage[i & 1], src + off, len, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(ctx->stage_ev[i & 1], ctx->stream);
+  };
+  FB_CUDA(ctx, issue(0));
+  for (size_t i = 0; i < nchunks; ++i) {
+    if (i + 1 < nchunks) FB_CUDA(ctx, issue(i + 1));           // next chunk crosses PCIe while this one is copied out
+    FB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[i & 1]));
+    const size_t off = i * kStageBytes, len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+    parallel_memcpy(dst + off, static_cast<const char*>(ctx->stage[i & 1]), len, nthreads);
+  }
   return FABLE_OK;
 }
 
@@ -259,6 +320,10 @@ void fable_ctx_destroy(fable_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ring) cudaFree(ctx->ring);
+  for (int s = 0; s < 2; ++s) {
+    if (ctx->stage[s]) cudaFreeHost(ctx->stage[s]);
+    if (ctx->stage_ev[s]) cudaEventDestroy(ctx->stage_ev[s]);
+  }
   if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -593,12 +658,16 @@ int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64
     const int64_t nj = p - j0 < nj_max ? p - j0 : nj_max;
     FB_TRY(fb_sample_ref(ctx, sa, m0, MC, j0, nj, MC, LambdaSamples ? dL.d() : nullptr,
                          SigmaSqSamples ? dS.d() : nullptr));
-    if (LambdaSamples)
-      FB_CUDA(ctx, cudaMemcpy2DAsync(LambdaSamples + ldm * (j0 * k), ldm * sizeof(double), dL.d(), MC * sizeof(double),
-                                     MC * sizeof(double), nj * k, cudaMemcpyDeviceToHost, ctx->stream));
-    if (SigmaSqSamples)
-      FB_CUDA(ctx, cudaMemcpy2DAsync(SigmaSqSamples + ldm * j0, ldm * sizeof(double), dS.d(), MC * sizeof(double),
-                                     MC * sizeof(double), nj, cudaMemcpyDeviceToHost, ctx->stream));
+    if (LambdaSamples) {
+      if (ldm == MC) FB_TRY(download(ctx, LambdaSamples + ldm * (j0 * k), dL.d(), static_cast<size_t>(MC) * nj * k));
+      else FB_CUDA(ctx, cudaMemcpy2DAsync(LambdaSamples + ldm * (j0 * k), ldm * sizeof(double), dL.d(), MC * sizeof(double),
+                                          MC * sizeof(double), nj * k, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (SigmaSqSamples) {
+      if (ldm == MC) FB_TRY(download(ctx, SigmaSqSamples + ldm * j0, dS.d(), static_cast<size_t>(MC) * nj));
+      else FB_CUDA(ctx, cudaMemcpy2DAsync(SigmaSqSamples + ldm * j0, ldm * sizeof(double), dS.d(), MC * sizeof(double),
+                                          MC * sizeof(double), nj, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->poll && ctx->poll(ctx->poll_user)) return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");
   }

@@ -25,6 +25,8 @@ struct fable_ctx {
   // optional device ring of materialised Psi draws kept by fable_sampler (fable_ctx_set_psi_ring)
   double* gemm_ws = nullptr;    // grow-only split-K workspace of the DMMA GEMM
   size_t gemm_ws_bytes = 0;
+  void* stage[2] = {nullptr, nullptr};          // pinned staging for D2H into pageable caller memory
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   int ring_slots = 0;
   double* ring = nullptr;
   size_t ring_bytes = 0;

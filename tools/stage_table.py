@@ -9,6 +9,10 @@ import os
 import sys
 import time
 
+# the CPU arm runs OpenMP regions right before the GPU arm: idle OpenMP workers must sleep, not spin,
+# or they steal the cores the library's copy threads need
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
