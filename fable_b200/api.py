@@ -431,6 +431,15 @@ class Posterior:
         self.ctx.check(_load().fable_posterior_accum_dev(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def accum_pack(self):
+        """(dev_sum, dev_sumsq, count): packed upper triangles for the multi-GPU reduction."""
+        a = C.c_void_p(); b = C.c_void_p(); n = C.c_int64()
+        self.ctx.check(_load().fable_posterior_accum_pack(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return int(a.value), int(b.value), n.value
+
+    def accum_unpack(self):
+        self.ctx.check(_load().fable_posterior_accum_unpack(self._h))
+
     def accum_reset(self):
         self.ctx.check(_load().fable_posterior_accum_reset(self._h))
 

@@ -254,6 +254,7 @@ struct fable_posterior {
   DevBuf Lw, s2w;
   int Bcap = 0;
   DevBuf acc_sum, acc_sq;
+  DevBuf pack_sum, pack_sq;     // packed upper triangles for the multi-GPU reduction
   bool mirrored = false;
   int64_t tile_begin = 0, tile_end = 0;
 };
@@ -703,6 +704,37 @@ int fable_posterior_accum_mirror(fable_posterior* post) {
   FB_TRY(fb_mirror_upper(ctx, post->acc_sum.d(), post->p));
   FB_TRY(fb_mirror_upper(ctx, post->acc_sq.d(), post->p));
   post->mirrored = true;
+  return FABLE_OK;
+}
+
+// Multi-GPU partition A: only the upper triangle of the accumulators carries information, so the one
+// collective of the path moves p(p+1)/2 doubles per accumulator instead of p^2.
+int fable_posterior_accum_pack(fable_posterior* post, double** dev_sum, double** dev_sumsq, int64_t* count) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_TRY(ensure_accum(post));
+  const int64_t p = post->p, cnt = p * (p + 1) / 2;
+  if (!post->pack_sum.ptr) {
+    FB_CUDA(ctx, post->pack_sum.alloc(static_cast<size_t>(cnt) * sizeof(double)));
+    FB_CUDA(ctx, post->pack_sq.alloc(static_cast<size_t>(cnt) * sizeof(double)));
+  }
+  FB_TRY(fb_pack_upper(ctx, post->acc_sum.d(), p, post->pack_sum.d(), 0));
+  FB_TRY(fb_pack_upper(ctx, post->acc_sq.d(), p, post->pack_sq.d(), 0));
+  if (dev_sum) *dev_sum = post->pack_sum.d();
+  if (dev_sumsq) *dev_sumsq = post->pack_sq.d();
+  if (count) *count = cnt;
+  return FABLE_OK;
+}
+
+int fable_posterior_accum_unpack(fable_posterior* post) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, post->pack_sum.ptr && post->acc_sum.ptr, "accum_unpack: nothing was packed");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_TRY(fb_pack_upper(ctx, post->acc_sum.d(), post->p, post->pack_sum.d(), 1));
+  FB_TRY(fb_pack_upper(ctx, post->acc_sq.d(), post->p, post->pack_sq.d(), 1));
+  post->mirrored = false;
   return FABLE_OK;
 }
 

@@ -149,6 +149,7 @@ struct PsiArgs {
 int fb_psi(fable_ctx* ctx, const PsiArgs& a);
 int64_t fb_psi_tile_slots(int64_t p);   // length of the (super-block padded) tile enumeration
 int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p);
+int fb_pack_upper(fable_ctx* ctx, double* dA, int64_t p, double* d_packed, int unpack);
 // dst (k rows of pp, zero-padded) <- src (k rows of lds, p valid)
 int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, int KP, double* dst);
 // post.cu: Lsel [S][k][MC], Ssel [S][MC], idx [S] (0-based selected variables); outputs S x S column-major

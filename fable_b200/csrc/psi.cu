@@ -523,6 +523,22 @@ int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64
   return FABLE_OK;
 }
 
+// upper triangle (u <= v) of a column-major p x p matrix <-> packed vector, element (u, v) at v(v+1)/2 + u
+__global__ void __launch_bounds__(256) k_pack_upper(double* __restrict__ A, int64_t p, double* __restrict__ packed, int unpack) {
+  const int64_t v = blockIdx.y;
+  const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (u > v) return;
+  const int64_t i = v * (v + 1) / 2 + u;
+  if (unpack) A[u + p * v] = packed[i]; else packed[i] = A[u + p * v];
+}
+
+int fb_pack_upper(fable_ctx* ctx, double* dA, int64_t p, double* d_packed, int unpack) {
+  dim3 grid(static_cast<unsigned>(ceil_div(p, 256)), static_cast<unsigned>(p));
+  k_pack_upper<<<grid, 256, 0, ctx->stream>>>(dA, p, d_packed, unpack);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
 int64_t fb_psi_tile_slots(int64_t p) {
   const int64_t nT = ceil_div(p, TILE), nSB = ceil_div(nT, SB);
   return nSB * (nSB + 1) / 2 * SB * SB;

@@ -66,17 +66,32 @@ def allreduce_moments(tensors, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
-def allreduce_posterior_accumulators(post, device, group=None):
-    """All-reduce the device-resident sum / sumsq accumulators of a fable_posterior in place.
-    The library's stream is drained first and torch's current stream is drained after, so the two
-    stream domains never overlap on the buffers."""
+def reduce_posterior_accumulators(post, device, dst=0, group=None):
+    """The one exchange step of partition A: sum the device-resident sum / sumsq accumulators of a
+    fable_posterior over ranks.  Only their upper triangles carry information, so those are packed
+    (p(p+1)/2 doubles each) and reduced to rank `dst` (dst=None: all-reduce, every rank gets the sums);
+    the result is unpacked in place on the receiving rank(s).  The library's stream is drained first and
+    torch's current stream after, so the two stream domains never overlap on the buffers."""
     import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    a, b, n = post.accum_pack()
     post.ctx.synchronize()
-    a, b = post.accum_dev()
-    n = post.p * post.p
     ts = [as_torch(a, n, device), as_torch(b, n, device)]
-    allreduce_moments(ts, group)
+    for t in ts:
+        if dst is None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
     torch.cuda.synchronize(device)
+    if dst is None or dist.get_rank(group) == dst:
+        post.accum_unpack()
+        post.ctx.synchronize()
+
+
+def allreduce_posterior_accumulators(post, device, group=None):
+    reduce_posterior_accumulators(post, device, dst=None, group=group)
 
 
 def gather_sample_rows(local, MC, rank, world, group=None):

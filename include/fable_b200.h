@@ -197,6 +197,11 @@ int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** 
 int fable_posterior_accum_reset(fable_posterior* post);
 int fable_posterior_accum_mirror(fable_posterior* post); /* make both triangles valid (device) */
 int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sumsq); /* host out  */
+/* Multi-GPU partition A (draws sharded over ranks): pack the upper triangles (element (u,v), u <= v, at
+ * v(v+1)/2 + u; count = p(p+1)/2) into device vectors for the one NCCL sum of the path, and write the
+ * reduced vectors back.  Only the upper triangle carries information (mirrored on fetch). */
+int fable_posterior_accum_pack(fable_posterior* post, double** dev_sum, double** dev_sumsq, int64_t* count);
+int fable_posterior_accum_unpack(fable_posterior* post);
 
 /* ---- device-pointer primitives ------------------------------------------------------------------ */
 /* out[u + p*v] = sum_l A[u + lda*l] A[v + lda*l] + (u==v ? s[u] : 0), dense symmetric p x p

@@ -273,6 +273,18 @@ def test_posterior_batches_accumulate_like_one_pass(ctx, c1):
     post.draw_batch(0, MC, accumulate=True)
     t1, t2 = post.accum_fetch()
     assert relerr_mat(t1, s1) < 1e-13 and relerr_mat(t2, s2) < 1e-13
+    # pack / unpack of the upper triangles (the payload of the multi-GPU reduction) is lossless
+    a_, b_, cnt = post.accum_pack()
+    assert cnt == p * (p + 1) // 2
+    from fable_b200 import parallel
+    ctx.synchronize()
+    packed = parallel.as_torch(a_, cnt, "cuda").clone()
+    iu = np.triu_indices(p); order = np.lexsort((iu[0], iu[1]))
+    np.testing.assert_array_equal(packed.cpu().numpy(), t1[iu[0][order], iu[1][order]])
+    parallel.as_torch(a_, cnt, "cuda").mul_(2.0); torch.cuda.synchronize()
+    post.accum_unpack()
+    u1, u2 = post.accum_fetch()
+    np.testing.assert_array_equal(u1, 2.0 * t1); np.testing.assert_array_equal(u2, t2)
     post.close()
 
 
