@@ -72,7 +72,8 @@ struct RowScratch {
 int row_pass(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, bool want_s) {
   FB_TRY(sc.ensure(ctx, in.p, k));
   FB_TRY(fb_cq(ctx, in.V.d(), in.p, in.d.d(), in.p, k, sc.c.d(), in.p, sc.q.d()));
-  if (k <= KSMALL) {
+  static const int ksmall = getenv("FABLE_B200_KSMALL") ? atoi(getenv("FABLE_B200_KSMALL")) : KSMALL;
+  if (k <= ksmall) {
     FB_TRY(fb_rowstats(ctx, in.Y.d(), in.n, in.p, in.n, in.U.d(), in.n, sc.c.d(), in.p, k,
                        want_s ? sc.s.d() : nullptr, sc.resid.d()));
   } else {

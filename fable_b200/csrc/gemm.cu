@@ -11,6 +11,8 @@
 // CTA tile 128 x 128 x 16, 8 warps as 2 (M) x 4 (N), warp tile 64 x 32 = 8 x 4 DMMA tiles.
 // Shared tiles are [kk][m] with row stride 132 doubles (132 mod 16 = 4): the 16 lanes of a
 // half-warp (g = 0..3, t = 0..3) read bank 4t+g -> conflict-free 8-byte fragment loads.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -199,15 +201,25 @@ int launch(fable_ctx* ctx, dim3 grid, int64_t M, int64_t N, int64_t K, int64_t k
 }  // namespace
 
 namespace {
-// split K so that the grid covers the 148 SMs about twice
+// Split K so that tiles x splits fills whole waves of the SMs (one 128 x 128 CTA per SM at 248 registers):
+// the smallest number of waves whose last wave is >= 90% full wins (36 tiles: 4 splits = 144 CTAs = one
+// wave, not 9 splits = 324 CTAs = 2.2 waves), subject to >= 4 k-tiles per split.
 int64_t choose_splits(const fable_ctx* ctx, int64_t tiles, int64_t K, int64_t* kper) {
+  const int64_t ktiles = ceil_div(K, BK), sms = ctx->sms;
   int64_t splits = 1;
-  const int64_t ktiles = ceil_div(K, BK);
-  if (tiles < 2 * ctx->sms) {
-    splits = ceil_div(2 * static_cast<int64_t>(ctx->sms), tiles);
-    if (splits > ktiles / 4) splits = ktiles / 4 > 0 ? ktiles / 4 : 1;
-    if (splits > 64) splits = 64;
+  if (tiles < sms) {
+    const int64_t cap = ktiles / 4 > 0 ? (ktiles / 4 < 64 ? ktiles / 4 : 64) : 1;
+    double best_eff = 0.0;
+    for (int64_t w = 1; w <= 3; ++w) {
+      int64_t s = w * sms / tiles;
+      if (s > cap) s = cap;
+      if (s < 1) continue;
+      const double eff = static_cast<double>(tiles * s) / static_cast<double>(ceil_div(tiles * s, sms) * sms);
+      if (eff > best_eff + 1e-9) { best_eff = eff; splits = s; }
+      if (eff >= 0.9) break;
+    }
   }
+  if (const char* e = getenv("FABLE_B200_SPLITS")) splits = atoi(e);
   *kper = round_up(ceil_div(K, splits), BK);
   return ceil_div(K, *kper);
 }
