@@ -8,6 +8,7 @@
 // no separate accumulation of Q.  Each round applies m/2 disjoint rotations (round-robin
 // "tournament" ordering), one CTA per column pair; a sweep is m-1 rounds.
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <numeric>
 
@@ -81,6 +82,237 @@ k_gather_normalise(const double* __restrict__ A, int64_t m, int64_t ld, const in
   if (threadIdx.x == 0) W[blockIdx.x] = nv;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Block one-sided Jacobi (m > kBlockMin).  Columns are grouped in blocks of BW = 32; a round pairs the
+// blocks (round-robin) and for every pair (I, J) of a round
+//   1. k_bj_gram : H = W'W for the m x 64 panel W = [A_I A_J]   (FP64 tensor cores, split over the rows)
+//   2. k_bj_eig  : one two-sided cyclic Jacobi sweep on the 64 x 64 matrix H in shared memory -> R
+//                  (inexact inner solve: more inner sweeps cost 0.9 ms per pair and do not reduce the
+//                  number of outer sweeps; measured)
+//   3. k_bj_apply: W <- W R         (FP64 tensor cores, in place, one CTA per 128 rows)
+// so a round streams the matrix through HBM once per 32 columns instead of once per column: m/32 - 1
+// rounds per sweep instead of m - 1.  The working matrix is padded with zero rows (to a multiple of 16)
+// and zero columns (to an even number of blocks); zero columns are never rotated.
+constexpr int BW = 32, PW = 2 * BW;
+constexpr int GKT = 16, GS = GKT + 4;      // Gram stage: 16 rows, column stride 20 (= 4 mod 16: conflict-free fragments)
+constexpr int ASTR = 128 + 4, RSTR = PW + 4;
+
+__device__ __forceinline__ void bj_pair(int i, int round, int NB, int& bi, int& bj) {
+  int ca, cb;
+  if (i == 0) { ca = NB - 1; cb = round; }
+  else { ca = (round + i) % (NB - 1); cb = (round - i + (NB - 1)) % (NB - 1); }
+  bi = ca < cb ? ca : cb; bj = ca < cb ? cb : ca;
+}
+__device__ __forceinline__ int64_t bj_col(int a, int bi, int bj) { return a < BW ? static_cast<int64_t>(bi) * BW + a : static_cast<int64_t>(bj) * BW + (a - BW); }
+
+__device__ __forceinline__ void dmma4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+
+// H_part[(pair * nsplit + split)][64 x 64 column-major] = sum over the split's rows of W[i,a] W[i,b]
+__global__ void __launch_bounds__(128)
+k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int64_t mrows, int round, int NB,
+          double* __restrict__ Hpart) {
+  __shared__ __align__(16) double T[2][PW * GS];
+  int bi, bj;
+  bj_pair(blockIdx.x, round, NB, bi, bj);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wa = (warp & 1) * 32, wb = (warp >> 1) * 32;
+  const int64_t r0 = blockIdx.y * rows_per_split;
+  const int64_t r1 = r0 + rows_per_split < mrows ? r0 + rows_per_split : mrows;
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+  // stage = 16 rows x 64 columns = 512 chunks of 16 bytes (2 rows); 4 per thread
+  auto load = [&](int64_t i0, int buf) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = tid + 128 * q, a = idx >> 3, ch = idx & 7;
+      cp16(&T[buf][a * GS + 2 * ch], A + bj_col(a, bi, bj) * ld + i0 + 2 * ch);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load(r0, 0);
+  int buf = 0;
+  for (int64_t i0 = r0; i0 < r1; i0 += GKT, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (i0 + GKT < r1) load(i0 + GKT, buf ^ 1);
+    const double* Ts = T[buf];
+#pragma unroll
+    for (int ks = 0; ks < GKT / 4; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = Ts[(wa + i * 8 + g) * GS + ks * 4 + t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Ts[(wb + j * 8 + g) * GS + ks * 4 + t];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma4(c[i][j], af[i], bf[j]);
+    }
+  }
+  double* H = Hpart + (static_cast<int64_t>(blockIdx.x) * gridDim.y + blockIdx.y) * (PW * PW);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) H[(wa + i * 8 + g) + PW * (wb + j * 8 + 2 * t + e)] = c[i][j][e];
+}
+
+// two-sided cyclic Jacobi on H (64 x 64, shared memory), rotations accumulated in R; one CTA per pair
+__global__ void __launch_bounds__(256)
+k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, double* __restrict__ Rout, int* __restrict__ nrot) {
+  constexpr int S = PW + 1;
+  extern __shared__ double dsm[];
+  double* H = dsm;
+  double* R = dsm + PW * S;
+  __shared__ double cs[BW], sn[BW];
+  __shared__ int pp[BW], qq[BW];
+  __shared__ int any_rot, need;
+  const int tid = threadIdx.x;
+  const double* src = Hpart + static_cast<int64_t>(blockIdx.x) * nsplit * (PW * PW);
+  for (int idx = tid; idx < PW * PW; idx += 256) {
+    double v = 0.0;
+    for (int s = 0; s < nsplit; ++s) v += src[static_cast<int64_t>(s) * (PW * PW) + idx];
+    const int a = idx & (PW - 1), b = idx >> 6;
+    H[a * S + b] = v;
+    R[a * S + b] = (a == b) ? 1.0 : 0.0;
+  }
+  if (tid == 0) { any_rot = 0; need = 0; }
+  __syncthreads();
+  // does this pair need work at all?  (outer convergence test)
+  for (int idx = tid; idx < PW * PW; idx += 256) {
+    const int a = idx & (PW - 1), b = idx >> 6;
+    if (a < b) {
+      const double h = H[a * S + b];
+      if (h != 0.0 && fabs(h) > tol * sqrt(H[a * S + a]) * sqrt(H[b * S + b])) need = 1;
+    }
+  }
+  __syncthreads();
+  if (need) {
+    if (tid == 0) atomicAdd(nrot, 1);
+    for (int sweep = 0; sweep < inner; ++sweep) {
+      if (tid == 0) any_rot = 0;
+      __syncthreads();
+      for (int step = 0; step < PW - 1; ++step) {
+        if (tid < BW) {
+          int a, b;
+          if (tid == 0) { a = PW - 1; b = step; }
+          else { a = (step + tid) % (PW - 1); b = (step - tid + (PW - 1)) % (PW - 1); }
+          const int p = a < b ? a : b, q = a < b ? b : a;
+          const double hpq = H[p * S + q], hpp = H[p * S + p], hqq = H[q * S + q];
+          double c_ = 1.0, s_ = 0.0;
+          if (hpq != 0.0 && fabs(hpq) > tol * sqrt(hpp) * sqrt(hqq)) {
+            const double zeta = (hqq - hpp) / (2.0 * hpq);
+            const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            c_ = 1.0 / sqrt(1.0 + tt * tt); s_ = c_ * tt;
+            any_rot = 1;
+          }
+          cs[tid] = c_; sn[tid] = s_; pp[tid] = p; qq[tid] = q;
+        }
+        __syncthreads();
+        // columns: H <- H J, R <- R J
+        for (int idx = tid; idx < BW * PW; idx += 256) {
+          const int r = idx >> 6, i = idx & (PW - 1);
+          const double c_ = cs[r], s_ = sn[r];
+          if (s_ != 0.0) {
+            const int p = pp[r], q = qq[r];
+            const double hp = H[i * S + p], hq = H[i * S + q];
+            H[i * S + p] = c_ * hp - s_ * hq; H[i * S + q] = s_ * hp + c_ * hq;
+            const double rp = R[i * S + p], rq = R[i * S + q];
+            R[i * S + p] = c_ * rp - s_ * rq; R[i * S + q] = s_ * rp + c_ * rq;
+          }
+        }
+        __syncthreads();
+        // rows: H <- J' H
+        for (int idx = tid; idx < BW * PW; idx += 256) {
+          const int r = idx >> 6, j = idx & (PW - 1);
+          const double c_ = cs[r], s_ = sn[r];
+          if (s_ != 0.0) {
+            const int p = pp[r], q = qq[r];
+            const double hp = H[p * S + j], hq = H[q * S + j];
+            H[p * S + j] = c_ * hp - s_ * hq; H[q * S + j] = s_ * hp + c_ * hq;
+          }
+        }
+        __syncthreads();
+      }
+      if (!any_rot) break;
+      __syncthreads();
+    }
+  }
+  double* Rg = Rout + static_cast<int64_t>(blockIdx.x) * (PW * PW);
+  for (int idx = tid; idx < PW * PW; idx += 256) {
+    const int a = idx & (PW - 1), b = idx >> 6;
+    Rg[a + PW * b] = R[a * S + b];          // column-major 64 x 64
+  }
+}
+
+// W (rows i0..i0+127 of the pair's 64 columns) <- W R, in place
+__global__ void __launch_bounds__(256)
+k_bj_apply(double* __restrict__ A, int64_t ld, int round, int NB, const double* __restrict__ Rall) {
+  extern __shared__ __align__(16) double sm[];
+  double* TA = sm;                    // [64 cols a][ASTR]  (128 rows each)
+  double* TR = sm + PW * ASTR;        // [64 cols c][RSTR]  (64 entries a each): R[a][c]
+  int bi, bj;
+  bj_pair(blockIdx.x, round, NB, bi, bj);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * 128;
+  const double* R = Rall + static_cast<int64_t>(blockIdx.x) * (PW * PW);
+  for (int idx = tid; idx < PW * 64; idx += 256) {         // A tile: 64 columns x 64 chunks of 2 rows
+    const int a = idx >> 6, ch = idx & 63;
+    if (i0 + 2 * ch < ld) cp16(TA + a * ASTR + 2 * ch, A + bj_col(a, bi, bj) * ld + i0 + 2 * ch);
+  }
+  for (int idx = tid; idx < PW * 32; idx += 256) {         // R: 64 columns x 32 chunks
+    const int cc = idx >> 5, ch = idx & 31;
+    cp16(TR + cc * RSTR + 2 * ch, R + cc * PW + 2 * ch);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+  double c[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+#pragma unroll 4
+  for (int ks = 0; ks < PW / 4; ++ks) {
+    double af[4], bf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) af[i] = TA[(ks * 4 + t) * ASTR + wr + i * 8 + g];      // A[m = row][k = a]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf[j] = TR[(wc + j * 8 + g) * RSTR + ks * 4 + t];      // B[k = a][n = c] = R[a][c]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma4(c[i][j], af[i], bf[j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t row = i0 + wr + i * 8 + g;
+        if (row < ld) A[bj_col(wc + j * 8 + 2 * t + e, bi, bj) * ld + row] = c[i][j][e];
+      }
+}
+
+__global__ void __launch_bounds__(256) k_bj_copy_in(const double* __restrict__ G, int64_t m, double* __restrict__ W, int64_t ld, int64_t ncols) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x, j = blockIdx.y;
+  if (i >= ld || j >= ncols) return;
+  W[i + ld * j] = (i < m && j < m) ? G[i + m * j] : 0.0;
+}
+
 }  // namespace
 
 int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps_out) {
@@ -93,7 +325,53 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
   FB_CUDA(ctx, perm.alloc(m * sizeof(int)));
   int sweeps = 0;
   const int max_sweeps = 40;
-  if (m > 1) {
+  constexpr int64_t kBlockMin = 256;
+  DevBuf Wbuf;
+  double* Acols = dG;          // matrix whose columns end up as lambda_i q_i, leading dimension lda
+  int64_t lda = m;
+  if (m > kBlockMin) {
+    const int NB = static_cast<int>(ceil_div(m, BW) + (ceil_div(m, BW) & 1));     // even number of blocks
+    const int64_t ld = round_up(m, 16), ncols = static_cast<int64_t>(NB) * BW;
+    const int npairs = NB / 2;
+    const int inner = getenv("FABLE_B200_BJ_INNER") ? atoi(getenv("FABLE_B200_BJ_INNER")) : 1;
+    int64_t nsplit = ceil_div(2 * static_cast<int64_t>(ctx->sms), npairs);
+    if (nsplit > ld / 64) nsplit = ld / 64 > 0 ? ld / 64 : 1;
+    const int64_t rows_per_split = round_up(ceil_div(ld, nsplit), GKT);
+    nsplit = ceil_div(ld, rows_per_split);
+    DevBuf Hpart, Rall;
+    FB_CUDA(ctx, Wbuf.alloc(static_cast<size_t>(ld) * ncols * sizeof(double)));
+    FB_CUDA(ctx, Hpart.alloc(static_cast<size_t>(npairs) * nsplit * PW * PW * sizeof(double)));
+    FB_CUDA(ctx, Rall.alloc(static_cast<size_t>(npairs) * PW * PW * sizeof(double)));
+    k_bj_copy_in<<<dim3(static_cast<unsigned>(ceil_div(ld, 256)), static_cast<unsigned>(ncols)), 256, 0, ctx->stream>>>(
+        dG, m, Wbuf.d(), ld, ncols);
+    FB_LAUNCHED(ctx);
+    const size_t apply_smem = static_cast<size_t>(PW * ASTR + PW * RSTR) * sizeof(double);
+    const size_t eig_smem = static_cast<size_t>(2 * PW * (PW + 1)) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+      FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem)));
+      FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eig_smem)));
+      attr = true;
+    }
+    for (; sweeps < max_sweeps; ++sweeps) {
+      FB_CUDA(ctx, cudaMemsetAsync(cnt.ptr, 0, sizeof(int), ctx->stream));
+      for (int r = 0; r < NB - 1; ++r) {
+        k_bj_gram<<<dim3(npairs, static_cast<unsigned>(nsplit)), 128, 0, ctx->stream>>>(Wbuf.d(), ld, rows_per_split, ld, r, NB,
+                                                                                         Hpart.d());
+        k_bj_eig<<<npairs, 256, eig_smem, ctx->stream>>>(Hpart.d(), static_cast<int>(nsplit), tol, inner, Rall.d(), static_cast<int*>(cnt.ptr));
+        k_bj_apply<<<dim3(npairs, static_cast<unsigned>(ceil_div(ld, 128))), 256, apply_smem, ctx->stream>>>(Wbuf.d(), ld, r, NB,
+                                                                                                             Rall.d());
+        ctx->launches += 3;
+      }
+      FB_CUDA(ctx, cudaGetLastError());
+      int nrot = 0;
+      FB_CUDA(ctx, cudaMemcpyAsync(&nrot, cnt.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (nrot == 0) { ++sweeps; break; }
+    }
+    if (sweeps >= max_sweeps) return ctx->fail(FABLE_ERR_NUMERIC, "syevj: block Jacobi sweeps did not converge");
+    Acols = Wbuf.d(); lda = ld;
+  } else if (m > 1) {
     for (; sweeps < max_sweeps; ++sweeps) {
       FB_CUDA(ctx, cudaMemsetAsync(cnt.ptr, 0, sizeof(int), ctx->stream));
       for (int r = 0; r < N - 1; ++r) {
@@ -108,7 +386,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     }
     if (sweeps >= max_sweeps) return ctx->fail(FABLE_ERR_NUMERIC, "syevj: Jacobi sweeps did not converge");
   }
-  k_colnorm<<<static_cast<unsigned>(m), JT, 0, ctx->stream>>>(dG, m, m, nrm.d());
+  k_colnorm<<<static_cast<unsigned>(m), JT, 0, ctx->stream>>>(Acols, m, lda, nrm.d());
   FB_LAUNCHED(ctx);
   std::vector<double> h(m);
   FB_CUDA(ctx, cudaMemcpyAsync(h.data(), nrm.d(), m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -117,7 +395,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h[a] > h[b]; });
   FB_CUDA(ctx, cudaMemcpyAsync(perm.ptr, order.data(), m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  k_gather_normalise<<<static_cast<unsigned>(m), JT, 0, ctx->stream>>>(dG, m, m, static_cast<const int*>(perm.ptr),
+  k_gather_normalise<<<static_cast<unsigned>(m), JT, 0, ctx->stream>>>(Acols, m, lda, static_cast<const int*>(perm.ptr),
                                                                       nrm.d(), dQ, dW);
   FB_LAUNCHED(ctx);
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -421,7 +421,7 @@ def test_dmma_gemm(ctx, M, N, K, akf, bkf):
     assert relerr_mat(dC.cpu().numpy().T, 0.5 * A @ B.T) < 1e-13
 
 
-@pytest.mark.parametrize("m", [1, 2, 7, 64, 301])
+@pytest.mark.parametrize("m", [1, 2, 7, 64, 256, 257, 301, 640, 1000])
 def test_jacobi_eigensolver(ctx, m):
     import torch
     rng = np.random.default_rng(m)
@@ -433,8 +433,8 @@ def test_jacobi_eigensolver(ctx, m):
     w = dW.cpu().numpy(); Q = dQ.cpu().numpy().T
     assert sweeps <= 30
     assert relerr_vec(w, np.linalg.eigvalsh(G)[::-1]) < 1e-11
-    assert relerr_mat(Q @ np.diag(w) @ Q.T, G) < 1e-12
-    assert relerr_mat(Q.T @ Q, np.eye(m)) < 1e-12
+    assert relerr_mat(Q @ np.diag(w) @ Q.T, G) < 1e-11
+    assert relerr_mat(Q.T @ Q, np.eye(m)) < 1e-11
 
 
 # ---- error behaviour (reference: Armadillo bounds errors surface as R errors, §8b) ------------------
