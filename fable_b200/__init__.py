@@ -9,7 +9,7 @@ anywhere, but every call raises `FableError` when the library or a B200 is missi
 from .api import (  # noqa: F401
     FableError, Context, Posterior,
     FABLEPosteriorMean, FABLEPosteriorSampler,
-    CPPRankEstimator, CPPCriterionFunction, CPPBisectionRecursion,
+    CPPRankEstimator, CPPCriterionFunction, CPPBisectionRecursion, CPPLogLikelihoodEval,
     FABLEHyperParameters, CPPcov_correct_matrix, cov_correct_matrix, var_inflation,
     CPPFABLEPostMean, CPPFABLESampler, CPPsvd, svd, kmax_rule,
     CPPCCFABLEPostProcessing, CCFABLEPostProcessingSubmatrix, CCFABLEPostProcessingSubmatrix_Optimized,
@@ -19,7 +19,7 @@ from . import synth  # noqa: F401
 
 __all__ = [
     "FableError", "Context", "Posterior", "FABLEPosteriorMean", "FABLEPosteriorSampler",
-    "CPPRankEstimator", "CPPCriterionFunction", "CPPBisectionRecursion", "FABLEHyperParameters",
+    "CPPRankEstimator", "CPPCriterionFunction", "CPPBisectionRecursion", "CPPLogLikelihoodEval", "FABLEHyperParameters",
     "CPPcov_correct_matrix", "cov_correct_matrix", "var_inflation", "CPPFABLEPostMean",
     "CPPFABLESampler", "CPPsvd", "svd", "kmax_rule", "CPPCCFABLEPostProcessing",
     "CCFABLEPostProcessingSubmatrix", "CCFABLEPostProcessingSubmatrix_Optimized", "default_context", "library_path", "synth",

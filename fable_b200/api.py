@@ -196,6 +196,20 @@ def CPPCriterionFunction(kInd, Y, U_Y, V_Y, svalsY, ctx=None):
     return out.value
 
 
+def CPPLogLikelihoodEval(Y, M, Lambda, SigmaSq, ctx=None):
+    """cpp:95-125 (exported by the reference, not used by its wrappers)."""
+    ctx = _ctx(ctx)
+    Y = _F(Y, "Y"); M = _F(M, "M"); L = _F(Lambda, "Lambda"); s = _F(SigmaSq)
+    n, p = Y.shape
+    k = M.shape[1]
+    if M.shape[0] != n or L.shape != (p, k) or s.shape[0] != p:
+        raise FableError(1, "CPPLogLikelihoodEval: M must be n x k, Lambda p x k, SigmaSq length p")
+    out = C.c_double()
+    ctx.check(_load().fable_log_likelihood_eval(ctx._h, _ptr(Y), _i64(n), _i64(p), _ptr(M), _ptr(L), C.c_int(k), _ptr(s),
+                                                C.byref(out)))
+    return out.value
+
+
 def CPPBisectionRecursion(lower, upper, Y, U_Y, V_Y, svalsY, ctx=None):
     ctx = _ctx(ctx)
     Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)

@@ -423,6 +423,28 @@ int fable_kmax(const double* d, int64_t r, double maxProp, int* kMax) {
   return FABLE_ERR_INVALID;                                  // R: min(integer(0)) = Inf + warning
 }
 
+// ---- f4: CPPLogLikelihoodEval (cpp:95-125) ----------------------------------------------------------
+int fable_log_likelihood_eval(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* M, const double* Lambda,
+                              int k, const double* SigmaSq, double* out) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, Y && M && Lambda && SigmaSq && out, "log_likelihood: NULL pointer");
+  FB_REQUIRE(ctx, n >= 1 && p >= 1 && k >= 1, "log_likelihood: need n, p, k >= 1");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf dY, dM, dL, dS, dR;
+  FB_TRY(upload(ctx, dY, Y, static_cast<size_t>(n) * p));
+  FB_TRY(upload(ctx, dM, M, static_cast<size_t>(n) * k));
+  FB_TRY(upload(ctx, dL, Lambda, static_cast<size_t>(p) * k));
+  FB_TRY(upload(ctx, dS, SigmaSq, static_cast<size_t>(p)));
+  FB_CUDA(ctx, dR.alloc(static_cast<size_t>(p) * sizeof(double)));
+  // residual column sums of squares of Y - M Lambda' (cpp:113): the row-pass kernels with U := M, c := Lambda
+  if (k <= KSMALL) FB_TRY(fb_rowstats(ctx, dY.d(), n, p, n, dM.d(), n, dL.d(), p, k, nullptr, dR.d()));
+  else FB_TRY(fb_gemm_resid(ctx, n, p, k, dY.d(), n, dM.d(), n, dL.d(), p, dR.d()));
+  double sum_log_sd = 0.0, sum_ros = 0.0;
+  FB_TRY(fb_loglik_terms(ctx, dR.d(), dS.d(), p, &sum_log_sd, &sum_ros));
+  *out = (-static_cast<double>(n) * sum_log_sd) + (-0.5 * sum_ros);                 // cpp:116-120
+  return FABLE_OK;
+}
+
 // ---- a3 / a4 / a5 --------------------------------------------------------------------------------
 int fable_criterion(fable_ctx* ctx, int kInd, const double* Y, int64_t n, int64_t p, const double* U,
                     const double* V, const double* d, int64_t r, double* out) {

@@ -106,6 +106,8 @@ int fb_cq(fable_ctx* ctx, const double* dV, int64_t ldv, const double* dd, int64
           double* d_c, int64_t ldc, double* d_q);
 // reduce.cu
 int fb_sum_log_scaled(fable_ctx* ctx, const double* d_x, int64_t p, double scale, double* host_out);
+int fb_loglik_terms(fable_ctx* ctx, const double* d_resid, const double* d_sig, int64_t p, double* sum_log_sd,
+                    double* sum_resid_over_sig);
 int fb_tausq(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, int k,
              double* host_tausq);
 int fb_finish_posterior(fable_ctx* ctx, const double* d_c, int64_t ldc, const double* d_s,

@@ -27,6 +27,15 @@ struct LogScaled {
   const double* x; double scale;
   __device__ double operator()(int64_t j) const { return log(x[j] * scale); }
 };
+// CPPLogLikelihoodEval (cpp:95-125): Term1 = -n sum_j log(sqrt(SigmaSq_j)); Term2 = -0.5 sum_j resid_j / SigmaSq_j
+struct LogSd {
+  const double* sig;
+  __device__ double operator()(int64_t j) const { return log(sqrt(sig[j])); }
+};
+struct ResidOverSig {
+  const double* resid; const double* sig;
+  __device__ double operator()(int64_t j) const { return resid[j] / sig[j]; }
+};
 struct QOverSig {
   const double* q; const double* resid; double inv_n;
   __device__ double operator()(int64_t j) const { return q[j] / (resid[j] * inv_n); }
@@ -186,6 +195,12 @@ k_sum_partials(const double* __restrict__ part, int64_t nparts, int64_t len, int
 
 int fb_sum_log_scaled(fable_ctx* ctx, const double* d_x, int64_t p, double scale, double* host_out) {
   return reduce_to_host(ctx, LogScaled{d_x, scale}, p, host_out);
+}
+
+int fb_loglik_terms(fable_ctx* ctx, const double* d_resid, const double* d_sig, int64_t p, double* sum_log_sd,
+                    double* sum_resid_over_sig) {
+  FB_TRY(reduce_to_host(ctx, LogSd{d_sig}, p, sum_log_sd));
+  return reduce_to_host(ctx, ResidOverSig{d_resid, d_sig}, p, sum_resid_over_sig);
 }
 
 int fb_tausq(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, int k,

@@ -79,6 +79,11 @@ int fable_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, 
 /* min{ i : cumsum(d)_i / sum(d) >= maxProp }, 1-based (R/FABLE_wrapper.R:27, 94). Host-only. */
 int fable_kmax(const double* d, int64_t r, double maxProp, int* kMax);
 
+/* ---- f4: CPPLogLikelihoodEval (updated-FABLE-functions.cpp:95-125; exported, unused by the wrappers) ----
+ * -n sum_j log sqrt(SigmaSq_j) - 0.5 sum_ij ((Y - M Lambda')_ij / sqrt(SigmaSq_j))^2.  M n x k, Lambda p x k. */
+int fable_log_likelihood_eval(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* M,
+                              const double* Lambda, int k, const double* SigmaSq, double* out);
+
 /* ---- a3: CPPCriterionFunction (updated-FABLE-functions.cpp:127-213) ------------------------- */
 int fable_criterion(fable_ctx* ctx, int kInd, const double* Y, int64_t n, int64_t p,
                     const double* U, const double* V, const double* d, int64_t r, double* out);

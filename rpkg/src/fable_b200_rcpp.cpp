@@ -53,6 +53,14 @@ struct Svd {
 
 }  // namespace
 
+// reference cpp:95-125
+// [[Rcpp::export]]
+double CPPLogLikelihoodEval(Rcpp::NumericMatrix Y, Rcpp::NumericMatrix M, Rcpp::NumericMatrix Lambda, Rcpp::NumericVector SigmaSq) {
+  double out = 0.0;
+  check(fable_log_likelihood_eval(ctx(), Y.begin(), Y.nrow(), Y.ncol(), M.begin(), Lambda.begin(), M.ncol(), SigmaSq.begin(), &out));
+  return out;
+}
+
 // reference cpp:127-213
 // [[Rcpp::export]]
 double CPPCriterionFunction(int kInd, Rcpp::NumericMatrix Y, Rcpp::NumericMatrix U_Y, Rcpp::NumericMatrix V_Y,

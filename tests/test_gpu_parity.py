@@ -404,6 +404,17 @@ def test_coverage_pattern_of_the_replication_script(ctx):
     assert 0.85 <= cover <= 1.0, cover
 
 
+@pytest.mark.parametrize("n,p,k", [(9, 5, 2), (50, 300, 7), (64, 200, 40)])
+def test_log_likelihood_eval(ctx, n, p, k):
+    rng = np.random.default_rng(n * p + k)
+    Y = rng.standard_normal((n, p)); M = rng.standard_normal((n, k)); Lam = rng.standard_normal((p, k)); sig = rng.uniform(0.5, 2, p)
+    got = fb.CPPLogLikelihoodEval(Y, M, Lam, sig, ctx=ctx)
+    assert abs(got / orc.log_likelihood_eval(Y, M, Lam, sig) - 1) < TOL
+    from oracle import ref_oracle as ref
+    if ref.available():
+        assert abs(got / ref.log_likelihood_eval(Y, M, Lam, sig) - 1) < TOL
+
+
 # ---- DMMA GEMM + eigensolver primitives -------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (127, 129, 17), (128, 128, 16), (300, 200, 1000), (64, 1000, 33)])
 @pytest.mark.parametrize("akf,bkf", [(0, 0), (0, 1), (1, 0), (1, 1)])
