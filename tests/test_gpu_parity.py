@@ -448,6 +448,32 @@ def test_jacobi_eigensolver(ctx, m):
     assert relerr_mat(Q.T @ Q, np.eye(m)) < 1e-11
 
 
+# ---- degenerate shapes ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,p,k", [(3, 1, 1), (2, 2, 1), (5, 3, 2), (4, 70, 4), (70, 4, 3), (8, 8, 8)])
+def test_tiny_and_degenerate_shapes(ctx, n, p, k):
+    """p = 1, n < 4, tall and wide, k equal to the full rank: every entry point against the oracle."""
+    rng = np.random.default_rng(n * 100 + p)
+    Y = np.asfortranarray(rng.standard_normal((n, p)) + 3.0 * rng.standard_normal((n, 1)) @ rng.standard_normal((1, p)))
+    u, d, v = orc.svd_thin(Y)
+    r = d.size
+    s = fb.svd(Y, ctx=ctx)
+    assert relerr_vec(s["d"], d) < 1e-9
+    kk = min(k, r)
+    if kk < r:                                # at full rank the residual is rounding noise (log of ~1e-30)
+        assert abs(fb.CPPCriterionFunction(kk, Y, u, v, d, ctx=ctx) / orc.criterion(kk, Y, u, v, d) - 1) < TOL
+        kMax = r - 1
+        assert fb.CPPRankEstimator(Y, u, v, d, kMax, ctx=ctx) == orc.rank_estimator(Y, u, v, d, kMax)
+        hg, ho = fb.FABLEHyperParameters(Y, u, v, d, kk, ctx=ctx), orc.hyper_parameters(Y, u, v, d, kk)
+        assert relerr_mat(hg["G"], ho["G"]) < TOL and relerr_vec(hg["SigmaSqEstimate"], ho["SigmaSqEstimate"]) < TOL
+        MC = 3
+        gam, z = synth.injected_draws(MC, p, kk, 0.5 * (3.0 + n), seed=n + p)
+        sg = fb.CPPFABLESampler(Y, 3.0, 1.0, MC, u, v, d, kk, 1.1, ctx=ctx, gam=gam, z=z, psi_moments=True)
+        so = orc.sampler(Y, 3.0, 1.0, MC, u, v, d, kk, 1.1, gam, z)
+        assert relerr_mat(sg["LambdaSamples"], so["LambdaSamples"]) < TOL and relerr_vec(sg["SigmaSqSamples"], so["SigmaSqSamples"]) < TOL
+        s1, s2 = orc.psi_moments(so["LambdaSamples"], so["SigmaSqSamples"], kk)
+        assert relerr_mat(sg["PsiSum"], s1) < TOL and relerr_mat(sg["PsiSumSq"], s2) < TOL
+
+
 # ---- error behaviour (reference: Armadillo bounds errors surface as R errors, §8b) ------------------
 def test_errors_are_status_codes_not_crashes(ctx, golden):
     Y, u, d, v = golden["a_Y"], golden["a_u"], golden["a_d"], golden["a_v"]
