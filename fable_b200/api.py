@@ -422,6 +422,10 @@ class Posterior:
                                                           C.c_int(psi_slots), C.c_int(1 if accumulate else 0),
                                                           C.c_void_p(dev_gam or None), C.c_void_p(dev_z or None)))
 
+    def set_entrywise_correction(self, on=True):
+        """f3 (R/FABLE_code.R:212-298): materialised draws become G + B o (Lambda Lambda' - G) + diag(sigma2)."""
+        self.ctx.check(_load().fable_posterior_set_entrywise_correction(self._h, C.c_int(1 if on else 0)))
+
     def tile_slots(self):
         n = C.c_int64()
         self.ctx.check(_load().fable_posterior_tile_slots(self._h, C.byref(n)))

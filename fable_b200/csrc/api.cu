@@ -256,6 +256,8 @@ struct fable_posterior {
   int Bcap = 0;
   DevBuf acc_sum, acc_sq;
   DevBuf pack_sum, pack_sq;     // packed upper triangles for the multi-GPU reduction
+  DevBuf cc_gdiag;              // entry-wise coverage correction (f3): diag(G0 G0'); NULL = off
+  bool cc = false;
   bool mirrored = false;
   int64_t tile_begin = 0, tile_end = 0;
 };
@@ -625,19 +627,37 @@ int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double*
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (B > post->Bcap) {
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    FB_CUDA(ctx, post->Lw.alloc(static_cast<size_t>(B) * post->KP * post->pp * sizeof(double)));
+    // one extra leading slot: G0 as the pseudo-draw of the entry-wise correction (unused otherwise)
+    FB_CUDA(ctx, post->Lw.alloc(static_cast<size_t>(B + 1) * post->KP * post->pp * sizeof(double)));
     FB_CUDA(ctx, post->s2w.alloc(static_cast<size_t>(B) * post->pp * sizeof(double)));
     post->Bcap = B;
   }
   if (accumulate) { FB_TRY(ensure_accum(post)); post->mirrored = false; }
-  FB_TRY(fb_sample_work(ctx, sample_args(post, dev_gam, dev_z, m0), m0, B, post->pp, post->KP, post->Lw.d(),
-                        post->s2w.d()));
+  double* draws = post->Lw.d() + static_cast<size_t>(post->KP) * post->pp;      // slots 1..B
+  FB_TRY(fb_sample_work(ctx, sample_args(post, dev_gam, dev_z, m0), m0, B, post->pp, post->KP, draws, post->s2w.d()));
   PsiArgs a;
-  a.Lw = post->Lw.d(); a.s2w = post->s2w.d(); a.pp = post->pp; a.p = post->p; a.k = post->k; a.KP = post->KP;
+  if (post->cc) {
+    FB_REQUIRE(ctx, dev_psi, "draw_batch: the entry-wise correction applies to materialised draws");
+    FB_TRY(fb_pad_rows(ctx, post->rp.G0.d(), post->p, post->p, post->pp, post->k, post->KP, post->Lw.d()));   // slot 0 = G0
+    a.cc_gdiag = post->cc_gdiag.d(); a.cc_sig = post->rp.sig.d();
+  }
+  a.Lw = post->cc ? post->Lw.d() : draws; a.s2w = post->s2w.d(); a.pp = post->pp; a.p = post->p; a.k = post->k; a.KP = post->KP;
   a.B = B; a.psi = dev_psi; a.psi_slots = psi_slots; a.slot0 = 0;
   a.acc_sum = accumulate ? post->acc_sum.d() : nullptr; a.acc_sq = accumulate ? post->acc_sq.d() : nullptr;
   a.tile_begin = post->tile_begin; a.tile_end = post->tile_end;
   return fb_psi(ctx, a);
+}
+
+int fable_posterior_set_entrywise_correction(fable_posterior* post, int on) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (on && !post->cc_gdiag.ptr) {
+    FB_CUDA(ctx, post->cc_gdiag.alloc(static_cast<size_t>(post->p) * sizeof(double)));
+    FB_TRY(fb_gdiag(ctx, post->rp.G0.d(), post->p, post->p, post->k, post->cc_gdiag.d()));     // diag(G), R:193
+  }
+  post->cc = on != 0;
+  return FABLE_OK;
 }
 
 int fable_posterior_tile_slots(fable_posterior* post, int64_t* slots) {

@@ -114,6 +114,7 @@ int fb_finish_posterior(fable_ctx* ctx, const double* d_c, int64_t ldc, const do
                         const double* d_q, const double* d_resid, int64_t n, int64_t p, int k,
                         double gamma0, double delta0sq, double tausq, int shrunk, double* d_G0,
                         int64_t ldg, double* d_gnd, double* d_sig, double* d_sigmahat);
+int fb_gdiag(fable_ctx* ctx, const double* d_G0, int64_t ldg, int64_t p, int k, double* d_gdiag);
 int fb_var_inflation(fable_ctx* ctx, const double* d_sig, const double* d_G0, int64_t ldg, int64_t p,
                      int k, double* host_sum_upper, double* host_sum_diag);
 int fb_cov_correct_dense(fable_ctx* ctx, const double* d_sig, const double* d_G, int64_t p,
@@ -145,6 +146,8 @@ struct PsiArgs {
   int slot0;           // draw b goes to slot slot0 + b (< psi_slots)
   double* acc_sum;     // p x p accumulators (NULL: none); upper tiles only
   double* acc_sq;
+  const double* cc_gdiag = nullptr;   // entry-wise coverage correction (f3): diag(G) and sig_hat (length p);
+  const double* cc_sig = nullptr;     // Lw then carries G0 in slot 0 ahead of the B draws
   int64_t tile_begin = 0, tile_end = 0;   // slice of the tile enumeration (tile_end == 0: all tiles)
   int tma_mode = 0;    // set by fb_psi: 1 = 4-D whole-tile TMA boxes, 2 = 3-D sub-boxes, 0 = plain stores
 };

@@ -150,8 +150,13 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 
 // Lw: working-layout draws, rows zero-padded to pp (a multiple of TILE), rank zero-padded to KP (a
 // multiple of 4), 16-byte aligned.
-template <bool MAT, bool ACC>
-__global__ void __launch_bounds__(256, 2)
+//
+// CC (f3, R/FABLE_code.R:212-298 CCFABLE_DirectSampler): the entry-wise coverage correction
+//   Psi_m = G + B o (Lambda_m Lambda_m' - G) + diag(sigma2_m),  B = cov_correct_matrix(sig_hat, G)  (R:251, 282-290).
+// Slot 0 of Lw then holds G0 as a pseudo-draw (b = -1): its tile product is G, from which B is formed once
+// per CTA (R:196-202) and both stay in registers (64 more: one CTA per SM).
+template <bool MAT, bool ACC, bool CC>
+__global__ void __launch_bounds__(256, CC ? 1 : 2)
 k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_sum,
       const __grid_constant__ CUtensorMap tmap_sq) {
   extern __shared__ unsigned char smem_dyn[];
@@ -172,8 +177,9 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   const bool bulk = MAT && even;
   const int K4 = a.KP;
   const int nch = (K4 + KC - 1) / KC;
-  const int nsteps = a.B * nch;
+  const int nsteps = (a.B + (CC ? 1 : 0)) * nch;
   const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+  double gq[CC ? 4 : 1][2][2], bq[CC ? 4 : 1][2][2];      // G tile and B tile of the entry-wise correction
 
   // threads 0..127 stage the u-operand, 128..255 the v-operand: chunk column = tid & 31 (16 bytes),
   // rank rows (tid >> 5) & 3, +4, +8, +12
@@ -218,7 +224,8 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   __syncthreads();
   for (int s = 0; s < nsteps; ++s) {
     const int buf = s & 1;
-    const int b = s / nch, ch = s - b * nch;
+    const int bs = s / nch, ch = s - bs * nch;
+    const int b = bs - (CC ? 1 : 0);                   // CC: step group 0 is the G0 pseudo-draw
     const int kc = min(KC, K4 - ch * KC);
     if (s + 1 < nsteps) prefetch(s + 1, buf ^ 1);      // buf^1 was last read before the previous barrier
 
@@ -242,6 +249,38 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
       cp_async_wait_all();
       __syncthreads();
       continue;
+    }
+
+    if (CC) {
+      if (b < 0) {
+        // c holds the G tile: keep it, form B_uv = sqrt(1 + (g_uu g_vv + g_uv^2) / (g_uu s_v + s_u g_vv)), the
+        // ratio halved on the diagonal (R/FABLE_code.R:196-202)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+              double bb = 0.0;
+              if (u < p && v < p) {
+                const double gu = a.cc_gdiag[u], gv = a.cc_gdiag[v], su = a.cc_sig[u], sv = a.cc_sig[v];
+                bb = (gu * gv + c[i][j][e] * c[i][j][e]) / (gu * sv + su * gv);
+                if (u == v) bb = bb / 2.0;
+                bb = sqrt(1.0 + bb);
+              }
+              gq[i][j][e] = c[i][j][e]; bq[i][j][e] = bb; c[i][j][e] = 0.0;
+            }
+        cp_async_wait_all();
+        __syncthreads();
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) c[i][j][e] = gq[i][j][e] + bq[i][j][e] * (c[i][j][e] - gq[i][j][e]);   // R:285
     }
 
     // ---- draw b of this tile is complete in registers ----------------------------------------
@@ -444,16 +483,16 @@ int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorM
   return FABLE_OK;
 }
 
-template <bool MAT, bool ACC>
+template <bool MAT, bool ACC, bool CC = false>
 int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned grid, int64_t t0, const CUtensorMap& tmap,
                const CUtensorMap& tsum, const CUtensorMap& tsq) {
   constexpr size_t smem = SMEM_BYTES;
   static bool attr = false;
   if (!attr) {
-    FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = true;
   }
-  k_psi<MAT, ACC><<<grid, 256, smem, ctx->stream>>>(a, t0, tmap, tsum, tsq);
+  k_psi<MAT, ACC, CC><<<grid, 256, smem, ctx->stream>>>(a, t0, tmap, tsum, tsq);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
 }
@@ -467,6 +506,8 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
   FB_REQUIRE(ctx, (a.acc_sum == nullptr) == (a.acc_sq == nullptr), "psi: need both accumulators");
   const bool mat = a.psi != nullptr, acc = a.acc_sum != nullptr;
   FB_REQUIRE(ctx, mat || acc, "psi: nothing to do");
+  FB_REQUIRE(ctx, (a.cc_gdiag == nullptr) == (a.cc_sig == nullptr), "psi: entry-wise correction needs gdiag and sig");
+  FB_REQUIRE(ctx, !a.cc_gdiag || mat, "psi: the entry-wise correction is defined for materialised draws");
   FB_REQUIRE(ctx, !mat || a.psi_slots > 0, "psi: psi_slots must be positive");
   FB_REQUIRE(ctx, a.pp % TILE == 0 && a.pp >= a.p && (reinterpret_cast<uintptr_t>(a.Lw) & 15) == 0,
              "psi: operand rows must be zero-padded to a multiple of 64 and 16-byte aligned");
@@ -509,7 +550,9 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
   }
   for (int64_t t0 = t_lo; t0 < t_hi; t0 += chunk) {
     const unsigned g = static_cast<unsigned>(t_hi - t0 < chunk ? t_hi - t0 : chunk);
-    if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0, tmap, tsum, tsq)));
+    if (a.cc_gdiag && mat && acc) FB_TRY((launch_psi<true, true, true>(ctx, a, g, t0, tmap, tsum, tsq)));
+    else if (a.cc_gdiag && mat) FB_TRY((launch_psi<true, false, true>(ctx, a, g, t0, tmap, tsum, tsq)));
+    else if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0, tmap, tsum, tsq)));
     else if (mat) FB_TRY((launch_psi<true, false>(ctx, a, g, t0, tmap, tsum, tsq)));
     else FB_TRY((launch_psi<false, true>(ctx, a, g, t0, tmap, tsum, tsq)));
   }

@@ -228,6 +228,12 @@ int fb_finish_posterior(fable_ctx* ctx, const double* d_c, int64_t ldc, const do
   return FABLE_OK;
 }
 
+int fb_gdiag(fable_ctx* ctx, const double* d_G0, int64_t ldg, int64_t p, int k, double* d_gdiag) {
+  k_gdiag<<<static_cast<unsigned>(ceil_div(p, 256)), 256, 0, ctx->stream>>>(d_G0, ldg, p, k, d_gdiag);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
 int fb_var_inflation(fable_ctx* ctx, const double* d_sig, const double* d_G0, int64_t ldg, int64_t p, int k,
                      double* host_sum_upper, double* host_sum_diag) {
   const int64_t nT = ceil_div(p, VT), tiles = nT * (nT + 1) / 2;

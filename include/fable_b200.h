@@ -185,6 +185,12 @@ int fable_posterior_get(fable_posterior* post, double* G0s, double* gnd, double*
 int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi,
                                int psi_slots, int accumulate, const double* dev_gam,
                                const double* dev_z);
+/* f3: CCFABLE_DirectSampler (R/FABLE_code.R:212-298).  on != 0: the draws materialised by draw_batch become
+ *   Psi_m = G + B o (Lambda_m Lambda_m' - G) + diag(sigma2_m),  B = cov_correct_matrix(sig_hat, G)  (R:251, 282-290),
+ * the entry-wise coverage correction of the R prototype, with G = G0 G0' (shrunk G0) and B formed per tile
+ * on the fly (never stored).  The prototype uses a_n = 1/sqrt(n + 1/tau^2): create the posterior with
+ * varInflation = 1.  Accumulators, when requested, sum the corrected draws. */
+int fable_posterior_set_entrywise_correction(fable_posterior* post, int on);
 /* Multi-GPU partition B (tiles): restrict draw_batch to the slice [t_begin, t_end) of the kernel's tile
  * enumeration (64 x 64 upper-triangle tiles in 16 x 16 super-block order; fable_posterior_tile_slots
  * gives its length, padding slots included).  Ranks owning disjoint slices and processing the same

@@ -38,7 +38,7 @@ __all__ = [
     "hyper_parameters", "cov_correct_matrix_R", "cpp_cov_correct_matrix", "var_inflation_wrapper",
     "var_inflation_script", "post_mean", "sampler", "psi_draw", "psi_moments", "arma_quantile",
     "post_processing", "post_processing_submatrix", "symmetrize", "FABLEPosteriorMean",
-    "FABLEPosteriorSampler", "log_likelihood_eval",
+    "FABLEPosteriorSampler", "log_likelihood_eval", "direct_sampler_psi",
 ]
 
 
@@ -315,6 +315,31 @@ def post_processing(out, alpha):
     """CPPCCFABLEPostProcessing (cpp:631-713) = the submatrix form on all p indices."""
     p = out["SigmaSqSamples"].shape[1]
     return post_processing_submatrix(out, alpha, np.arange(1, p + 1))
+
+
+def direct_sampler_psi(Y, gamma0, delta0sq, U, V, d, k, gam, z):
+    """CCFABLE_DirectSampler (R/FABLE_code.R:212-298) with injected draws: the MC x p x p array of
+    entry-wise coverage-corrected Psi draws.  (The R prototype picks k with its own RankEstimator,
+    R:221; here k is an input.)"""
+    Y = np.asarray(Y, dtype=np.float64)
+    n, p = Y.shape
+    st = _shrunk_stats(Y, U, V, d, k, gamma0, delta0sq)       # R:236-257 (same sig, tau, G0, gnd as cpp:564-592)
+    G0, gnd, sig = st["G0"], st["gnd"], st["sig"]
+    G = G0 @ G0.T                                             # R:249
+    CC = cov_correct_matrix_R(sig, G)                         # R:251
+    a_n = 1.0 / math.sqrt(st["w"])                            # R:263
+    gam = np.asarray(gam, dtype=np.float64).reshape(-1, p)
+    MC = gam.shape[0]
+    z = np.asarray(z, dtype=np.float64).reshape(MC, k, p)
+    out = np.empty((MC, p, p))
+    for m in range(MC):
+        s2 = (0.5 * gnd) / gam[m]                             # R:271-272: 1 / rgamma(shape, rate = gnd/2)
+        Z = z[m].T                                            # p x k (column-major fill, R:279)
+        SZ = Z * np.sqrt(s2)[:, None]                         # R:280
+        SZG = SZ @ G0.T                                       # R:281
+        part2 = a_n * (SZG + SZG.T) + a_n ** 2 * ((Z @ Z.T) * np.outer(np.sqrt(s2), np.sqrt(s2)))   # R:283-284
+        out[m] = G + CC * part2 + np.diag(s2)                 # R:286-290
+    return out
 
 
 def log_likelihood_eval(Y, M, Lambda, SigmaSq):

@@ -306,6 +306,32 @@ def test_c4_like_ranks_above_one_chunk(ctx, n, p, k, B):
     post.close()
 
 
+@pytest.mark.parametrize("n,p,k", [(60, 160, 3), (40, 77, 2), (50, 130, 17)])
+def test_entrywise_corrected_draws_f3(ctx, n, p, k):
+    """CCFABLE_DirectSampler (R/FABLE_code.R:212-298): G + B o (Lambda Lambda' - G) + diag(sigma2), B on the fly."""
+    import torch
+    Y, u, d, v = _svd_inputs(n, p, k, 71)
+    MC = 4
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=n + k)
+    want = orc.direct_sampler_psi(Y, 1.0, 1.0, u, v, d, k, gam, z)
+    post = fb.Posterior(Y, 1.0, 1.0, u, v, d, k, 1.0, ctx=ctx)        # a_n = 1/sqrt(n + 1/tau^2): varInflation 1
+    post.set_entrywise_correction(True)
+    psi = torch.zeros((MC, p, p), dtype=torch.float64, device="cuda")
+    dg = torch.from_numpy(np.ascontiguousarray(gam)).cuda(); dz = torch.from_numpy(np.ascontiguousarray(z)).cuda()
+    post.draw_batch(0, MC, dev_psi=psi.data_ptr(), psi_slots=MC, accumulate=True, dev_gam=dg.data_ptr(), dev_z=dz.data_ptr())
+    s1, s2 = post.accum_fetch()
+    got = psi.cpu().numpy().transpose(0, 2, 1)
+    assert relerr_mat(got, want) < TOL
+    assert relerr_mat(s1, want.sum(axis=0)) < TOL and relerr_mat(s2, (want ** 2).sum(axis=0)) < TOL
+    # switching the correction off restores the plain draws
+    post.set_entrywise_correction(False)
+    post.draw_batch(0, MC, dev_psi=psi.data_ptr(), psi_slots=MC, accumulate=False, dev_gam=dg.data_ptr(), dev_z=dz.data_ptr())
+    ctx.synchronize()
+    o = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.0, gam, z)
+    assert relerr_mat(psi[1].cpu().numpy().T, orc.psi_draw(o["LambdaSamples"][1], o["SigmaSqSamples"][1], k)) < TOL
+    post.close()
+
+
 def test_tile_partition_needs_no_collective(ctx):
     """Partition B: two 'ranks' owning disjoint tile slices and processing the same draws fill disjoint
     parts of the accumulators and of every Psi_m; their union is the single-GPU result (p % 16 == 0:
