@@ -242,6 +242,8 @@ def run_b200(args, w, wname):
     m0 = rank * 10_000_000           # disjoint draw ranges per rank (counter-based stream)
     for _ in range(args.warmup):
         post.draw_batch(m0, B, dev_psi=ring.data_ptr(), psi_slots=slots, accumulate=True); m0 += B
+    if world > 1:      # warm the reduction too: NCCL sets its rings / buffers up on the first call of a collective
+        parallel.reduce_posterior_accumulators(post, dev, dst=0)
     post.accum_reset()
     ctx.synchronize()
     clocks = ClockSampler(local); clocks.start()
