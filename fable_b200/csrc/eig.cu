@@ -347,7 +347,8 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     FB_LAUNCHED(ctx);
     const size_t apply_smem = static_cast<size_t>(PW * ASTR + PW * RSTR) * sizeof(double);
     const size_t eig_smem = static_cast<size_t>(2 * PW * (PW + 1)) * sizeof(double);
-    static bool attr = false;
+    static bool attr_dev[64] = {};
+    bool& attr = attr_dev[ctx->device & 63];
     if (!attr) {
       FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem)));
       FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eig_smem)));

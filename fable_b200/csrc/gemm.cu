@@ -186,7 +186,8 @@ template <bool AKF, bool BKF, bool RESID, bool SYRK = false>
 int launch(fable_ctx* ctx, dim3 grid, int64_t M, int64_t N, int64_t K, int64_t kper, double alpha, const double* A,
            int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t split_stride,
            const double* Yres, int64_t ldy) {
-  static bool attr = false;
+  static bool attr_dev[64] = {};
+  bool& attr = attr_dev[ctx->device & 63];
   if (!attr) {
     FB_CUDA(ctx, cudaFuncSetAttribute(k_gemm<AKF, BKF, RESID, SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(kSmemBytes)));

@@ -487,7 +487,8 @@ template <bool MAT, bool ACC, bool CC = false>
 int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned grid, int64_t t0, const CUtensorMap& tmap,
                const CUtensorMap& tsum, const CUtensorMap& tsq) {
   constexpr size_t smem = SMEM_BYTES;
-  static bool attr = false;
+  static bool attr_dev[64] = {};
+  bool& attr = attr_dev[ctx->device & 63];
   if (!attr) {
     FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = true;

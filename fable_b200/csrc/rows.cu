@@ -144,7 +144,8 @@ int fb_rowstats(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t 
   FB_REQUIRE(ctx, NI >= 128, "rowstats: rank too large for the small-k kernel");
   if (NI > round_up(n, 128)) NI = round_up(n, 128);
   const size_t smem = (static_cast<size_t>(k) * NI + static_cast<size_t>(COLS_PER_BLOCK) * k) * sizeof(double);
-  static bool attr_set = false;
+  static bool attr_dev[64] = {};
+  bool& attr_set = attr_dev[ctx->device & 63];
   if (!attr_set) {
     FB_CUDA(ctx, cudaFuncSetAttribute(k_rowstats, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_set = true;
