@@ -31,6 +31,13 @@
 
 #include "common.cuh"
 
+// PSI_LAB: diagnostic builds only (tools/psi_lab.sh, profiles/r01_psi_lab.md): 1 skips the DMMA loop, 2 the operand
+// prefetch, 4 the staging stores, 16 the accumulator loads -- results are then wrong by construction; never defined
+// in the product build.
+#ifndef PSI_LAB
+#define PSI_LAB 0
+#endif
+
 namespace {
 
 constexpr int TILE = 64;
@@ -38,10 +45,19 @@ constexpr int KC = 16;             // rank chunk per pipeline step (multiple of 
 constexpr int OSTR = TILE + 4;     // operand row stride: 68 = 4 mod 16 -> conflict-free DMMA fragment loads
 constexpr int BOXW = 16;           // TMA box row: 16 doubles = 128 bytes = one swizzle row
 constexpr int BOX_DOUBLES = BOXW * TILE;   // 16 x 64 sub-box, 8 KB; 4 sub-boxes per orientation
-constexpr int OP_DOUBLES = 2 * 2 * KC * OSTR;                      // [buf][operand][l][row]
-constexpr size_t OP_BYTES = OP_DOUBLES * sizeof(double);           // 34 KB
-constexpr size_t STAGE_BYTES = 2 * TILE * TILE * sizeof(double);   // direct + mirrored, 32 KB each
-constexpr size_t SMEM_BYTES = OP_BYTES + STAGE_BYTES + 1024;       // + slack to align the boxes to 1024 bytes
+// A CTA owns TILE rows (u) x TV columns (v) of one 64 x 64 tile slot: TV = 64 (one CTA per slot, two CTAs per
+// SM) or TV = 32 (two CTAs per slot, three per SM -- more independent store streams per SM, see fb_psi).
+template <int TV> struct Geo {
+  static constexpr int VSTR = TV + 4;                                  // v-operand row stride (4 mod 16, as OSTR)
+  static constexpr int BUF_DOUBLES = KC * (OSTR + VSTR);               // one operand buffer: [u rows][v rows] x KC
+  static constexpr size_t OP_BYTES = 2 * BUF_DOUBLES * sizeof(double); // double-buffered: 34 KB / 26 KB
+  static constexpr int STAGE_DOUBLES = TILE * TV;                      // one orientation: 32 KB / 16 KB
+  static constexpr size_t SMEM_BYTES = OP_BYTES + 2 * STAGE_DOUBLES * sizeof(double) + 1024;   // + 1 KB alignment slack
+  static constexpr int NWU = TV == 64 ? 2 : 4;                         // warps along u; 8 / NWU along v (16 columns each)
+  static constexpr int WR = TILE / NWU;                                // warp rows: 32 / 16
+  static constexpr int NI = WR / 8;                                    // 8-row DMMA tiles per warp: 4 / 2
+  static constexpr int CTAS = TV == 64 ? 2 : 3;                        // resident CTAs per SM
+};
 
 // Staging layouts = the shared-memory image of 128-byte-swizzled TMA boxes: sub-box q holds 16
 // consecutive rows-of-the-matrix (the contiguous index) for 64 columns; inside a sub-box, row r is 8
@@ -51,8 +67,9 @@ constexpr size_t SMEM_BYTES = OP_BYTES + STAGE_BYTES + 1024;       // + slack to
 // With the DMMA accumulator layout (u = g, v = 2t+e per 8 x 8 tile) the direct 8-byte stores are
 // bank-conflict-free and the mirrored 16-byte stores are 2-way conflicted (dense 512-byte rows
 // would be 4-way / 2-way).
+template <int TV = TILE>
 __device__ __forceinline__ int d_off(int u, int v) {
-  return (u >> 4) * BOX_DOUBLES + v * BOXW + ((((u & 15) >> 1) ^ (v & 7)) << 1) + (u & 1);
+  return (u >> 4) * (BOXW * TV) + v * BOXW + ((((u & 15) >> 1) ^ (v & 7)) << 1) + (u & 1);
 }
 __device__ __forceinline__ int m_off(int u, int v) {
   return (v >> 4) * BOX_DOUBLES + u * BOXW + ((((v & 15) >> 1) ^ (u & 7)) << 1) + (v & 1);
@@ -101,12 +118,7 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, uint64_t 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// the materialised draws are write-once streams: evict_first keeps them from displacing the operands
-__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uint32_t bytes, uint64_t pol) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
-               "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol)
-               : "memory");
-}
+// (the materialised draws are write-once streams: their stores carry evict_first so they do not displace the operands)
 // The p x p x slots output is described to TMA as a 4-D tensor (r_lo = 16 contiguous rows, column,
 // r_hi = row block of 16, slot) so that ONE store moves a whole 64 x 64 tile as a {16, 64, 4, 1} box whose
 // shared-memory image is the four swizzled sub-boxes above (TMA clips the box at the matrix edge).
@@ -155,23 +167,26 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 //   Psi_m = G + B o (Lambda_m Lambda_m' - G) + diag(sigma2_m),  B = cov_correct_matrix(sig_hat, G)  (R:251, 282-290).
 // Slot 0 of Lw then holds G0 as a pseudo-draw (b = -1): its tile product is G, from which B is formed once
 // per CTA (R:196-202) and both stay in registers (64 more: one CTA per SM).
-template <bool MAT, bool ACC, bool CC>
-__global__ void __launch_bounds__(256, CC ? 1 : 2)
-k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_sum,
-      const __grid_constant__ CUtensorMap tmap_sq) {
+template <bool MAT, bool ACC, bool CC, int TV>
+__global__ void __launch_bounds__(256, CC ? 1 : Geo<TV>::CTAS)
+k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_m,
+      const __grid_constant__ CUtensorMap tmap_sum, const __grid_constant__ CUtensorMap tmap_sq) {
+  using G_ = Geo<TV>;
+  constexpr int NI = G_::NI, WR = G_::WR, VSTR = G_::VSTR, BUFD = G_::BUF_DOUBLES, HALVES = TILE / TV;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms: 1 KB aligned
   double* op = reinterpret_cast<double*>(smem_raw);
-  double* D = reinterpret_cast<double*>(smem_raw + OP_BYTES);   // direct   staging (4 swizzled sub-boxes)
-  double* M = D + TILE * TILE;                                  // mirrored staging (4 swizzled sub-boxes)
+  double* D = reinterpret_cast<double*>(smem_raw + G_::OP_BYTES);   // direct   staging (swizzled sub-boxes)
+  double* M = D + G_::STAGE_DOUBLES;                                // mirrored staging (swizzled sub-boxes)
 
   int I, J;
-  if (!tile_of(tile_begin + blockIdx.x, static_cast<int>((a.p + TILE - 1) / TILE), I, J)) return;
+  if (!tile_of(tile_begin + blockIdx.x / HALVES, static_cast<int>((a.p + TILE - 1) / TILE), I, J)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wu = warp & 1, wv = warp >> 1;
-  const int64_t u0 = static_cast<int64_t>(I) * TILE, v0 = static_cast<int64_t>(J) * TILE;
+  const int wu = warp % G_::NWU, wv = warp / G_::NWU;
+  const int64_t u0 = static_cast<int64_t>(I) * TILE, v0 = static_cast<int64_t>(J) * TILE + (blockIdx.x % HALVES) * TV;
   const int64_t p = a.p;
+  if (v0 >= p) return;                           // second half of an edge tile
   const bool diag = (I == J);
   const bool even = a.tma_mode != 0;             // TMA tensor maps exist (1: 4-D whole-tile boxes, 2: 3-D sub-boxes)
   const bool bulk = MAT && even;
@@ -179,7 +194,7 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   const int nch = (K4 + KC - 1) / KC;
   const int nsteps = (a.B + (CC ? 1 : 0)) * nch;
   const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
-  double gq[CC ? 4 : 1][2][2], bq[CC ? 4 : 1][2][2];      // G tile and B tile of the entry-wise correction
+  double gq[CC ? NI : 1][2][2], bq[CC ? NI : 1][2][2];    // G tile and B tile of the entry-wise correction
 
   // threads 0..127 stage the u-operand, 128..255 the v-operand: chunk column = tid & 31 (16 bytes),
   // rank rows (tid >> 5) & 3, +4, +8, +12
@@ -188,19 +203,32 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   auto prefetch = [&](int s, int buf) {
     const int b = s / nch, l0 = (s - b * nch) * KC;
     const int kc = min(KC, K4 - l0);
-    const double* src = a.Lw + (static_cast<int64_t>(b) * a.KP + l0 + pf_l0) * a.pp + pf_col;
-    double* dst = op + buf * (2 * KC * OSTR) + (pf_o * KC + pf_l0) * OSTR + 2 * pf_ch;
+    if (TV == TILE) {
+      const double* src = a.Lw + (static_cast<int64_t>(b) * a.KP + l0 + pf_l0) * a.pp + pf_col;
+      double* dst = op + buf * BUFD + (pf_o * KC + pf_l0) * OSTR + 2 * pf_ch;
 #pragma unroll
-    for (int l = 0; l < KC; l += 4)
-      if (pf_l0 + l < kc) cp_async16(dst + l * OSTR, src + static_cast<int64_t>(l) * a.pp, pol_keep);
+      for (int l = 0; l < KC; l += 4)
+        if (pf_l0 + l < kc) cp_async16(dst + l * OSTR, src + static_cast<int64_t>(l) * a.pp, pol_keep);
+    } else {
+      // 64 u-rows: chunk tid & 31 of rank rows tid >> 5 and + 8; TV v-rows: chunk tid & 15 of rank row tid >> 4
+      const double* base = a.Lw + (static_cast<int64_t>(b) * a.KP + l0) * a.pp;
+      double* dst = op + buf * BUFD;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int l = (tid >> 5) + 8 * h;
+        if (l < kc) cp_async16(dst + l * OSTR + 2 * (tid & 31), base + static_cast<int64_t>(l) * a.pp + u0 + 2 * (tid & 31), pol_keep);
+      }
+      const int l = tid >> 4;
+      if (l < kc) cp_async16(dst + KC * OSTR + l * VSTR + 2 * (tid & 15), base + static_cast<int64_t>(l) * a.pp + v0 + 2 * (tid & 15), pol_keep);
+    }
     cp_async_commit();
   };
 
-  // fragment coordinates: c[i][j][e] is entry (u, v) = (wu*32 + i*8 + g, wv*16 + j*8 + 2t + e) of the tile
-  double acc_s[4][2][2], acc_q[4][2][2];
-  double c[4][2][2];
+  // fragment coordinates: c[i][j][e] is entry (u, v) = (wu*WR + i*8 + g, wv*16 + j*8 + 2t + e) of the tile
+  double acc_s[NI][2][2], acc_q[NI][2][2];
+  double c[NI][2][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NI; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -212,8 +240,8 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
           // batch ends with a plain store (no read-modify-write, no L2 atomics)
           // (materialising kernels only: there the batch is store-bound and the loads are free; the
           // accumulate-only kernel is FP64-bound and keeps zero-init + one TMA reduce-add per batch)
-          const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
-          const bool in = MAT && u < p && v < p;
+          const int64_t u = u0 + wu * WR + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+          const bool in = MAT && !(PSI_LAB & 16) && u < p && v < p;
           acc_s[i][j][e] = in ? __ldcs(a.acc_sum + v * p + u) : 0.0;
           acc_q[i][j][e] = in ? __ldcs(a.acc_sq + v * p + u) : 0.0;
         }
@@ -227,20 +255,20 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
     const int bs = s / nch, ch = s - bs * nch;
     const int b = bs - (CC ? 1 : 0);                   // CC: step group 0 is the G0 pseudo-draw
     const int kc = min(KC, K4 - ch * KC);
-    if (s + 1 < nsteps) prefetch(s + 1, buf ^ 1);      // buf^1 was last read before the previous barrier
+    if (s + 1 < nsteps && !(PSI_LAB & 2)) prefetch(s + 1, buf ^ 1);      // buf^1 was last read before the previous barrier
 
-    const double* As = op + buf * (2 * KC * OSTR) + wu * 32 + g + t * OSTR;
-    const double* Bs = op + buf * (2 * KC * OSTR) + KC * OSTR + wv * 16 + g + t * OSTR;
+    const double* As = op + buf * BUFD + wu * WR + g + t * OSTR;
+    const double* Bs = op + buf * BUFD + KC * OSTR + wv * 16 + g + t * VSTR;
 #pragma unroll
     for (int ks = 0; ks < KC / 4; ++ks) {
-      if (ks * 4 < kc) {
-        double af[4], bf[2];
+      if (ks * 4 < kc && !(PSI_LAB & 1)) {
+        double af[NI], bf[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) af[i] = As[ks * 4 * OSTR + i * 8];
+        for (int i = 0; i < NI; ++i) af[i] = As[ks * 4 * OSTR + i * 8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) bf[j] = Bs[ks * 4 * OSTR + j * 8];
+        for (int j = 0; j < 2; ++j) bf[j] = Bs[ks * 4 * VSTR + j * 8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < NI; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j) dmma(c[i][j], af[i], bf[j]);
       }
@@ -256,12 +284,12 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
         // c holds the G tile: keep it, form B_uv = sqrt(1 + (g_uu g_vv + g_uv^2) / (g_uu s_v + s_u g_vv)), the
         // ratio halved on the diagonal (R/FABLE_code.R:196-202)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < NI; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+              const int64_t u = u0 + wu * WR + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
               double bb = 0.0;
               if (u < p && v < p) {
                 const double gu = a.cc_gdiag[u], gv = a.cc_gdiag[v], su = a.cc_sig[u], sv = a.cc_sig[v];
@@ -276,7 +304,7 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
         continue;
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -284,20 +312,20 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
     }
 
     // ---- draw b of this tile is complete in registers ----------------------------------------
-    if (diag && a.s2w && wu == (wv >> 1)) {
+    if (diag && a.s2w) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int ul = wu * 32 + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t + e;
-            if (ul == vl && u0 + ul < p) c[i][j][e] += a.s2w[static_cast<int64_t>(b) * a.pp + u0 + ul];
+            const int64_t u = u0 + wu * WR + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+            if (u == v && u < p) c[i][j][e] += a.s2w[static_cast<int64_t>(b) * a.pp + u];
           }
     }
     if (ACC) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -309,13 +337,14 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
     if (MAT) {
       if (bulk && tid == 0) bulk_wait_read();         // the previous draw's TMA stores have read the staging
       __syncthreads();
+      if (!(PSI_LAB & 4))
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int ul = wu * 32 + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
-          D[d_off(ul, vl)] = c[i][j][0];
-          D[d_off(ul, vl + 1)] = c[i][j][1];
+          const int ul = wu * WR + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
+          D[d_off<TV>(ul, vl)] = c[i][j][0];
+          D[d_off<TV>(ul, vl + 1)] = c[i][j][1];
           if (!diag) *reinterpret_cast<double2*>(M + m_off(ul, vl)) = make_double2(c[i][j][0], c[i][j][1]);
         }
       if (bulk) fence_async_smem();      // generic-proxy smem writes -> visible to the async (bulk copy) proxy
@@ -331,7 +360,7 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
         if (tid == 0) {
           if (a.tma_mode == 1) {
             tma_store_tile(&tmap, static_cast<int>(v0), static_cast<int>(u0 >> 4), a.slot0 + b, D, pol_stream);
-            if (!diag) tma_store_tile(&tmap, static_cast<int>(u0), static_cast<int>(v0 >> 4), a.slot0 + b, M, pol_stream);
+            if (!diag) tma_store_tile(&tmap_m, static_cast<int>(u0), static_cast<int>(v0 >> 4), a.slot0 + b, M, pol_stream);
           } else {
             for (int q = 0; q < TILE / BOXW; ++q) {
               if (u0 + q * BOXW < p)
@@ -349,7 +378,7 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
         for (int cidx = warp; cidx < TILE; cidx += 8) {
           if (v0 + cidx < p)
             for (int h = 0; h < 2; ++h)
-              if (u0 + lane + 32 * h < p) __stcs(out + (v0 + cidx) * p + u0 + lane + 32 * h, D[d_off(lane + 32 * h, cidx)]);
+              if (u0 + lane + 32 * h < p) __stcs(out + (v0 + cidx) * p + u0 + lane + 32 * h, D[d_off<TV>(lane + 32 * h, cidx)]);
           if (!diag && u0 + cidx < p)
             for (int h = 0; h < 2; ++h)
               if (v0 + lane + 32 * h < p) __stcs(out + (u0 + cidx) * p + v0 + lane + 32 * h, M[m_off(cidx, lane + 32 * h)]);
@@ -357,7 +386,7 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
   }
@@ -368,14 +397,14 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
     // (old value + batch) are staged as two swizzled tiles and leave as plain TMA tensor stores
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int ul = wu * 32 + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
-        D[d_off(ul, vl)] = acc_s[i][j][0];
-        D[d_off(ul, vl + 1)] = acc_s[i][j][1];
-        M[d_off(ul, vl)] = acc_q[i][j][0];      // both accumulators use the direct orientation
-        M[d_off(ul, vl + 1)] = acc_q[i][j][1];
+        const int ul = wu * WR + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
+        D[d_off<TV>(ul, vl)] = acc_s[i][j][0];
+        D[d_off<TV>(ul, vl + 1)] = acc_s[i][j][1];
+        M[d_off<TV>(ul, vl)] = acc_q[i][j][0];      // both accumulators use the direct orientation
+        M[d_off<TV>(ul, vl + 1)] = acc_q[i][j][1];
       }
     fence_async_smem();
     __syncthreads();
@@ -406,12 +435,12 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   } else if (ACC) {
     // odd p (no tensor maps): the register accumulators hold old + batch (MAT) or the batch alone
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NI; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int64_t u = u0 + wu * 32 + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
+          const int64_t u = u0 + wu * WR + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
           if (v < p && u < p) {
             if (MAT) { a.acc_sum[v * p + u] = acc_s[i][j][e]; a.acc_sq[v * p + u] = acc_q[i][j][e]; }
             else { a.acc_sum[v * p + u] += acc_s[i][j][e]; a.acc_sq[v * p + u] += acc_q[i][j][e]; }
@@ -454,7 +483,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // p x p x slots FP64 tensor of column-major matrices, 128-byte swizzle.
 //   p % 16 == 0: 4-D (r_lo 16, column p, r_hi p/16, slot), box {16, 64, 4, 1} = a whole tile per store
 //   p %  2 == 0: 3-D (row p, column p, slot),              box {16, 64, 1}    = one sub-box per store
-int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorMap* out) {
+//   box_cols x (16 * box_rblk) rows per 4-D store: {64, 4} whole 64 x 64 tiles; {32, 4} / {64, 2} the direct / mirrored
+//   image of a 64 x 32 half tile
+int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorMap* out, int box_cols = TILE,
+                    int box_rblk = TILE / BOXW) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -469,7 +501,7 @@ int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorM
   if (p % BOXW == 0) {
     const cuuint64_t dims[4] = {BOXW, up, up / BOXW, static_cast<cuuint64_t>(slots)};
     const cuuint64_t strides[3] = {up * 8, BOXW * 8, up * up * 8};
-    const cuuint32_t box[4] = {BOXW, TILE, TILE / BOXW, 1};
+    const cuuint32_t box[4] = {BOXW, static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rblk), 1};
     r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, psi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
@@ -483,19 +515,34 @@ int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorM
   return FABLE_OK;
 }
 
-template <bool MAT, bool ACC, bool CC = false>
-int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned grid, int64_t t0, const CUtensorMap& tmap,
-               const CUtensorMap& tsum, const CUtensorMap& tsq) {
-  constexpr size_t smem = SMEM_BYTES;
+struct PsiMaps { CUtensorMap out, out_m, sum, sq; };
+
+template <bool MAT, bool ACC, bool CC = false, int TV = TILE>
+int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned slots, int64_t t0, const PsiMaps& m) {
+  constexpr size_t smem = Geo<TV>::SMEM_BYTES;
   static bool attr_dev[64] = {};
   bool& attr = attr_dev[ctx->device & 63];
   if (!attr) {
-    FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC, CC, TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = true;
   }
-  k_psi<MAT, ACC, CC><<<grid, 256, smem, ctx->stream>>>(a, t0, tmap, tsum, tsq);
+  k_psi<MAT, ACC, CC, TV><<<slots * (TILE / TV), 256, smem, ctx->stream>>>(a, t0, m.out, m.out_m, m.sum, m.sq);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
+}
+
+// TV = 32 (half tiles, three CTAs per SM) is used for the materialising kernels whenever whole-tile 4-D stores
+// exist (p % 16 == 0): the batch is bound by how evenly the SMs keep HBM's write queues fed, and three
+// staggered store streams per SM do that better than two (tools/store_lab.cu lab 2).  FABLE_B200_PSI_TV=64
+// forces the whole-tile kernel (A/B measurements).
+int psi_tv(const PsiArgs& a, bool mat) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("FABLE_B200_PSI_TV");
+    forced = e ? atoi(e) : 0;
+  }
+  if (!mat || a.cc_gdiag || a.tma_mode != 1) return TILE;
+  return forced == TILE ? TILE : 32;
 }
 
 }  // namespace
@@ -516,7 +563,7 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
   FB_REQUIRE(ctx, !mat || a.psi_slots >= a.slot0 + a.B, "psi: one output slot per draw of the batch");
   const int64_t nT = ceil_div(a.p, TILE), nSB = ceil_div(nT, SB);
   const int64_t tiles = nSB * (nSB + 1) / 2 * SB * SB;    // super-block order, padding slots exit at once
-  const int64_t chunk = 1 << 30;
+  const int64_t chunk = 1 << 29;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->timing) {
     while (ctx->ev_pool.size() < ctx->ev_used + 2) {
@@ -528,18 +575,20 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
     ctx->ev_used += 2;
     FB_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
   }
-  CUtensorMap tmap, tsum, tsq;
-  memset(&tmap, 0, sizeof(tmap)); memset(&tsum, 0, sizeof(tsum)); memset(&tsq, 0, sizeof(tsq));
+  PsiMaps m;
+  memset(&m, 0, sizeof(m));
+  const int tv = psi_tv(a, mat);
   if (a.tma_mode != 0) {
     if (mat) {
       FB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(a.psi) & 15) == 0, "psi: the output buffer must be 16-byte aligned");
-      FB_TRY(make_output_map(ctx, a.psi, a.p, a.psi_slots, &tmap));
+      FB_TRY(make_output_map(ctx, a.psi, a.p, a.psi_slots, &m.out, tv, TILE / BOXW));
+      FB_TRY(make_output_map(ctx, a.psi, a.p, a.psi_slots, &m.out_m, TILE, tv / BOXW));
     }
     if (acc) {
       FB_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(a.acc_sum) | reinterpret_cast<uintptr_t>(a.acc_sq)) & 15) == 0,
                  "psi: the accumulators must be 16-byte aligned");
-      FB_TRY(make_output_map(ctx, a.acc_sum, a.p, 1, &tsum));
-      FB_TRY(make_output_map(ctx, a.acc_sq, a.p, 1, &tsq));
+      FB_TRY(make_output_map(ctx, a.acc_sum, a.p, 1, &m.sum, tv, TILE / BOXW));
+      FB_TRY(make_output_map(ctx, a.acc_sq, a.p, 1, &m.sq, tv, TILE / BOXW));
     }
   }
   // optional slice of the tile enumeration (multi-GPU partition B: every rank processes all draws for
@@ -551,11 +600,13 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
   }
   for (int64_t t0 = t_lo; t0 < t_hi; t0 += chunk) {
     const unsigned g = static_cast<unsigned>(t_hi - t0 < chunk ? t_hi - t0 : chunk);
-    if (a.cc_gdiag && mat && acc) FB_TRY((launch_psi<true, true, true>(ctx, a, g, t0, tmap, tsum, tsq)));
-    else if (a.cc_gdiag && mat) FB_TRY((launch_psi<true, false, true>(ctx, a, g, t0, tmap, tsum, tsq)));
-    else if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0, tmap, tsum, tsq)));
-    else if (mat) FB_TRY((launch_psi<true, false>(ctx, a, g, t0, tmap, tsum, tsq)));
-    else FB_TRY((launch_psi<false, true>(ctx, a, g, t0, tmap, tsum, tsq)));
+    if (a.cc_gdiag && mat && acc) FB_TRY((launch_psi<true, true, true>(ctx, a, g, t0, m)));
+    else if (a.cc_gdiag && mat) FB_TRY((launch_psi<true, false, true>(ctx, a, g, t0, m)));
+    else if (mat && acc && tv == 32) FB_TRY((launch_psi<true, true, false, 32>(ctx, a, g, t0, m)));
+    else if (mat && tv == 32) FB_TRY((launch_psi<true, false, false, 32>(ctx, a, g, t0, m)));
+    else if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0, m)));
+    else if (mat) FB_TRY((launch_psi<true, false>(ctx, a, g, t0, m)));
+    else FB_TRY((launch_psi<false, true>(ctx, a, g, t0, m)));
   }
   if (ev1) FB_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
   return FABLE_OK;

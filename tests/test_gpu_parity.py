@@ -6,6 +6,7 @@ Tolerance: BASELINE.json north_star -- 1e-10 relative in FP64 (SURVEY.md §8c me
 max|x-ref|/max|ref|, positive vectors element-wise relative, integers exact).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -15,6 +16,8 @@ from fable_b200 import synth
 from oracle import fable_oracle as orc
 from oracle import c_oracle
 from conftest import relerr_mat, relerr_vec, TOL
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -288,9 +291,11 @@ def test_posterior_batches_accumulate_like_one_pass(ctx, c1):
     post.close()
 
 
-@pytest.mark.parametrize("n,p,k,B", [(120, 640, 20, 3), (90, 333, 17, 2), (50, 64, 1, 5)])
+@pytest.mark.parametrize("n,p,k,B", [(120, 640, 20, 3), (90, 333, 17, 2), (50, 64, 1, 5), (60, 16, 2, 2), (60, 80, 3, 3),
+                                     (60, 96, 5, 2), (70, 144, 12, 2), (70, 1104, 10, 2), (70, 150, 4, 2)])
 def test_c4_like_ranks_above_one_chunk(ctx, n, p, k, B):
-    """BASELINE configs[3] in miniature (k = 20 > the 16-row rank chunk; p on / off the TMA paths):
+    """BASELINE configs[3] in miniature (k = 20 > the 16-row rank chunk; p on / off the TMA paths; p a multiple of
+    16 but not of 32 / 64, where the half-tile kernel has clipped boxes and empty second halves):
     materialised draws and accumulators against the oracle rebuilt from the returned samples."""
     import torch
     Y, u, d, v = _svd_inputs(n, p, k, 51)
@@ -376,7 +381,8 @@ def test_syrk_gram(ctx, M, K, akf):
     assert np.array_equal(got, got.T)
 
 
-@pytest.mark.parametrize("p,k", [(1, 1), (63, 1), (64, 2), (65, 3), (130, 13), (200, 20), (257, 33), (320, 10)])
+@pytest.mark.parametrize("p,k", [(1, 1), (16, 1), (48, 4), (63, 1), (64, 2), (65, 3), (80, 2), (96, 7), (112, 5), (130, 13),
+                                 (200, 20), (257, 33), (320, 10), (1040, 3)])
 def test_rankk_cov_ragged_shapes(ctx, p, k):
     """dense A A' + diag(s) (G = G0 G0', CovPostMean) at tile-edge sizes and ranks above one chunk."""
     import torch
@@ -389,6 +395,39 @@ def test_rankk_cov_ragged_shapes(ctx, p, k):
     ctx.synchronize()
     want = A @ A.T + np.diag(s)
     assert relerr_mat(out.cpu().numpy().T, want) < 1e-13
+
+
+def test_whole_tile_kernel_forced_by_env():
+    """FABLE_B200_PSI_TV=64 selects the whole-tile (64 x 64, two CTAs per SM) covariance kernel where the half-tile one
+    is the default (p % 16 == 0): both must produce the same bits (same DMMA order per entry)."""
+    import subprocess, sys
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import fable_b200 as fb
+from fable_b200 import synth
+n, p, k, B = 60, 208, 6, 3
+Y = synth.factor_data(n, p, k, rep=3)
+lam, Q = np.linalg.eigh(Y @ Y.T)
+U = np.asfortranarray(Q[:, ::-1][:, :k]); T = Y.T @ U; d = np.linalg.norm(T, axis=0); V = np.asfortranarray(T / d)
+ctx = fb.Context(0, 99)
+post = fb.Posterior(Y, 1.0, 1.0, U, V, d, k, 1.7, ctx=ctx)
+psi = torch.zeros((B, p, p), dtype=torch.float64, device="cuda")
+post.draw_batch(0, B, dev_psi=psi.data_ptr(), psi_slots=B, accumulate=True)
+s1, s2 = post.accum_fetch()
+np.savez(sys.argv[1], psi=psi.cpu().numpy(), s1=s1, s2=s2)
+""" % ROOT
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for tv in ("32", "64"):
+            path = os.path.join(td, f"tv{tv}.npz")
+            env = dict(os.environ, FABLE_B200_PSI_TV=tv)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+            outs.append(dict(np.load(path)))
+    for key in ("psi", "s1", "s2"):
+        np.testing.assert_array_equal(outs[0][key], outs[1][key])
+    assert np.abs(outs[0]["psi"]).max() > 0
 
 
 # ---- f1: post-processing (mean + exact type-5 sample quantiles) -------------------------------------

@@ -147,9 +147,11 @@ float run_tiles(double* d, int64_t p, int S, int B, int slots, int mirror) {
   return ms;
 }
 
+int lab2_main(int64_t p, int B);
 int main(int argc, char** argv) {
   const int64_t p = argc > 1 ? atoll(argv[1]) : 20000;
   const int B = argc > 2 ? atoi(argv[2]) : 8;
+  if (argc > 3) return lab2_main(p, B);
   const int slots = B;   // one slot per draw: a shorter ring is absorbed by the 126 MB L2 (tile-major order)
   double* d; CK(cudaMalloc(&d, sizeof(double) * p * p * slots));
   CK(cudaMemset(d, 0, sizeof(double) * p * p * slots));
@@ -174,5 +176,86 @@ int main(int argc, char** argv) {
       printf("T=256 kind=cs  order=%2d mirror=%d        %8.1f GB/s\n", S, mirror, g / (run_tiles<256, 1>(d, p, S, B, slots, mirror) * 1e-3));
       printf("T=64  kind=st  order=%2d mirror=%d        %8.1f GB/s\n", S, mirror, g / (run_tiles<64, 0>(d, p, S, B, slots, mirror) * 1e-3));
     }
+  return 0;
+}
+
+// ---- lab 2: stage + TMA tensor store structure of the covariance kernel, without the math -------------
+// Per draw and CTA: wait until the previous stores have read the staging, rewrite the staging (both
+// orientations), fence, barrier, one thread issues the two tensor stores.  TU x TV tile, NT threads,
+// `spin` clocks of dummy work per draw standing in for the math.  Answers: what does this structure reach
+// with 2 agents per SM (64 x 64, 256 threads) vs 4 agents per SM (64 x 32, 128 threads)?
+#include <cuda.h>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CUtensorMap make_map(double* base, int64_t p, int slots, int box_cols, int box_rblk) {
+  void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  CUtensorMap m;
+  const cuuint64_t up = (cuuint64_t)p;
+  const cuuint64_t dims[4] = {16, up, up / 16, (cuuint64_t)slots};
+  const cuuint64_t strides[3] = {up * 8, 16 * 8, up * up * 8};
+  const cuuint32_t box[4] = {16, (cuuint32_t)box_cols, (cuuint32_t)box_rblk, 1}, es[4] = {1, 1, 1, 1};
+  CUresult r = ((EncodeTiledFn)fn)(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(1); }
+  return m;
+}
+template <int TU, int TV, int NT>
+__global__ void __launch_bounds__(NT) k_stage(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapM,
+                                              int nTu, int B, int spin, double* sink) {
+  extern __shared__ unsigned char raw[];
+  unsigned char* al = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+  double* D = reinterpret_cast<double*>(al);
+  double* M = D + TU * TV;
+  // tile (I over TU-row blocks, J over TV-column blocks), upper part only: I*TU <= J*TV + TV - 1
+  const int J = blockIdx.y, I = blockIdx.x;
+  if ((int64_t)I * TU > (int64_t)J * TV + TV - 1) return;
+  const bool diag = ((int64_t)I * TU + TU > (int64_t)J * TV);
+  const int tid = threadIdx.x;
+  double acc = tid;
+  for (int b = 0; b < B; ++b) {
+    if (spin > 0) { const long long t0 = clock64(); while (clock64() - t0 < spin) acc = acc * 1.0000001 + 1e-9; }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    for (int i = tid; i < TU * TV; i += NT) { D[i] = acc + i; M[i] = acc - i; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"((uint64_t)&mapD), "r"(0),
+                   "r"(J * TV), "r"(I * TU / 16), "r"(b), "r"(smem_u32(D)) : "memory");
+      if (!diag)
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"((uint64_t)&mapM), "r"(0),
+                     "r"(I * TU), "r"(J * TV / 16), "r"(b), "r"(smem_u32(M)) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (acc == 12345.678) sink[0] = acc;
+}
+template <int TU, int TV, int NT>
+void run_stage(double* d, int64_t p, int B, int spin, size_t smem_force, const char* label) {
+  CUtensorMap mD = make_map(d, p, B, TV, TU / 16), mM = make_map(d, p, B, TU, TV / 16);
+  size_t smem = 2 * TU * TV * 8 + 1024;
+  if (smem_force > smem) smem = smem_force;
+  CK(cudaFuncSetAttribute(k_stage<TU, TV, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((p + TU - 1) / TU), (unsigned)((p + TV - 1) / TV));
+  double* sink; CK(cudaMalloc(&sink, 8));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_stage<TU, TV, NT><<<grid, NT, smem>>>(mD, mM, 0, 2, spin, sink); CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  k_stage<TU, TV, NT><<<grid, NT, smem>>>(mD, mM, 0, B, spin, sink);
+  CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  printf("%-44s spin=%5d  %8.1f GB/s\n", label, spin, 8.0 * p * p * B / 1e9 / (ms * 1e-3));
+}
+int lab2_main(int64_t p, int B) {
+  double* d; CK(cudaMalloc(&d, sizeof(double) * p * p * B));
+  for (int spin : {0, 2500, 3500, 4000, 4500, 5000}) {
+    run_stage<64, 64, 256>(d, p, B, spin, 100 * 1024, "stage+TMA 64x64, 256 thr, 2 CTAs/SM");
+    run_stage<64, 64, 256>(d, p, B, spin, 70 * 1024, "stage+TMA 64x64, 256 thr, 3 CTAs/SM");
+    run_stage<64, 32, 128>(d, p, B, spin, 50 * 1024, "stage+TMA 64x32, 128 thr, 4 CTAs/SM");
+    run_stage<64, 32, 128>(d, p, B, spin, 35 * 1024, "stage+TMA 64x32, 128 thr, 6 CTAs/SM");
+  }
   return 0;
 }
