@@ -113,6 +113,10 @@ class Context:
     def synchronize(self):
         self.check(_load().fable_ctx_synchronize(self._h))
 
+    def trim_cache(self):
+        """Return the library's idle cached device blocks to the driver (they are reused across calls otherwise)."""
+        self.check(_load().fable_ctx_trim_cache(self._h))
+
     def kernel_timing(self, enable=True):
         """Start (and clear) / stop per-launch CUDA-event timing of the covariance kernel."""
         self.check(_load().fable_ctx_kernel_timing(self._h, C.c_int(1 if enable else 0)))

@@ -12,6 +12,106 @@
 
 #include "common.cuh"
 
+// ---- device block cache (see common.cuh) ----------------------------------------------------------
+#include <mutex>
+#include <unordered_map>
+namespace {
+struct MemCache {
+  std::mutex mu;
+  struct Block { int device; size_t bytes; };
+  std::unordered_map<void*, Block> live;                         // handed out
+  std::multimap<std::pair<int, size_t>, void*> idle;             // (device, rounded bytes) -> block
+  size_t idle_bytes = 0;
+  size_t cap() {
+    static size_t c = [] {
+      const char* e = getenv("FABLE_B200_CACHE_GB");
+      const double gb = e ? atof(e) : 24.0;
+      return static_cast<size_t>((gb < 0 ? 0 : gb) * 1073741824.0);
+    }();
+    return c;
+  }
+  // caller holds mu; frees idle blocks of `device` (all devices if < 0); returns to the caller's device
+  void trim_locked(int device) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto it = idle.begin(); it != idle.end();) {
+      if (device < 0 || it->first.first == device) {
+        cudaSetDevice(it->first.first);
+        cudaFree(it->second);
+        idle_bytes -= it->first.second;
+        it = idle.erase(it);
+      } else {
+        ++it;
+      }
+    }
+    cudaSetDevice(cur);
+  }
+};
+MemCache& mem_cache() { static MemCache* m = new MemCache; return *m; }   // leaked on purpose: outlives static destructors
+size_t mem_round(size_t b) { return b <= (1u << 20) ? (b + 511) / 512 * 512 : (b + (2u << 20) - 1) / (2u << 20) * (2u << 20); }
+}  // namespace
+
+cudaError_t fb_mem_acquire(void** ptr, size_t bytes) {
+  MemCache& m = mem_cache();
+  const size_t rb = mem_round(bytes);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(m.mu);
+  auto it = m.idle.find({dev, rb});
+  if (it != m.idle.end()) {
+    *ptr = it->second;
+    m.idle.erase(it);
+    m.idle_bytes -= rb;
+  } else {
+    e = cudaMalloc(ptr, rb);
+    if (e == cudaErrorMemoryAllocation) {      // the cache may be what is holding the memory: flush and retry once
+      (void)cudaGetLastError();
+      m.trim_locked(dev);
+      e = cudaMalloc(ptr, rb);
+    }
+    if (e != cudaSuccess) { *ptr = nullptr; return e; }
+  }
+  m.live[*ptr] = {dev, rb};
+  return cudaSuccess;
+}
+
+void fb_mem_release(void* ptr) {
+  if (!ptr) return;
+  MemCache& m = mem_cache();
+  std::lock_guard<std::mutex> lk(m.mu);
+  auto it = m.live.find(ptr);
+  if (it == m.live.end()) { cudaFree(ptr); return; }
+  const MemCache::Block b = it->second;
+  m.live.erase(it);
+  // like cudaFree, a release waits for the device: the next owner may use the block on another stream
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cur != b.device) cudaSetDevice(b.device);
+  cudaDeviceSynchronize();
+  if (b.bytes > m.cap()) {
+    cudaFree(ptr);
+  } else {
+    while (m.idle_bytes + b.bytes > m.cap() && !m.idle.empty()) {      // make room: drop the largest idle blocks first
+      auto big = std::prev(m.idle.end());
+      cudaSetDevice(big->first.first);
+      cudaFree(big->second);
+      m.idle_bytes -= big->first.second;
+      m.idle.erase(big);
+    }
+    cudaSetDevice(b.device);
+    m.idle.insert({{b.device, b.bytes}, ptr});
+    m.idle_bytes += b.bytes;
+  }
+  if (cur != b.device) cudaSetDevice(cur);
+}
+
+void fb_mem_trim(int device) {
+  MemCache& m = mem_cache();
+  std::lock_guard<std::mutex> lk(m.mu);
+  m.trim_locked(device);
+}
+
 namespace {
 
 constexpr int KSMALL = 32;   // ranks up to this use the streaming row kernel; above: DMMA residual GEMM
@@ -329,6 +429,7 @@ void fable_ctx_destroy(fable_ctx* ctx) {
     if (ctx->stage_ev[s]) cudaEventDestroy(ctx->stage_ev[s]);
   }
   if (ctx->gemm_ws) cudaFree(ctx->gemm_ws);
+  fb_mem_trim(ctx->device);          // the block cache does not outlive the context that filled it
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -342,6 +443,13 @@ int fable_ctx_set_interrupt(fable_ctx* ctx, int (*poll)(void*), void* user) {
   return FABLE_OK;
 }
 int64_t fable_ctx_launch_count(const fable_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int fable_ctx_trim_cache(fable_ctx* ctx) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_CUDA(ctx, cudaDeviceSynchronize());
+  fb_mem_trim(ctx->device);
+  return FABLE_OK;
+}
 int fable_ctx_synchronize(fable_ctx* ctx) {
   if (!ctx) return FABLE_ERR_INVALID;
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -837,11 +945,15 @@ static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_
       if (need != ctx->ring_bytes) {
         FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->ring) { cudaFree(ctx->ring); ctx->ring = nullptr; ctx->ring_bytes = 0; }
-        FB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->ring), need));
+        if (cudaMalloc(reinterpret_cast<void**>(&ctx->ring), need) != cudaSuccess) {
+          (void)cudaGetLastError();
+          fb_mem_trim(ctx->device);                  // idle cached blocks may be what is in the way
+          FB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->ring), need));
+        }
         ctx->ring_bytes = need;
       }
     }
-    const int B = ctx->ring_slots > 0 ? (ctx->ring_slots < 32 ? ctx->ring_slots : 32) : 32;
+    const int B = ctx->ring_slots > 0 ? (ctx->ring_slots < 64 ? ctx->ring_slots : 64) : 32;
     for (int64_t b0 = 0; b0 < MC; b0 += B) {
       const int nb = static_cast<int>(MC - b0 < B ? MC - b0 : B);
       FB_TRY(fable_posterior_draw_batch(post, m0 + b0, nb, ctx->ring_slots > 0 ? ctx->ring : nullptr,

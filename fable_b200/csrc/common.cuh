@@ -66,6 +66,15 @@ struct fable_ctx {
     FB_CUDA(ctx, cudaGetLastError());    \
   } while (0)
 
+// Device block cache behind DevBuf (api.cu): the entry points allocate the same multi-GB work buffers on every
+// call (accumulators, sample layouts, residuals), and cudaMalloc / cudaFree of such blocks map and unmap device
+// memory synchronously -- tens to hundreds of milliseconds per call, with outliers.  Released blocks are therefore
+// kept per device and handed out again to requests of the same rounded size; the cache is bounded
+// (FABLE_B200_CACHE_GB, default 24), flushed when an allocation fails, and emptied by fb_mem_trim().
+cudaError_t fb_mem_acquire(void** ptr, size_t bytes);
+void fb_mem_release(void* ptr);
+void fb_mem_trim(int device);      // device < 0: every device
+
 // RAII device buffer of doubles (or bytes via raw()).
 struct DevBuf {
   void* ptr = nullptr;
@@ -80,13 +89,13 @@ struct DevBuf {
   }
   ~DevBuf() { release(); }
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) fb_mem_release(ptr);
     ptr = nullptr; bytes = 0;
   }
   cudaError_t alloc(size_t nbytes) {
     release();
     if (nbytes == 0) nbytes = 16;
-    cudaError_t e = cudaMalloc(&ptr, nbytes);
+    cudaError_t e = fb_mem_acquire(&ptr, nbytes);
     if (e == cudaSuccess) bytes = nbytes; else ptr = nullptr;
     return e;
   }
