@@ -20,7 +20,8 @@
 //     next draw; every global run is a full, aligned 512-byte line group written exactly once;
 //   * the HBM accumulators are read into the register accumulators when the CTA starts (latency hidden
 //     behind the first draw) and written back once per batch by TMA tensor stores.
-// Tile = 64 x 64, 256 threads = 8 warps as 2 (u) x 4 (v); warp tile 32 x 16 = 4 x 2 FP64 tensor-core
+// Tile slot = 64 x 64; a CTA (256 threads = 8 warps) owns 64 rows x TV columns of it: TV = 64 (2 x 4 warps of
+// 32 x 16, two CTAs per SM) or TV = 32 (4 x 2 warps of 16 x 16, two CTAs per slot, three per SM); FP64 tensor-core
 // tiles (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no f64 kind), rank padded to a multiple
 // of 4 with zero rows.  DMMA runs at the DFMA rate on sm_100a but needs 6 fragment loads per 8 MMAs
 // (2048 FMAs) instead of 6 loads per 16 DFMAs (512 FMAs), which frees the issue slots and shared-memory
