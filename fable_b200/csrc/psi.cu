@@ -153,6 +153,26 @@ __device__ __forceinline__ void tma_reduce_add_tile(const CUtensorMap* tmap, int
                "r"(0), "r"(col), "r"(rowblk), "r"(0), "r"(smem_u32(ssrc))
                : "memory");
 }
+// accumulator tiles come in by TMA tensor loads (UTMALDG) signalled on an mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred P1;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(const CUtensorMap* tmap, int col, int rowblk, double* sdst, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                   smem_u32(sdst)),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(col), "r"(rowblk), "r"(0), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -203,7 +223,7 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   const int64_t pf_col = (pf_o ? v0 : u0) + 2 * pf_ch;
   auto prefetch = [&](int s, int buf) {
     const int b = s / nch, l0 = (s - b * nch) * KC;
-    const int kc = min(KC, K4 - l0);
+    const int kc = nch == 1 ? a.k : min(KC, K4 - l0);      // single chunk: the zero pad rows are never fetched
     if (TV == TILE) {
       const double* src = a.Lw + (static_cast<int64_t>(b) * a.KP + l0 + pf_l0) * a.pp + pf_col;
       double* dst = op + buf * BUFD + (pf_o * KC + pf_l0) * OSTR + 2 * pf_ch;
@@ -225,6 +245,20 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
     cp_async_commit();
   };
 
+  // Materialising kernels with whole-box tensor maps: the running accumulator tiles are fetched by two TMA tensor
+  // loads into the (still unused) staging buffers and folded into the registers when draw 0 is accumulated.
+  __shared__ uint64_t acc_bar;
+  const bool acc_tma = MAT && ACC && a.tma_mode == 1 && !(PSI_LAB & 16);
+  if (acc_tma) {
+    if (tid == 0) mbar_init(&acc_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&acc_bar, 2 * G_::STAGE_DOUBLES * sizeof(double));
+      tma_load_tile(&tmap_sum, static_cast<int>(v0), static_cast<int>(u0 >> 4), D, &acc_bar);
+      tma_load_tile(&tmap_sq, static_cast<int>(v0), static_cast<int>(u0 >> 4), M, &acc_bar);
+    }
+  }
+
   // fragment coordinates: c[i][j][e] is entry (u, v) = (wu*WR + i*8 + g, wv*16 + j*8 + 2t + e) of the tile
   double acc_s[NI][2][2], acc_q[NI][2][2];
   double c[NI][2][2];
@@ -236,18 +270,32 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
       for (int e = 0; e < 2; ++e) {
         c[i][j][e] = 0.0;
         if (ACC) {
-          // the running HBM accumulators are loaded into the register accumulators up front: the loads
-          // are first needed when draw 0 is folded in, so their latency hides behind its math, and the
-          // batch ends with a plain store (no read-modify-write, no L2 atomics)
-          // (materialising kernels only: there the batch is store-bound and the loads are free; the
-          // accumulate-only kernel is FP64-bound and keeps zero-init + one TMA reduce-add per batch)
+          // without whole-box tensor maps the running HBM accumulators are loaded into the register accumulators
+          // up front; either way they are first needed when draw 0 is folded in, and the batch ends with a plain
+          // store (no read-modify-write, no L2 atomics).  (Materialising kernels only; the accumulate-only
+          // kernel is FP64-bound and keeps zero-init + one TMA reduce-add per batch.)
           const int64_t u = u0 + wu * WR + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
-          const bool in = MAT && !(PSI_LAB & 16) && u < p && v < p;
+          const bool in = MAT && !acc_tma && !(PSI_LAB & 16) && u < p && v < p;
           acc_s[i][j][e] = in ? __ldcs(a.acc_sum + v * p + u) : 0.0;
           acc_q[i][j][e] = in ? __ldcs(a.acc_sq + v * p + u) : 0.0;
         }
       }
 
+  if (nch == 1 && a.k < K4) {
+    // rank rows k..KP-1 are zero padding: clear them once in both operand buffers instead of re-reading zeros from
+    // L2 / HBM for every draw (17 % of the operand traffic at k = 10)
+    const int nz = (K4 - a.k) * (OSTR + VSTR);
+    for (int idx = tid; idx < 2 * nz; idx += 256) {
+      const int buf = idx / nz, r = idx - buf * nz;
+      const int lu = r / OSTR;                       // first the (K4 - k) u-rows, then the v-rows
+      double* base = op + buf * BUFD;
+      if (lu < K4 - a.k) base[(a.k + lu) * OSTR + (r - lu * OSTR)] = 0.0;
+      else {
+        const int rv = r - (K4 - a.k) * OSTR, lv = rv / VSTR;
+        base[KC * OSTR + (a.k + lv) * VSTR + (rv - lv * VSTR)] = 0.0;
+      }
+    }
+  }
   prefetch(0, 0);
   cp_async_wait_all();
   __syncthreads();
@@ -325,6 +373,19 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
           }
     }
     if (ACC) {
+      if (acc_tma && b == 0) {
+        mbar_wait(&acc_bar, 0);
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int ul = wu * WR + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t + e;
+              acc_s[i][j][e] = D[d_off<TV>(ul, vl)];
+              acc_q[i][j][e] = M[d_off<TV>(ul, vl)];
+            }
+      }
 #pragma unroll
       for (int i = 0; i < NI; ++i)
 #pragma unroll
