@@ -33,7 +33,7 @@
 #include "common.cuh"
 
 // PSI_LAB: diagnostic builds only (tools/psi_lab.sh, profiles/r01_psi_lab.md): 1 skips the DMMA loop, 2 the operand
-// prefetch, 4 the staging stores, 16 the accumulator loads -- results are then wrong by construction; never defined
+// prefetch, 4 the staging stores, 16 the accumulator loads, 32 makes every draw read the operands of draw 0 (L2-resident) -- results are then wrong by construction; never defined
 // in the product build.
 #ifndef PSI_LAB
 #define PSI_LAB 0
@@ -222,7 +222,7 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   const int pf_o = tid >> 7, pf_ch = tid & 31, pf_l0 = (tid >> 5) & 3;
   const int64_t pf_col = (pf_o ? v0 : u0) + 2 * pf_ch;
   auto prefetch = [&](int s, int buf) {
-    const int b = s / nch, l0 = (s - b * nch) * KC;
+    const int b = (PSI_LAB & 32) ? 0 : s / nch, l0 = (s - s / nch * nch) * KC;
     const int kc = nch == 1 ? a.k : min(KC, K4 - l0);      // single chunk: the zero pad rows are never fetched
     if (TV == TILE) {
       const double* src = a.Lw + (static_cast<int64_t>(b) * a.KP + l0 + pf_l0) * a.pp + pf_col;
