@@ -431,8 +431,10 @@ np.savez(sys.argv[1], psi=psi.cpu().numpy(), s1=s1, s2=s2)
 
 
 # ---- f1: post-processing (mean + exact type-5 sample quantiles) -------------------------------------
-@pytest.mark.parametrize("MC", [1, 2, 7, 100, 1000, 1025])
+@pytest.mark.parametrize("MC", [1, 2, 7, 100, 1000, 1025, 16384, 16385, 20000, 30011])
 def test_post_processing_against_oracle(ctx, MC):
+    """<= 16384 draws: shared-memory sort; above: radix selection (keys in shared memory up to 25600 draws, in a
+    global scratch beyond)."""
     n, p, k = 40, 9, 2
     Y, u, d, v = _svd_inputs(n, p, k, 41)
     gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=MC)
@@ -451,6 +453,24 @@ def test_post_processing_against_oracle(ctx, MC):
         fb.CCFABLEPostProcessingSubmatrix(o, 0.1, [0, 2], ctx=ctx)
     with pytest.raises(fb.FableError):
         fb.CCFABLEPostProcessingSubmatrix(o, 0.1, [2, p + 1], ctx=ctx)
+
+
+@pytest.mark.parametrize("MC", [1000, 17000, 26000])
+def test_post_processing_ties_and_extreme_levels(ctx, MC):
+    """Draws that take few distinct values (every order statistic sits inside a run of duplicates, some entries are
+    constant, signed zeros occur) and levels outside [0.5/N, (N-0.5)/N] (Armadillo returns min / max there):
+    the sort path and both selection paths against the oracle."""
+    rng = np.random.default_rng(MC)
+    p, k = 5, 3
+    o = {"LambdaSamples": np.asfortranarray(rng.integers(-2, 3, size=(MC, p * k)).astype(np.float64)),
+         "SigmaSqSamples": np.asfortranarray(rng.integers(1, 3, size=(MC, p)).astype(np.float64)), "EstimatedRank": k}
+    o["LambdaSamples"][:, :k] = 0.0                       # variable 1: every cross product is +-0, its variance is sigma^2 only
+    o["LambdaSamples"][::2, 0] = -0.0
+    for alpha in (0.05, 0.5, 1e-7, 1.0):
+        ref = orc.post_processing(o, alpha)
+        got = fb.CPPCCFABLEPostProcessing(o, alpha, ctx=ctx)
+        for key in ("PostMeanMatrix", "LowerQuantileMatrix", "UpperQuantileMatrix"):
+            np.testing.assert_allclose(got[key], ref[key], rtol=1e-12, atol=1e-12, err_msg=f"{key} alpha={alpha}")
 
 
 def test_coverage_pattern_of_the_replication_script(ctx):
