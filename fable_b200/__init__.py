@@ -13,7 +13,7 @@ from .api import (  # noqa: F401
     FABLEHyperParameters, CPPcov_correct_matrix, cov_correct_matrix, var_inflation,
     CPPFABLEPostMean, CPPFABLESampler, CPPsvd, svd, kmax_rule,
     CPPCCFABLEPostProcessing, CCFABLEPostProcessingSubmatrix, CCFABLEPostProcessingSubmatrix_Optimized,
-    default_context, library_path,
+    default_context, library_path, row_posterior,
 )
 from . import synth  # noqa: F401
 
@@ -22,5 +22,5 @@ __all__ = [
     "CPPRankEstimator", "CPPCriterionFunction", "CPPBisectionRecursion", "CPPLogLikelihoodEval", "FABLEHyperParameters",
     "CPPcov_correct_matrix", "cov_correct_matrix", "var_inflation", "CPPFABLEPostMean",
     "CPPFABLESampler", "CPPsvd", "svd", "kmax_rule", "CPPCCFABLEPostProcessing",
-    "CCFABLEPostProcessingSubmatrix", "CCFABLEPostProcessingSubmatrix_Optimized", "default_context", "library_path", "synth",
+    "CCFABLEPostProcessingSubmatrix", "CCFABLEPostProcessingSubmatrix_Optimized", "default_context", "library_path", "row_posterior", "synth",
 ]

@@ -72,6 +72,9 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_dp)
 
 
+_ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int64)
+
+
 class Context:
     """fable_ctx: one device, one stream set.  `seed` keys the Philox stream (fable-philox-v1)."""
 
@@ -112,6 +115,32 @@ class Context:
 
     def synchronize(self):
         self.check(_load().fable_ctx_synchronize(self._h))
+
+    shard = None
+
+    def set_column_shard(self, p_total, col_offset=0, rank=0, world=1, allreduce=None):
+        """Column-sharded estimation (fable_ctx_set_column_shard): this context holds columns
+        [col_offset, col_offset + p_local) of a p_total-column problem; `allreduce(a)` must sum the float64 numpy
+        array `a` over all ranks in place, with identical bits on every rank.  p_total = 0 switches it off."""
+        lib = _load()
+        if not p_total:
+            self.check(lib.fable_ctx_set_column_shard(self._h, _i64(0), _i64(0), C.c_int(0), C.c_int(1), None, None))
+            self.shard = None
+            self._shard_cb = None
+            return
+
+        def _cb(_user, vals, count):
+            try:
+                allreduce(np.ctypeslib.as_array(vals, shape=(count,)))
+                return 0
+            except Exception:            # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = _ALLREDUCE_FN(_cb)
+        self.check(lib.fable_ctx_set_column_shard(self._h, _i64(p_total), _i64(col_offset), C.c_int(rank), C.c_int(world), cb, None))
+        self._shard_cb = cb             # keep the trampoline alive as long as the context uses it
+        self.shard = (int(p_total), int(col_offset), int(rank), int(world))
 
     def trim_cache(self):
         """Return the library's idle cached device blocks to the driver (they are reused across calls otherwise)."""
@@ -166,7 +195,7 @@ def svd(Y, ctx=None):
     ctx = _ctx(ctx)
     Y = _F(Y, "Y")
     n, p = Y.shape
-    r = min(n, p)
+    r = n if ctx.shard else min(n, p)          # column shard: Y holds the local columns, r = min(n, p_total) = n
     U = np.empty((n, r), order="F"); d = np.empty(r); V = np.empty((p, r), order="F")
     ctx.check(_load().fable_svd(ctx._h, _ptr(Y), _i64(n), _i64(p), _ptr(U), _ptr(d), _ptr(V)))
     return {"d": d, "u": U, "v": V}
@@ -391,8 +420,37 @@ def CCFABLEPostProcessingSubmatrix(FABLEOutput, alpha, SelectedIndices, ctx=None
 CCFABLEPostProcessingSubmatrix_Optimized = CCFABLEPostProcessingSubmatrix   # cpp:821-893: same results
 
 
+def row_posterior(Y, gamma0, delta0sq, U_Y, V_Y, svalsY, k, shrunk=True, ctx=None):
+    """fable_row_posterior: the per-variable conjugate posterior -- G0 (p x k), gnd, sig (plug-in
+    sigma^2), sigmahat (posterior mean of sigma^2), tauSq.  Under a column shard: the rows of the local variables."""
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Y, U_Y, V_Y, svalsY)
+    k = int(k)
+    G0 = np.empty((p, k), order="F"); gnd = np.empty(p); sig = np.empty(p); sh = np.empty(p); tau = C.c_double()
+    ctx.check(_load().fable_row_posterior(ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq),
+                                          _ptr(U), _ptr(V), _ptr(d), _i64(r), C.c_int(k), C.c_int(1 if shrunk else 0),
+                                          _ptr(G0), _ptr(gnd), _ptr(sig), _ptr(sh), C.byref(tau)))
+    return {"G0": G0, "gnd": gnd, "sig": sig, "sigmahat": sh, "tausq": tau.value}
+
+
 class Posterior:
     """fable_posterior: the row posterior resident in HBM + batched draw / covariance kernels."""
+
+    @classmethod
+    def from_rows(cls, n, gamma0, delta0sq, rows, varInflation, ctx=None):
+        """fable_posterior_create_from_rows: `rows` = row_posterior(...) output for ALL variables (e.g. gathered
+        from column shards); Y is not needed."""
+        self = cls.__new__(cls)
+        self.ctx = _ctx(ctx)
+        G0 = _F(rows["G0"]); gnd = _F(rows["gnd"]); sig = _F(rows["sig"]); sh = _F(rows["sigmahat"])
+        p, k = G0.shape
+        self.n, self.p, self.k = int(n), p, k
+        h = C.c_void_p()
+        self.ctx.check(_load().fable_posterior_create_from_rows(self.ctx._h, _i64(n), _i64(p), C.c_int(k), C.c_double(gamma0),
+                                                                C.c_double(delta0sq), _ptr(G0), _ptr(gnd), _ptr(sig), _ptr(sh),
+                                                                C.c_double(rows["tausq"]), C.c_double(varInflation), C.byref(h)))
+        self._h = h
+        return self
 
     def __init__(self, Y, gamma0, delta0sq, U_Y, V_Y, svalsY, kEst, varInflation, ctx=None):
         self.ctx = _ctx(ctx)

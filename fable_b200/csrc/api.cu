@@ -124,11 +124,27 @@ struct Inputs {
   int kcols = 0;   // number of leading singular triplets resident
 };
 
+// Column shard (fable_ctx_set_column_shard): Y, V and every per-variable vector hold the columns this context
+// owns; p_total replaces p wherever the reference's formula means "all variables", and sums over variables are
+// completed by the caller's all-reduce.
+inline bool shard_on(const fable_ctx* ctx) { return ctx->shard_p > 0; }
+inline int64_t glob_p(const fable_ctx* ctx, int64_t p_local) { return shard_on(ctx) ? ctx->shard_p : p_local; }
+int shard_sum(fable_ctx* ctx, double* vals, int64_t count) {
+  if (!shard_on(ctx)) return FABLE_OK;
+  if (ctx->shard_fn(ctx->shard_user, vals, count) != 0) return ctx->fail(FABLE_ERR_INVALID, "column shard: the all-reduce callback failed");
+  return FABLE_OK;
+}
+#define FB_NO_SHARD(ctx, what)                                                                                          \
+  FB_REQUIRE(ctx, !shard_on(ctx), what " needs all variables on one device: not available under a column shard "        \
+                                       "(gather the row posterior and use fable_posterior_create_from_rows)")
+
 int check_dims(fable_ctx* ctx, const void* Y, int64_t n, int64_t p, const void* U, const void* V, const void* d,
                int64_t r) {
   FB_REQUIRE(ctx, Y && U && V && d, "NULL input matrix");
   FB_REQUIRE(ctx, n >= 1 && p >= 1, "Y must have at least one row and one column");
-  FB_REQUIRE(ctx, r >= 1 && r <= (n < p ? n : p), "length(svalsY) must be in 1..min(n,p)");
+  FB_REQUIRE(ctx, !shard_on(ctx) || ctx->shard_off + p <= ctx->shard_p, "column shard: offset + local columns exceed p_total");
+  const int64_t pg = glob_p(ctx, p);
+  FB_REQUIRE(ctx, r >= 1 && r <= (n < pg ? n : pg), "length(svalsY) must be in 1..min(n,p)");
   return FABLE_OK;
 }
 
@@ -188,8 +204,9 @@ int criterion_dev(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, doubl
   FB_REQUIRE(ctx, k >= 1 && k <= in.kcols, "criterion: kInd out of range");   // arma: cols(0,k-1) throws
   FB_TRY(row_pass(ctx, in, k, sc, false));
   double sumlog = 0.0;
-  const double dn = static_cast<double>(in.n), dp = static_cast<double>(in.p);
+  const double dn = static_cast<double>(in.n), dp = static_cast<double>(glob_p(ctx, in.p));
   FB_TRY(fb_sum_log_scaled(ctx, sc.resid.d(), in.p, 1.0 / dn, &sumlog));
+  FB_TRY(shard_sum(ctx, &sumlog, 1));                                            // sum over ALL variables (cpp:199)
   if (!std::isfinite(sumlog)) return ctx->fail(FABLE_ERR_NUMERIC, "criterion: non-positive residual variance");
   const double LL = (-dn * dp / 2.0) - (dn * sumlog / 2.0);                     // cpp:199
   const double maxint = dn > dp ? dn : dp, minint = dn < dp ? dn : dp;          // cpp:206-207
@@ -252,7 +269,11 @@ int row_posterior(fable_ctx* ctx, const Inputs& in, int k, double gamma0, double
                   RowPosterior& rp) {
   RowScratch sc;
   FB_TRY(row_pass(ctx, in, k, sc, true));
-  FB_TRY(fb_tausq(ctx, sc.q.d(), sc.resid.d(), in.n, in.p, k, &rp.tausq));
+  double qsum = 0.0;
+  FB_TRY(fb_q_over_sig_sum(ctx, sc.q.d(), sc.resid.d(), in.n, in.p, &qsum));
+  FB_TRY(shard_sum(ctx, &qsum, 1));
+  // mean_j(q_j / sig_j) / (n k) over all variables (cpp:383, :483, :577)
+  rp.tausq = (qsum / static_cast<double>(glob_p(ctx, in.p))) / (static_cast<double>(in.n) * static_cast<double>(k));
   if (!(rp.tausq > 0.0) || !std::isfinite(rp.tausq))
     return ctx->fail(FABLE_ERR_NUMERIC, "row posterior: tauSq estimate is not positive and finite");
   rp.w = static_cast<double>(in.n) + 1.0 / rp.tausq;
@@ -383,6 +404,64 @@ static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_
                            double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
                            double* tausq, double* G, double* psi_sum, double* psi_sumsq);
 
+// Thin SVD of a column-sharded Y (SURVEY 8(e) "Gram/SVD"; n <= p_total, so the Gram side is n): every rank forms the
+// n x n Gram of its own columns on the FP64 tensor cores, the Grams are summed by the caller's all-reduce (the only
+// O(n^2) exchange), the eigensolver runs replicated on bit-identical input -- so every rank holds the same U -- and
+// V = Y'U D^-1 is formed for the local columns only.  d and the sign convention (largest |entry| of each V column
+// positive, first index on ties) need the whole column: one all-reduce of r partial sums of squares and one of the
+// per-rank (max |v|, global row, value) triples.
+static int svd_sharded(fable_ctx* ctx, const double* dY, int64_t n, int64_t p_loc, double* dU, double* dd, double* dV) {
+  const int64_t r = n;
+  DevBuf G, W, tmp;
+  FB_CUDA(ctx, G.alloc(static_cast<size_t>(n) * n * sizeof(double)));
+  FB_CUDA(ctx, W.alloc(static_cast<size_t>(n) * sizeof(double)));
+  FB_CUDA(ctx, tmp.alloc(static_cast<size_t>(3) * r * sizeof(double)));
+  FB_TRY(fb_syrk(ctx, 0, n, p_loc, 1.0, dY, n, G.d(), n));                          // local Y Y'
+  std::vector<double> h(static_cast<size_t>(n) * n);
+  FB_CUDA(ctx, cudaMemcpyAsync(h.data(), G.d(), h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FB_TRY(shard_sum(ctx, h.data(), static_cast<int64_t>(h.size())));
+  FB_CUDA(ctx, cudaMemcpyAsync(G.d(), h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int sweeps = 0;
+  FB_TRY(fb_syevj(ctx, G.d(), n, W.d(), dU, &sweeps));                              // replicated, identical bits
+  FB_TRY(fb_gemm(ctx, 1, 1, p_loc, r, n, 1.0, dY, n, dU, n, dV, p_loc));           // T = Y_loc' U
+  // d_l = || T[:, l] || over all ranks
+  FB_TRY(fb_col_sumsq(ctx, dV, p_loc, p_loc, r, tmp.d()));
+  std::vector<double> ss(r);
+  FB_CUDA(ctx, cudaMemcpyAsync(ss.data(), tmp.d(), r * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FB_TRY(shard_sum(ctx, ss.data(), r));
+  // sign convention: gather every rank's candidate by summing into disjoint slots
+  FB_TRY(fb_col_absmax(ctx, dV, p_loc, p_loc, r, tmp.d(), tmp.d() + r, tmp.d() + 2 * r));
+  std::vector<double> loc(static_cast<size_t>(3) * r), all(static_cast<size_t>(3) * r * ctx->shard_world, 0.0);
+  FB_CUDA(ctx, cudaMemcpyAsync(loc.data(), tmp.d(), loc.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t l = 0; l < r; ++l) {
+    double* slot = all.data() + (static_cast<size_t>(ctx->shard_rank) * r + l) * 3;
+    slot[0] = loc[l]; slot[1] = loc[r + l] + static_cast<double>(ctx->shard_off); slot[2] = loc[2 * r + l];
+  }
+  FB_TRY(shard_sum(ctx, all.data(), static_cast<int64_t>(all.size())));
+  std::vector<double> scale(static_cast<size_t>(2) * r);
+  for (int64_t l = 0; l < r; ++l) {
+    double bm = -1.0, bi = 0.0, bv = 0.0;
+    for (int g = 0; g < ctx->shard_world; ++g) {
+      const double* slot = all.data() + (static_cast<size_t>(g) * r + l) * 3;
+      if (slot[0] > bm || (slot[0] == bm && slot[1] < bi)) { bm = slot[0]; bi = slot[1]; bv = slot[2]; }
+    }
+    const double sgn = bv < 0.0 ? -1.0 : 1.0;
+    const double nv = std::sqrt(ss[l]);
+    ss[l] = nv;
+    scale[l] = nv > 0.0 ? sgn / nv : 0.0;     // V column: normalise and orient
+    scale[r + l] = sgn;                       // U column: orient
+  }
+  FB_CUDA(ctx, cudaMemcpyAsync(tmp.d(), scale.data(), scale.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FB_TRY(fb_col_scale(ctx, dV, p_loc, p_loc, r, tmp.d()));
+  FB_TRY(fb_col_scale(ctx, dU, n, n, r, tmp.d() + r));
+  FB_CUDA(ctx, cudaMemcpyAsync(dd, ss.data(), r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // host vectors go out of scope
+  return FABLE_OK;
+}
+
 extern "C" {
 
 int fable_abi_version(void) { return FABLE_B200_ABI_VERSION; }
@@ -450,6 +529,21 @@ int fable_ctx_trim_cache(fable_ctx* ctx) {
   fb_mem_trim(ctx->device);
   return FABLE_OK;
 }
+int fable_ctx_set_column_shard(fable_ctx* ctx, int64_t p_total, int64_t col_offset, int rank, int world,
+                               fable_allreduce_sum_fn fn, void* user) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  if (p_total == 0) {          // off
+    ctx->shard_p = 0; ctx->shard_off = 0; ctx->shard_rank = 0; ctx->shard_world = 1; ctx->shard_fn = nullptr; ctx->shard_user = nullptr;
+    return FABLE_OK;
+  }
+  FB_REQUIRE(ctx, fn, "column shard: NULL all-reduce callback");
+  FB_REQUIRE(ctx, world >= 1 && rank >= 0 && rank < world, "column shard: need 0 <= rank < world");
+  FB_REQUIRE(ctx, p_total >= 1 && col_offset >= 0 && col_offset <= p_total, "column shard: need 0 <= col_offset <= p_total");
+  ctx->shard_p = p_total; ctx->shard_off = col_offset; ctx->shard_rank = rank; ctx->shard_world = world;
+  ctx->shard_fn = fn; ctx->shard_user = user;
+  return FABLE_OK;
+}
+
 int fable_ctx_synchronize(fable_ctx* ctx) {
   if (!ctx) return FABLE_ERR_INVALID;
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -505,13 +599,16 @@ int fable_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, 
   FB_REQUIRE(ctx, Y && U && d && V, "svd: NULL pointer");
   FB_REQUIRE(ctx, n >= 1 && p >= 1, "svd: Y must have at least one row and one column");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int64_t r = n < p ? n : p;
+  FB_REQUIRE(ctx, !shard_on(ctx) || (n <= ctx->shard_p && ctx->shard_off + p <= ctx->shard_p),
+             "svd under a column shard: needs n <= p_total and offset + local columns <= p_total");
+  const int64_t r = shard_on(ctx) ? n : (n < p ? n : p);
   DevBuf dY, dU, dd, dV;
   FB_TRY(upload(ctx, dY, Y, static_cast<size_t>(n) * p));
   FB_CUDA(ctx, dU.alloc(static_cast<size_t>(n) * r * sizeof(double)));
   FB_CUDA(ctx, dV.alloc(static_cast<size_t>(p) * r * sizeof(double)));
   FB_CUDA(ctx, dd.alloc(static_cast<size_t>(r) * sizeof(double)));
-  FB_TRY(fb_svd(ctx, dY.d(), n, p, dU.d(), dd.d(), dV.d()));
+  if (shard_on(ctx)) FB_TRY(svd_sharded(ctx, dY.d(), n, p, dU.d(), dd.d(), dV.d()));
+  else FB_TRY(fb_svd(ctx, dY.d(), n, p, dU.d(), dd.d(), dV.d()));
   FB_TRY(download(ctx, U, dU.d(), static_cast<size_t>(n) * r));
   FB_TRY(download(ctx, d, dd.d(), static_cast<size_t>(r)));
   FB_TRY(download(ctx, V, dV.d(), static_cast<size_t>(p) * r));
@@ -537,6 +634,7 @@ int fable_kmax(const double* d, int64_t r, double maxProp, int* kMax) {
 int fable_log_likelihood_eval(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* M, const double* Lambda,
                               int k, const double* SigmaSq, double* out) {
   if (!ctx) return FABLE_ERR_INVALID;
+  FB_NO_SHARD(ctx, "CPPLogLikelihoodEval");
   FB_REQUIRE(ctx, Y && M && Lambda && SigmaSq && out, "log_likelihood: NULL pointer");
   FB_REQUIRE(ctx, n >= 1 && p >= 1 && k >= 1, "log_likelihood: need n, p, k >= 1");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -593,6 +691,7 @@ int fable_hyper_parameters(fable_ctx* ctx, const double* Y, int64_t n, int64_t p
                            const double* V, const double* d, int64_t r, int kEst, double* sig, double* G0,
                            double* tausq, double* G) {
   if (!ctx) return FABLE_ERR_INVALID;
+  if (G) FB_NO_SHARD(ctx, "the dense G = G0 G0' of FABLEHyperParameters");
   FB_REQUIRE(ctx, kEst >= 1 && kEst <= r, "kEst must be in 1..length(svalsY)");
   Inputs in;
   FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kEst, in));
@@ -656,6 +755,7 @@ int fable_post_mean(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, doubl
                     const double* U, const double* V, const double* d, int64_t r, int kMax, double* Cov,
                     int* kEst, double* G0s, double* SigmaHat) {
   if (!ctx) return FABLE_ERR_INVALID;
+  FB_NO_SHARD(ctx, "CPPFABLEPostMean (dense CovPostMean)");
   FB_REQUIRE(ctx, kEst, "post_mean: NULL kEst");
   FB_REQUIRE(ctx, kMax >= 1 && kMax <= r, "kMax must be in 1..length(svalsY)");
   Inputs in;
@@ -677,12 +777,68 @@ int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p
                            double delta0sq, const double* U, const double* V, const double* d, int64_t r,
                            int kEst, double varInflation, fable_posterior** out) {
   if (!ctx) return FABLE_ERR_INVALID;
+  FB_NO_SHARD(ctx, "the covariance pass");
   FB_REQUIRE(ctx, out, "posterior_create: NULL out");
   *out = nullptr;
   FB_REQUIRE(ctx, kEst >= 1 && kEst <= r, "kEst must be in 1..length(svalsY)");
   Inputs in;
   FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kEst, in));
   return posterior_from_inputs(ctx, in, gamma0, delta0sq, kEst, varInflation, out);
+}
+
+// The per-variable conjugate posterior of A.2 (cpp:371-391 unshrunk / cpp:470-499 = 564-592 shrunk) as its own entry
+// point: under a column shard every rank computes the rows of its own variables (tauSq is completed by the
+// all-reduce), the ranks exchange these O(p k) numbers, and each builds its sampler from all rows.
+int fable_row_posterior(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
+                        const double* U, const double* V, const double* d, int64_t r, int k, int shrunk, double* G0,
+                        double* gnd, double* sig, double* sigmahat, double* tausq) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, k >= 1 && k <= r, "k must be in 1..length(svalsY)");
+  FB_REQUIRE(ctx, G0 && gnd && sig && sigmahat, "row posterior: NULL output");
+  FB_REQUIRE(ctx, gamma0 + static_cast<double>(n) > 2.0, "gamma0 + n must exceed 2");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, k, in));
+  RowPosterior rp;
+  FB_TRY(row_posterior(ctx, in, k, gamma0, delta0sq, shrunk ? 1 : 0, rp));
+  FB_TRY(download(ctx, G0, rp.G0.d(), static_cast<size_t>(p) * k));
+  FB_TRY(download(ctx, gnd, rp.gnd.d(), p));
+  FB_TRY(download(ctx, sig, rp.sig.d(), p));
+  FB_TRY(download(ctx, sigmahat, rp.sigmahat.d(), p));
+  if (tausq) *tausq = rp.tausq;
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+int fable_posterior_create_from_rows(fable_ctx* ctx, int64_t n, int64_t p, int k, double gamma0, double delta0sq,
+                                     const double* G0, const double* gnd, const double* sig, const double* sigmahat,
+                                     double tausq, double varInflation, fable_posterior** out) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, out, "posterior_create_from_rows: NULL out");
+  *out = nullptr;
+  FB_REQUIRE(ctx, G0 && gnd && sig && sigmahat, "posterior_create_from_rows: NULL input");
+  FB_REQUIRE(ctx, n >= 1 && p >= 1 && k >= 1, "posterior_create_from_rows: n, p, k must be positive");
+  FB_REQUIRE(ctx, tausq > 0.0 && std::isfinite(tausq), "tauSq must be positive and finite");
+  FB_REQUIRE(ctx, varInflation >= 0.0 && std::isfinite(varInflation), "varInflation must be finite and >= 0");
+  FB_REQUIRE(ctx, gamma0 + static_cast<double>(n) > 2.0, "gamma0 + n must exceed 2");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  fable_posterior* post = new (std::nothrow) fable_posterior();
+  if (!post) return ctx->fail(FABLE_ERR_NOMEM, "out of host memory");
+  struct Guard { fable_posterior* p; ~Guard() { delete p; } } guard{post};
+  post->ctx = ctx; post->n = n; post->p = p; post->pp = round_up(p, 64); post->k = k;
+  post->KP = static_cast<int>(round_up(k, 4));
+  post->gamma0 = gamma0; post->delta0sq = delta0sq; post->varInflation = varInflation;
+  post->rp.tausq = tausq;
+  post->rp.w = static_cast<double>(n) + 1.0 / tausq;                          // cpp:584
+  post->rp.gamma_n = gamma0 + static_cast<double>(n);                          // cpp:586
+  FB_TRY(upload(ctx, post->rp.G0, G0, static_cast<size_t>(p) * k));
+  FB_TRY(upload(ctx, post->rp.gnd, gnd, p));
+  FB_TRY(upload(ctx, post->rp.sig, sig, p));
+  FB_TRY(upload(ctx, post->rp.sigmahat, sigmahat, p));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  post->a_n = std::sqrt(varInflation) / std::sqrt(post->rp.w);                 // cpp:597
+  guard.p = nullptr;
+  *out = post;
+  return FABLE_OK;
 }
 
 void fable_posterior_destroy(fable_posterior* post) {
@@ -907,6 +1063,7 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
                   double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
                   double* tausq, double* G, double* psi_sum, double* psi_sumsq) {
   if (!ctx) return FABLE_ERR_INVALID;
+  FB_NO_SHARD(ctx, "CPPFABLESampler");
   FB_REQUIRE(ctx, MC >= 1, "MC must be >= 1");
   FB_REQUIRE(ctx, (gam_inj == nullptr) == (z_inj == nullptr), "injected draws need both gam and z");
   FB_REQUIRE(ctx, (psi_sum == nullptr) == (psi_sumsq == nullptr), "psi_sum and psi_sumsq go together");
@@ -1018,6 +1175,7 @@ extern "C" {
 int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
                                  double maxProp, double* Cov, int* kEst, int* kMaxOut, double* U, double* d, double* V) {
   if (!ctx) return FABLE_ERR_INVALID;
+  FB_NO_SHARD(ctx, "FABLEPosteriorMean");
   FB_REQUIRE(ctx, kEst, "posterior_mean: NULL kEst");
   Pipeline pl;
   FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:87-94
@@ -1038,6 +1196,7 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
                                 double* hypSigma, double* hypG0, double* hypTau, double* hypG, double* varInflationOut,
                                 fable_posterior** out) {
   if (!ctx) return FABLE_ERR_INVALID;
+  FB_NO_SHARD(ctx, "FABLEPosteriorSampler");
   FB_REQUIRE(ctx, out, "sampler_begin: NULL out");
   *out = nullptr;
   Pipeline pl;

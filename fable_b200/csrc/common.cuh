@@ -30,6 +30,12 @@ struct fable_ctx {
   int ring_slots = 0;
   double* ring = nullptr;
   size_t ring_bytes = 0;
+  // column shard (fable_ctx_set_column_shard): this context holds columns [shard_off, shard_off + p_loc) of a
+  // p_total-column problem; sums over columns go through the caller's all-reduce
+  int64_t shard_p = 0, shard_off = 0;
+  int shard_rank = 0, shard_world = 1;
+  int (*shard_fn)(void*, double*, int64_t) = nullptr;
+  void* shard_user = nullptr;
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -117,6 +123,7 @@ int fb_cq(fable_ctx* ctx, const double* dV, int64_t ldv, const double* dd, int64
 int fb_sum_log_scaled(fable_ctx* ctx, const double* d_x, int64_t p, double scale, double* host_out);
 int fb_loglik_terms(fable_ctx* ctx, const double* d_resid, const double* d_sig, int64_t p, double* sum_log_sd,
                     double* sum_resid_over_sig);
+int fb_q_over_sig_sum(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, double* host_sum);
 int fb_tausq(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, int k,
              double* host_tausq);
 int fb_finish_posterior(fable_ctx* ctx, const double* d_c, int64_t ldc, const double* d_s,
@@ -142,6 +149,12 @@ int fb_gemm_resid(fable_ctx* ctx, int64_t n, int64_t p, int k, const double* dY,
 int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps);
 // svd.cu: thin SVD of the device matrix dY (n x p, ld n): dU n x r, dd r, dV p x r (dense lds).
 int fb_svd(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, double* dU, double* dd, double* dV);
+// column-wise pieces of the back-multiplication, for the column-sharded SVD: sums of squares, (max |x|, first row
+// index of it, the signed value there) and x[:, l] *= scale[l]
+int fb_col_sumsq(fable_ctx* ctx, const double* dT, int64_t rows, int64_t ld, int64_t cols, double* d_out);
+int fb_col_absmax(fable_ctx* ctx, const double* dT, int64_t rows, int64_t ld, int64_t cols, double* d_max, double* d_idx,
+                  double* d_val);
+int fb_col_scale(fable_ctx* ctx, double* dT, int64_t rows, int64_t ld, int64_t cols, const double* d_scale);
 // psi.cu
 struct PsiArgs {
   const double* Lw;    // working-layout draws: Lw[(b*KP + l)*pp + j]

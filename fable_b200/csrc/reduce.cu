@@ -203,10 +203,15 @@ int fb_loglik_terms(fable_ctx* ctx, const double* d_resid, const double* d_sig, 
   return reduce_to_host(ctx, ResidOverSig{d_resid, d_sig}, p, sum_resid_over_sig);
 }
 
+// sum_j q_j / sig_j over the columns held here (the numerator of tauSq; all-reduced under a column shard)
+int fb_q_over_sig_sum(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, double* host_sum) {
+  return reduce_to_host(ctx, QOverSig{d_q, d_resid, 1.0 / static_cast<double>(n)}, p, host_sum);
+}
+
 int fb_tausq(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, int k,
              double* host_tausq) {
   double sum = 0.0;
-  FB_TRY(reduce_to_host(ctx, QOverSig{d_q, d_resid, 1.0 / static_cast<double>(n)}, p, &sum));
+  FB_TRY(fb_q_over_sig_sum(ctx, d_q, d_resid, n, p, &sum));
   // mean_j(q_j / sig_j) / (n k)   (cpp:383, :483, :577)
   *host_tausq = (sum / static_cast<double>(p)) / (static_cast<double>(n) * static_cast<double>(k));
   return FABLE_OK;

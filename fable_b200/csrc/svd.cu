@@ -68,7 +68,67 @@ __global__ void __launch_bounds__(ST) k_sign_canon(double* __restrict__ U, int64
   for (int64_t r = threadIdx.x; r < n; r += ST) u[r] = -u[r];
 }
 
+// ---- column-wise pieces for the column-sharded SVD (api.cu svd_sharded) ------------------------------------
+__global__ void __launch_bounds__(ST) k_col_sumsq(const double* __restrict__ T, int64_t rows, int64_t ld, double* __restrict__ out) {
+  const double* x = T + ld * blockIdx.x;
+  double a = 0.0;
+  for (int64_t r = threadIdx.x; r < rows; r += ST) a = fma(x[r], x[r], a);
+  a = block_sum1(a);
+  if (threadIdx.x == 0) out[blockIdx.x] = a;
+}
+
+__global__ void __launch_bounds__(ST) k_col_absmax(const double* __restrict__ T, int64_t rows, int64_t ld, double* __restrict__ omax,
+                                                    double* __restrict__ oidx, double* __restrict__ oval) {
+  __shared__ double bestv[ST];
+  __shared__ long long besti[ST];
+  const double* v = T + ld * blockIdx.x;
+  double bv = -1.0; long long bi = 0;
+  for (int64_t r = threadIdx.x; r < rows; r += ST) {
+    const double a = fabs(v[r]);
+    if (a > bv) { bv = a; bi = r; }
+  }
+  bestv[threadIdx.x] = bv; besti[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = ST / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const double ov = bestv[threadIdx.x + s]; const long long oi = besti[threadIdx.x + s];
+      if (ov > bestv[threadIdx.x] || (ov == bestv[threadIdx.x] && oi < besti[threadIdx.x])) {
+        bestv[threadIdx.x] = ov; besti[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    omax[blockIdx.x] = rows > 0 ? bestv[0] : -1.0;
+    oidx[blockIdx.x] = static_cast<double>(besti[0]);
+    oval[blockIdx.x] = rows > 0 ? v[besti[0]] : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(ST) k_col_scale(double* __restrict__ T, int64_t rows, int64_t ld, const double* __restrict__ scale) {
+  double* x = T + ld * blockIdx.x;
+  const double sc = scale[blockIdx.x];
+  for (int64_t r = threadIdx.x; r < rows; r += ST) x[r] *= sc;
+}
+
 }  // namespace
+
+int fb_col_sumsq(fable_ctx* ctx, const double* dT, int64_t rows, int64_t ld, int64_t cols, double* d_out) {
+  k_col_sumsq<<<static_cast<unsigned>(cols), ST, 0, ctx->stream>>>(dT, rows, ld, d_out);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+int fb_col_absmax(fable_ctx* ctx, const double* dT, int64_t rows, int64_t ld, int64_t cols, double* d_max, double* d_idx,
+                  double* d_val) {
+  k_col_absmax<<<static_cast<unsigned>(cols), ST, 0, ctx->stream>>>(dT, rows, ld, d_max, d_idx, d_val);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+int fb_col_scale(fable_ctx* ctx, double* dT, int64_t rows, int64_t ld, int64_t cols, const double* d_scale) {
+  k_col_scale<<<static_cast<unsigned>(cols), ST, 0, ctx->stream>>>(dT, rows, ld, d_scale);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
 
 int fb_svd(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, double* dU, double* dd, double* dV) {
   const int64_t r = n < p ? n : p;

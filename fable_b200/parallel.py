@@ -10,6 +10,13 @@ Partition B (tiles, BASELINE config 4): rank g owns a set of upper-triangle 64 x
 and processes every draw for them; no collective.  `tile_range` gives the contiguous slice of the
 column-major upper-triangle tile enumeration used by the covariance kernel.
 
+Partition C (columns, estimation: SURVEY.md §8e "Gram/SVD" and "Rank / row-posterior"): rank g holds a block of
+the variables (columns of Y).  `column_range` gives the block, `host_allreduce` the callback the library completes
+its sums over variables with (`Context.set_column_shard`), `sharded_estimation` runs svd -> kMax -> rank search ->
+row posterior -> varInflation on the shards and returns the gathered O(p k) row posterior every rank builds its
+sampler from (`Posterior.from_rows`).  Exchanged: the n x n Gram once, a handful of scalars per criterion
+evaluation, the row posterior once.
+
 The reference has no multi-process code at all: there is nothing to mirror here,
 only its MC loop (src/updated-FABLE-functions.cpp:599-618) and pair loop (:650-688) to shard.
 """
@@ -106,3 +113,64 @@ def gather_sample_rows(local, MC, rank, world, group=None):
     out = np.concatenate(parts, axis=0)
     assert out.shape[0] == MC
     return np.asfortranarray(out)
+
+
+# ---- partition C: column-sharded estimation ---------------------------------------------------------------
+def column_range(p, rank, world):
+    """Contiguous [j_begin, j_end) of the variables (columns of Y) owned by `rank`."""
+    return draw_range(p, rank, world)
+
+
+def host_allreduce(device=None, group=None):
+    """In-place sum of a float64 numpy array over the ranks of `group`: the callback `Context.set_column_shard`
+    needs.  NCCL groups go through a device staging tensor (the library hands over host buffers: the n x n Gram
+    once, a few scalars per criterion evaluation); gloo groups reduce the host buffer directly."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(a):
+        if dist.get_backend(group) == "nccl":
+            t = torch.from_numpy(a).to(device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            a[...] = t.cpu().numpy()
+        else:
+            dist.all_reduce(torch.from_numpy(a), op=dist.ReduceOp.SUM, group=group)
+    return fn
+
+
+def gather_rows(local, p_total, col_offset, allreduce):
+    """Every rank's rows of a per-variable array (p_local, ...) -> the full (p_total, ...) array on every rank:
+    each rank writes its block into zeros and the blocks are summed (disjoint, so the sum is exact)."""
+    local = np.asarray(local, dtype=np.float64)
+    full = np.zeros((int(p_total),) + local.shape[1:], dtype=np.float64)
+    full[col_offset:col_offset + local.shape[0]] = local
+    flat = full.reshape(-1)
+    allreduce(flat)
+    return full
+
+
+def sharded_estimation(Y_local, p_total, col_offset, rank, world, ctx, allreduce, gamma0=1.0, delta0sq=1.0, maxProp=0.95,
+                       variant="wrapper"):
+    """The estimation half of FABLEPosteriorSampler (R/FABLE_wrapper.R:20-44) on column shards: every rank passes
+    its own columns of Y.  Returns, identical on every rank: svd d / u (and the local rows of v), kMax, kEst, the
+    gathered row posterior (G0, gnd, sig, sigmahat, tausq: what `Posterior.from_rows` takes), the plug-in
+    hyper-parameters' sigma^2 and unshrunk G0, and varInflation."""
+    from . import api
+    n = Y_local.shape[0]
+    ctx.set_column_shard(p_total, col_offset, rank, world, allreduce)
+    try:
+        s = api.svd(Y_local, ctx=ctx)                                              # wrapper:23-26
+        kMax = api.kmax_rule(s["d"], maxProp)                                      # wrapper:27
+        kEst = api.CPPRankEstimator(Y_local, s["u"], s["v"], s["d"], kMax, ctx=ctx)   # wrapper:31
+        hyp = api.row_posterior(Y_local, 1.0, 1.0, s["u"], s["v"], s["d"], kEst, shrunk=False, ctx=ctx)   # wrapper:36 (cpp:371-391)
+        rows = api.row_posterior(Y_local, gamma0, delta0sq, s["u"], s["v"], s["d"], kEst, shrunk=True, ctx=ctx)   # cpp:564-592
+    finally:
+        ctx.set_column_shard(0)
+    g = lambda a: gather_rows(a, p_total, col_offset, allreduce)
+    sig_plug = g(hyp["sig"])
+    G0_plug = np.asfortranarray(g(hyp["G0"]))
+    full = {"G0": np.asfortranarray(g(rows["G0"])), "gnd": g(rows["gnd"]), "sig": g(rows["sig"]),
+            "sigmahat": g(rows["sigmahat"]), "tausq": rows["tausq"]}
+    vi = api.var_inflation(sig_plug, G0_plug, variant, ctx=ctx)                    # wrapper:40-44 (replicated: O(p^2 k) flops, no p x p)
+    return {"svd": s, "kMax": kMax, "estRank": kEst, "rows": full, "SigmaSqEstimate": sig_plug, "G0_unshrunk": G0_plug,
+            "tauSqEstimate": hyp["tausq"], "varInflation": vi, "n": n}

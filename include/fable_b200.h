@@ -60,6 +60,22 @@ int64_t fable_ctx_launch_count(const fable_ctx* ctx);
  * repeated calls do not pay cudaMalloc / cudaFree of multi-GB blocks.  This returns the idle blocks to the driver
  * now, e.g. before another library needs the memory.  (No reference counterpart: R's gc() plays this role.) */
 int fable_ctx_trim_cache(fable_ctx* ctx);
+/* ---- column-sharded estimation (multi-GPU: one context per GPU, each holding a block of the variables) ----
+ * The reference has no distributed code; this is how its estimation path (svd -> kMax -> rank search -> row
+ * posterior) shards when p is large: rank g passes only ITS columns of Y (n x p_local) and its rows of V, and the
+ * library completes every sum over variables -- the Gram Y Y' of the SVD, the column norms and the sign convention
+ * of V, sum_j log sigma_j^2 of the criterion (cpp:199), the tauSq mean (cpp:383/483/577) -- through `fn`, which
+ * must sum `count` host doubles element-wise over all ranks IN PLACE with the same bits on every rank (an NCCL /
+ * MPI all-reduce; return 0 on success).  `p_total` = all variables (used wherever the reference's formula has p),
+ * `col_offset` = index of this rank's first column.  U, d, kMax, the criterion, the bisection and kEst come out
+ * identical on every rank; V, G0, gnd, sigma^2 are the local rows.  p_total = 0 switches the shard off.
+ * With a shard set, fable_svd (n <= p_total), fable_criterion, fable_bisection, fable_rank_estimator,
+ * fable_hyper_parameters (G = NULL) and fable_row_posterior work on the local block; entry points that need every
+ * pair of variables on one device (dense p x p outputs, the covariance pass) return FABLE_ERR_INVALID: gather the
+ * O(p k) row posterior and build the sampler with fable_posterior_create_from_rows. */
+typedef int (*fable_allreduce_sum_fn)(void* user, double* vals, int64_t count);
+int fable_ctx_set_column_shard(fable_ctx* ctx, int64_t p_total, int64_t col_offset, int rank, int world,
+                               fable_allreduce_sum_fn fn, void* user);
 int fable_ctx_synchronize(fable_ctx* ctx);
 /* the context's main stream as a cudaStream_t cast to void* (for CUDA-event timing). */
 void* fable_ctx_stream(fable_ctx* ctx);
@@ -178,6 +194,18 @@ int fable_post_processing(fable_ctx* ctx, const double* LambdaSamples, const dou
 int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
                            double delta0sq, const double* U, const double* V, const double* d,
                            int64_t r, int kEst, double varInflation, fable_posterior** out);
+/* The per-variable conjugate posterior by itself: cpp:371-391 (shrunk = 0: G0 = YtU / sqrt(n), the
+ * FABLEHyperParameters form) or cpp:470-499 = 564-592 (shrunk = 1: G0 = sqrt(n)/(n + 1/tauSq) YtU, gnd, the
+ * CPPFABLEPostMean / CPPFABLESampler form).  Outputs: G0 p x k, gnd p, sig = sigma^2 plug-in (cpp:379), sigmahat =
+ * gnd / (gamma_n - 2) (cpp:509), tauSq.  Under a column shard: the local rows, tauSq global. */
+int fable_row_posterior(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
+                        const double* U, const double* V, const double* d, int64_t r, int k, int shrunk, double* G0,
+                        double* gnd, double* sig, double* sigmahat, double* tausq);
+/* The same resident object from an already computed (e.g. gathered from column shards) row posterior: G0 p x k
+ * (shrunk form), gnd, sig, sigmahat p, tauSq.  Y is not needed: a_n = sqrt(varInflation) / sqrt(n + 1/tauSq). */
+int fable_posterior_create_from_rows(fable_ctx* ctx, int64_t n, int64_t p, int k, double gamma0, double delta0sq,
+                                     const double* G0, const double* gnd, const double* sig, const double* sigmahat,
+                                     double tausq, double varInflation, fable_posterior** out);
 void fable_posterior_destroy(fable_posterior* post);
 /* copy-out of the row posterior (NULL to skip): G0s p x k, gnd p, sig p, scalars[4] =
  * {tausq, a_n, gamma_n, w = n + 1/tausq}. */

@@ -611,3 +611,107 @@ def test_c2_full_size_properties(ctx):
     want = Lm @ Lm.T + np.diag(S[0])
     assert relerr_mat(psi[0].cpu().numpy().T, want) < 1e-12
     post.close()
+
+
+# ---- partition C: column-sharded estimation (SURVEY 8(e) "Gram/SVD", "Rank / row-posterior") -----------------
+class _ThreadAllreduce:
+    """In-process stand-in for an NCCL all-reduce: `world` threads, one context each, sum in rank order (so every
+    rank sees the same bits)."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.bar = threading.Barrier(world, timeout=120)
+        self.bufs = [None] * world
+        self.tot = None
+
+    def make(self, rank):
+        def fn(a):
+            self.bufs[rank] = a
+            self.bar.wait()
+            if rank == 0:
+                tot = self.bufs[0].copy()
+                for g in range(1, self.world):
+                    tot += self.bufs[g]
+                self.tot = tot
+            self.bar.wait()
+            a[...] = self.tot
+            self.bar.wait()
+        return fn
+
+
+@pytest.mark.parametrize("n,p,k,cuts", [(60, 200, 3, (0, 90, 200)), (40, 333, 4, (0, 100, 101, 333)), (50, 64, 2, (0, 64))])
+def test_column_sharded_estimation_matches_one_device(ctx, n, p, k, cuts):
+    """Each shard (a thread with its own context, its own columns of Y) runs svd -> kMax -> rank -> row posterior
+    with the sums over variables completed by the all-reduce callback; the result must match the unsharded path
+    and the oracle, and a sampler built from the gathered rows must draw the same samples."""
+    import threading
+    from fable_b200 import parallel
+    Y = synth.factor_data(n, p, k, rep=17)
+    world = len(cuts) - 1
+    ar = _ThreadAllreduce(world)
+    res = [None] * world
+    errs = []
+
+    def work(g):
+        c = fb.Context(0, 4242)
+        try:
+            res[g] = parallel.sharded_estimation(np.asfortranarray(Y[:, cuts[g]:cuts[g + 1]]), p, cuts[g], g, world, c, ar.make(g))
+            post = fb.Posterior.from_rows(n, 1.0, 1.0, res[g]["rows"], res[g]["varInflation"], ctx=c)
+            res[g]["samples"] = post.samples(5, 7)
+            post.close()
+        except Exception as e:                       # noqa: BLE001
+            errs.append((g, e))
+            ar.bar.abort()
+        finally:
+            c.close()
+
+    th = [threading.Thread(target=work, args=(g,)) for g in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+
+    one = fb.FABLEPosteriorSampler(Y, MC=2, ctx=ctx)          # the unsharded wrapper on one context
+    ref = orc.FABLEPosteriorMean(Y, maxProp=0.95)
+    s1 = fb.svd(Y, ctx=ctx)
+    for g in range(world):
+        r = res[g]
+        assert r["estRank"] == one["estRank"] == ref["estRank"]
+        assert relerr_vec(r["svd"]["d"], s1["d"]) < TOL
+        kk = r["estRank"]
+        # leading triplets (the ones the model uses) agree entry-wise, signs included; the whole factorisation reconstructs Y
+        assert relerr_mat(r["svd"]["u"][:, :kk], s1["u"][:, :kk]) < 1e-8
+        assert relerr_mat(r["svd"]["v"][:, :kk], s1["v"][cuts[g]:cuts[g + 1], :kk]) < 1e-8
+        assert relerr_mat((r["svd"]["u"] * r["svd"]["d"]) @ r["svd"]["v"].T, Y[:, cuts[g]:cuts[g + 1]]) < 1e-11
+        np.testing.assert_array_equal(r["svd"]["u"], res[0]["svd"]["u"])          # replicated pieces: identical bits
+        np.testing.assert_array_equal(r["rows"]["G0"], res[0]["rows"]["G0"])
+        assert abs(r["varInflation"] / one["varInflation"] - 1) < TOL
+        st = orc._shrunk_stats(Y, ref["svdY"]["u"], ref["svdY"]["v"], ref["svdY"]["d"], kk, 1.0, 1.0)
+        sgn = np.sign(np.sum(st["G0"] * r["rows"]["G0"], axis=0))                  # oracle SVD signs are LAPACK's
+        assert relerr_mat(r["rows"]["G0"] * sgn, st["G0"]) < TOL
+        assert relerr_vec(r["rows"]["gnd"], st["gnd"]) < TOL and relerr_vec(r["rows"]["sig"], st["sig"]) < TOL
+        assert abs(r["rows"]["tausq"] / st["tausq"] - 1) < TOL
+    # same Philox stream, same row posterior -> same draws as the one-device posterior
+    post1 = fb.Posterior(Y, 1.0, 1.0, s1["u"], s1["v"], s1["d"], one["estRank"], one["varInflation"], ctx=ctx)
+    ctx.set_seed(4242)
+    L1, S1 = post1.samples(5, 7)
+    ctx.set_seed(12345)
+    post1.close()
+    Lg, Sg = res[0]["samples"]
+    assert relerr_mat(Lg, L1) < 1e-9 and relerr_vec(Sg, S1) < 1e-9
+
+
+def test_column_shard_rejects_whole_matrix_entry_points(ctx):
+    Y = synth.factor_data(30, 40, 2, rep=1)
+    s = fb.svd(Y, ctx=ctx)
+    ctx.set_column_shard(80, 0, 0, 1, lambda a: None)
+    try:
+        with pytest.raises(fb.FableError):
+            fb.CPPFABLEPostMean(Y, 1.0, 1.0, s["u"], s["v"], s["d"], 5, ctx=ctx)
+        with pytest.raises(fb.FableError):
+            fb.CPPFABLESampler(Y, 1.0, 1.0, 3, s["u"], s["v"], s["d"], 2, 1.0, ctx=ctx)
+        with pytest.raises(fb.FableError):
+            fb.FABLEHyperParameters(Y, s["u"], s["v"], s["d"], 2, ctx=ctx)            # asks for the dense G
+    finally:
+        ctx.set_column_shard(0)
+    assert fb.CPPRankEstimator(Y, s["u"], s["v"], s["d"], 5, ctx=ctx) >= 1               # back to normal
