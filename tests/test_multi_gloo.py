@@ -81,3 +81,40 @@ def test_sharded_draws_and_allreduce_match_single_process(tmp_path):
     np.testing.assert_array_equal(got["L"], L)                     # samples: bit-identical, disjoint row ranges
     assert np.max(np.abs(got["s1"] - s1)) <= 1e-12 * np.max(np.abs(s1))   # sums: order of addition differs
     assert np.max(np.abs(got["s2"] - s2)) <= 1e-12 * np.max(np.abs(s2))
+
+
+# ---- partition C (columns): the all-reduce callback and the row gather --------------------------------------
+def _worker_columns(rank, world, port, n, p, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    Y = rng.standard_normal((n, p))                       # same matrix on every rank; each uses its own columns
+    j0, j1 = parallel.column_range(p, rank, world)
+    ar = parallel.host_allreduce()
+    gram = np.ascontiguousarray(Y[:, j0:j1] @ Y[:, j0:j1].T).reshape(-1)     # what the library hands to the callback
+    ar(gram)
+    s = np.array([np.sum(np.log(np.sum(Y[:, j0:j1] ** 2, axis=0)))])          # a per-variable sum (criterion pattern)
+    ar(s)
+    rows = parallel.gather_rows(Y[:, j0:j1].T.copy(), p, j0, ar)              # per-variable rows (p_local, n) -> (p, n)
+    vec = parallel.gather_rows(np.arange(j0, j1, dtype=np.float64), p, j0, ar)
+    np.savez(os.path.join(out_dir, f"cols{rank}.npz"), gram=gram, s=s, rows=rows, vec=vec)
+    dist.destroy_process_group()
+
+
+def test_column_shards_allreduce_and_gather(tmp_path):
+    n, p, world = 7, 23, 2
+    for P in (0, 1, 5, 23):
+        r = [parallel.column_range(P, g, 3) for g in range(3)]
+        assert r[0][0] == 0 and r[-1][1] == P and all(r[g][1] == r[g + 1][0] for g in range(2))
+    port = _free_port()
+    mp.start_processes(_worker_columns, args=(world, port, n, p, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    rng = np.random.default_rng(5)
+    Y = rng.standard_normal((n, p))
+    got = [np.load(tmp_path / f"cols{g}.npz") for g in range(world)]
+    for g in range(world):
+        np.testing.assert_allclose(got[g]["gram"].reshape(n, n), Y @ Y.T, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(got[g]["s"][0], np.sum(np.log(np.sum(Y ** 2, axis=0))), rtol=1e-13)
+        np.testing.assert_array_equal(got[g]["rows"], Y.T)                    # disjoint blocks: the gather is exact
+        np.testing.assert_array_equal(got[g]["vec"], np.arange(p, dtype=np.float64))
+        for key in ("gram", "s"):
+            np.testing.assert_array_equal(got[g][key], got[0][key])           # same bits on every rank
