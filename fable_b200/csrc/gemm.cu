@@ -9,6 +9,7 @@
 // C (M x N) = alpha * A B',  A: M x K, B: N x K.  Each operand is either "K-slow" (column-major
 // M x K: element (m,kk) at m + ld*kk) or "K-fast" (element (m,kk) at kk + ld*m).
 // CTA tile 128 x 128 x 16, 8 warps as 2 (M) x 4 (N), warp tile 64 x 32 = 8 x 4 DMMA tiles.
+// The Gram Y Y' of the K-slow layout has its own TMA-staged kernel (k_syrk_tma, below); k_gemm stages through registers:
 // Shared tiles are [kk][m] with row stride 132 doubles (132 mod 16 = 4): the 16 lanes of a
 // half-warp (g = 0..3, t = 0..3) read bank 4t+g -> conflict-free 8-byte fragment loads.
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
