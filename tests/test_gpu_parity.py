@@ -367,7 +367,12 @@ def test_tile_partition_needs_no_collective(ctx):
     post.close()
 
 
-@pytest.mark.parametrize("M,K,akf", [(1, 1, 0), (130, 77, 0), (130, 77, 1), (300, 4000, 0), (257, 1000, 1)])
+@pytest.mark.parametrize("M,K,akf", [(1, 1, 0), (130, 77, 0), (130, 77, 1), (300, 4000, 0), (257, 1000, 1),
+                                     # K-slow with an even leading dimension -> the TMA-staged kernel: one box, K shorter than a
+                                     # k-tile, fewer k-tiles than pipeline stages, M off the 16-row boxes, split-K, many tiles;
+                                     # odd leading dimension -> the register-staged kernel
+                                     (2, 5, 0), (16, 3, 0), (128, 16, 0), (128, 48, 0), (1000, 5000, 0), (129, 64, 0),
+                                     (2064, 1100, 0)])
 def test_syrk_gram(ctx, M, K, akf):
     import torch
     rng = np.random.default_rng(M + K)
