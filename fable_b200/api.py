@@ -551,6 +551,11 @@ def dev_syrk(ctx, a_kfast, M, K, alpha, dA, lda, dC):
                                      _i64(lda), C.c_void_p(dC)))
 
 
+def dev_rowstats(ctx, dY, n, p, dU, dC, ldc, k, ds, dresid):
+    ctx.check(_load().fable_dev_rowstats(ctx._h, C.c_void_p(dY), _i64(n), _i64(p), C.c_void_p(dU), C.c_void_p(dC),
+                                         _i64(ldc), C.c_int(k), C.c_void_p(ds or None), C.c_void_p(dresid)))
+
+
 def dev_syevj(ctx, dG, m, dW, dQ):
     sweeps = C.c_int()
     ctx.check(_load().fable_dev_syevj(ctx._h, C.c_void_p(dG), _i64(m), C.c_void_p(dW), C.c_void_p(dQ),

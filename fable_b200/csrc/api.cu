@@ -1319,6 +1319,15 @@ int fable_dev_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alp
   return fb_syrk(ctx, a_kfast != 0, M, K, alpha, dA, lda, dC, M);
 }
 
+int fable_dev_rowstats(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, const double* dU, const double* dC,
+                       int64_t ldc, int k, double* ds, double* dresid) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, dY && dU && dC && dresid && n >= 1 && p >= 1 && ldc >= p, "rowstats: bad arguments");
+  FB_REQUIRE(ctx, k >= 1 && k <= KSMALL, "rowstats: rank outside the streaming kernel's range");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return fb_rowstats(ctx, dY, n, p, n, dU, n, dC, ldc, k, ds, dresid);
+}
+
 int fable_dev_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps) {
   if (!ctx) return FABLE_ERR_INVALID;
   FB_REQUIRE(ctx, dG && dW && dQ, "syevj: NULL pointer");

@@ -73,9 +73,16 @@ k_rowstats(const double* __restrict__ Y, int64_t n, int64_t p, int64_t ldy, cons
   for (int64_t i0 = 0; i0 < n; i0 += NI) {
     const int ni = static_cast<int>(n - i0 < NI ? n - i0 : NI);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < k * NI; idx += 256) {
-      const int l = idx / NI, i = idx - l * NI;
-      Us[idx] = (i < ni) ? U[i0 + i + ldu * l] : 0.0;
+    for (int idx0 = threadIdx.x; idx0 < k * NI; idx0 += 256 * 8) {     // 8 independent loads in flight per thread
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = idx0 + u * 256, l = idx / NI, i = idx - l * NI;
+        v[u] = (idx < k * NI && i < ni) ? __ldg(U + i0 + i + ldu * l) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (idx0 + u * 256 < k * NI) Us[idx0 + u * 256] = v[u];
     }
     __syncthreads();
     for (int ib = 0; ib < ni; ib += 32 * RW) {
@@ -120,6 +127,207 @@ k_rowstats(const double* __restrict__ Y, int64_t n, int64_t p, int64_t ldy, cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// k_rowstats_mma<KS, IPW>: the same pass with the fit on the FP64 tensor cores (n even, n <= 32 * 16 * IPW rows with
+// KS * IPW <= 6; everything else takes k_rowstats above).
+//
+//   D' = Y_tile' + C_tile (-U_item)'          m8n8k4: M = 8 columns of Y, N = 8 rows of Y, K = 4 ranks
+//
+// In that orientation the accumulator fragment of lane (g, t) is column g, rows (2t, 2t + 1) of an 8 x 8 block:
+// two doubles that are ADJACENT in column-major Y, so an accumulator is initialised from one 16-byte piece of Y
+// (a warp instruction covers 8 columns x 64 contiguous bytes).  A = c (8 columns x 4 ranks), B = -U (4 ranks x
+// 8 rows).
+//
+// Work split: one CTA of 16 warps per SM.  A tile is 8 columns x all n rows, an item 32 rows of a tile (2 KB of Y).
+// G = min(16, items) warps share a tile, the CTA works on 16 / G tiles at a time, warp r of a group owns items r,
+// r + G, ... (at most IPW of them) of EVERY tile its group visits -- so the -U fragments of its items never change
+// and live in registers (KS * IPW * 4 doubles per lane, loaded once): no shared memory is spent on U_k, all of it
+// goes to the prefetch ring.
+// Prefetch: every lane copies ITS OWN accumulator fragments (16-byte cp.async, zero fill past n / p) and c fragments
+// (8-byte cp.async) of the following items into a per-warp ring of S stages (S = what 227 KB allow, 5 at k = 10) laid
+// out in fragment order -- a lane reads back exactly the slots it copied, 512 contiguous bytes per LDS.128, no
+// cross-lane hand-over, no barrier -- and waits with cp.async.wait_group S - 1, which leaves the S - 1 newer items
+// in flight: 128 KB per SM outstanding, re-issued item by item, so the memory pipe never drains.  (A ring of
+// REGISTER buffers cannot do that here: the DMMAs take four of the six scoreboards, all Y loads land on the one
+// that is left, and waiting for the oldest item waits for every load behind it -- measured: depth 3 in the source
+// ran like depth 0.  And with U_k in shared memory only 3 stages fit: 64 KB in flight = latency-bound at 3.5 TB/s.)
+// The per-column partial sums of a group's warps meet once per tile in a double-buffered shared array behind a
+// NAMED barrier of that group only -- groups drift freely against each other -- and are added in warp order:
+// bit-stable.
+constexpr int MW = 16;                 // warps per CTA
+constexpr int ITEM = 32;               // rows per item (4 DMMA column blocks of the transposed product)
+constexpr int MAXS = 8;                // ring stages per warp, at most
+
+__device__ __forceinline__ void dmma_884(double2& c, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp16_zfill(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp8_zfill(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+template <int KS>
+struct RowsMmaCfg {
+  static constexpr int kStage = 2048 + KS * 256;                  // 4 x 512 B of Y fragments, KS x 256 B of c fragments
+  static constexpr int kRed = 2 * MW * 16 * 8;
+  static constexpr int kFit = (227 * 1024 - kRed) / (MW * kStage);
+  static constexpr int S = kFit > MAXS ? MAXS : kFit;              // ring stages per warp (5 at k = 10)
+};
+
+// The loop is written for few instructions per item (the first version spent 275 per 2 KB item -- 64-bit index
+// arithmetic and bounds predicates on every copy -- and was bound by the serial latency of that stream with four
+// warps per scheduler, not by memory): per-lane source pointers advance by constants, validity is one flag per
+// tile plus a 32-bit row compare, predicated-off copies keep their pointer and read 0 bytes, the ring depth is a
+// compile-time constant.
+template <int KS, int IPW>
+__global__ void __launch_bounds__(MW * 32, 1)
+k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const double* __restrict__ U,
+               int64_t ldu, const double* __restrict__ c, int64_t ldc, int k, int nitems, int G, int nsuper,
+               double* __restrict__ s_out, double* __restrict__ resid_out) {
+  constexpr int STB = RowsMmaCfg<KS>::kStage, S = RowsMmaCfg<KS>::S;
+  extern __shared__ __align__(16) double smem[];
+  double* red = smem;                                              // [2][MW][16]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int TC = MW / G, ts = w / G, wr = w - ts * G;              // tile slot of the warp's group, rank in the group
+  if (ts >= TC) return;                                            // 16 % G warps have no group (no CTA barrier below)
+  const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(red + 2 * MW * 16)) + w * (S * STB) + lane * 16;
+  const uint32_t ring_a = ring - lane * 8 + 2048;                  // c fragments: 8 bytes per lane
+  const int sstep = gridDim.x, dcol = 8 * TC * sstep;
+
+  // load cursor: S - 1 items ahead of the work cursor
+  int lst = blockIdx.x, lit = wr, lstage = 0;
+  int lcol = (lst * TC + ts) * 8 + g;
+  bool lok = lst < nsuper && lcol < p;
+  const double* ytile = Y + ldy * lcol + 2 * t;                    // never dereferenced while !lok
+  const int64_t ytile_step = ldy * dcol;
+  const double* cl = c + lcol + ldc * t;
+  const int64_t ldc4 = 4 * ldc;
+  auto issue = [&]() {
+    const uint32_t sb = lstage * STB;
+    const int r0 = lit * ITEM + 2 * t;
+    const double* yp = ytile + lit * ITEM;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) cp16_zfill(ring + sb + nb * 512, yp + nb * 8, (lok && r0 + nb * 8 < n) ? 16 : 0);
+    if (lit == wr) {                                     // first item of a tile: its c fragments ride along
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) cp8_zfill(ring_a + sb + ks * 256, cl + ks * ldc4, (lok && ks * 4 + t < k) ? 8 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    lstage = lstage == S - 1 ? 0 : lstage + 1;
+    lit += G;
+    if (lit >= nitems) {
+      lit = wr; lst += sstep; lcol += dcol; ytile += ytile_step; cl += dcol;
+      lok = lst < nsuper && lcol < p;
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < S - 1; ++d) issue();
+
+  // -U fragments of the warp's own items: B[k = t][n = g] = -U[row g of the block][rank ks * 4 + t]
+  double ub[IPW][KS][4];
+#pragma unroll
+  for (int q = 0; q < IPW; ++q)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const int row = (wr + q * G) * ITEM + nb * 8 + g, l = ks * 4 + t;
+        ub[q][ks][nb] = (row < n && l < k) ? __ldg(U + row + ldu * l) : 0.0;
+      }
+#pragma unroll
+  for (int q = 0; q < IPW; ++q)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) ub[q][ks][nb] = -ub[q][ks][nb];      // after ALL loads are in flight
+
+  int buf = 0, stage = 0;
+  const int bar_id = 1 + ts, bar_threads = G * 32;
+  for (int st = blockIdx.x; st < nsuper; st += sstep) {
+    double ar0 = 0.0, ar1 = 0.0, as0 = 0.0, as1 = 0.0;
+    double a[KS];
+#pragma unroll
+    for (int q = 0; q < IPW; ++q) {
+      if (q == 0 || wr + q * G < nitems) {               // warp-uniform
+        issue();                                         // item + S - 1 into the stage consumed by the previous step
+        asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+        double2 acc[4];
+        const uint32_t sb = stage * STB;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(acc[nb].x), "=d"(acc[nb].y) : "r"(ring + sb + nb * 512) : "memory");
+        if (q == 0) {
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[ks]) : "r"(ring_a + sb + ks * 256) : "memory");
+        }
+        stage = stage == S - 1 ? 0 : stage + 1;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) { as0 = fma(acc[nb].x, acc[nb].x, as0); as1 = fma(acc[nb].y, acc[nb].y, as1); }
+#ifndef ROWS_LAB_NOMATH
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb) dmma_884(acc[nb], a[ks], ub[q][ks][nb]);
+#else
+        acc[0].x += a[0] * ub[q][0][0];
+#endif
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) { ar0 = fma(acc[nb].x, acc[nb].x, ar0); ar1 = fma(acc[nb].y, acc[nb].y, ar1); }
+      }
+    }
+    // the warp's part of this tile is complete
+    double r = ar0 + ar1, s = as0 + as1;
+    r += __shfl_xor_sync(0xffffffffu, r, 1); s += __shfl_xor_sync(0xffffffffu, s, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2); s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const int col = (st * TC + ts) * 8;
+    if (G == 1) {
+      if (t == 0 && col + g < p) {
+        resid_out[col + g] = r;
+        if (s_out) s_out[col + g] = s;
+      }
+    } else {
+      if (t == 0) {
+        red[(buf * MW + w) * 16 + g] = r;
+        red[(buf * MW + w) * 16 + 8 + g] = s;
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+      if (wr == 0 && lane < 16) {
+        double sum = 0.0;
+        for (int w2 = 0; w2 < G; ++w2) sum += red[(buf * MW + w + w2) * 16 + lane];
+        if (col + (lane & 7) < p) {
+          if (lane < 8) resid_out[col + lane] = sum;
+          else if (s_out) s_out[col + lane - 8] = sum;
+        }
+      }
+      buf ^= 1;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int KS, int IPW>
+int launch_rowstats_mma(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t ldy, const double* dU, int64_t ldu,
+                        const double* d_c, int64_t ldc, int k, int nitems, double* d_s, double* d_resid) {
+  using Cfg = RowsMmaCfg<KS>;
+  const size_t smem = Cfg::kRed + static_cast<size_t>(Cfg::S) * MW * Cfg::kStage;
+  static bool attr_dev[64] = {};
+  bool& attr_set = attr_dev[ctx->device & 63];
+  if (!attr_set) {
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_rowstats_mma<KS, IPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  const int G = nitems < MW ? nitems : MW;
+  const int64_t nsuper = ceil_div(ceil_div(p, 8), MW / G);
+  const unsigned grid = static_cast<unsigned>(nsuper < ctx->sms ? nsuper : ctx->sms);
+  k_rowstats_mma<KS, IPW><<<grid, MW * 32, smem, ctx->stream>>>(
+      dY, static_cast<int>(n), static_cast<int>(p), ldy, dU, ldu, d_c, ldc, k, nitems, G, static_cast<int>(nsuper), d_s, d_resid);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
 }  // namespace
 
 int fb_cq(fable_ctx* ctx, const double* dV, int64_t ldv, const double* dd, int64_t p, int k, double* d_c,
@@ -138,6 +346,22 @@ int fb_colsumsq(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t 
 // d_c: p x k (ldc) = YtU; outputs s (may be NULL), resid (sum of squared residuals, NOT divided by n)
 int fb_rowstats(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t ldy, const double* dU,
                 int64_t ldu, const double* d_c, int64_t ldc, int k, double* d_s, double* d_resid) {
+  // tensor-core pass: needs 16-byte aligned row pairs and the warps' -U fragments in registers (KS * IPW <= 6)
+  const char* env_mma = getenv("FABLE_B200_ROWS_MMA");       // 0: force the DFMA kernel (A/B runs, tests)
+  const int use_mma = env_mma ? atoi(env_mma) : 1;
+  if (use_mma && n % 2 == 0 && ldy % 2 == 0 && reinterpret_cast<uintptr_t>(dY) % 16 == 0 && n < (1 << 30) && p < (1 << 27)) {
+    const int KS = (k + 3) / 4;
+    const int64_t nitems = ceil_div(n, ITEM);
+    const int64_t IPW = ceil_div(nitems, MW);
+    const int ni = static_cast<int>(nitems);
+#define FB_ROWS_MMA(KS_, IPW_) \
+    if (KS == KS_ && IPW == IPW_) return launch_rowstats_mma<KS_, IPW_>(ctx, dY, n, p, ldy, dU, ldu, d_c, ldc, k, ni, d_s, d_resid);
+    FB_ROWS_MMA(1, 1) FB_ROWS_MMA(2, 1) FB_ROWS_MMA(3, 1) FB_ROWS_MMA(4, 1) FB_ROWS_MMA(5, 1) FB_ROWS_MMA(6, 1)
+    FB_ROWS_MMA(1, 2) FB_ROWS_MMA(2, 2) FB_ROWS_MMA(3, 2)
+    FB_ROWS_MMA(1, 3) FB_ROWS_MMA(2, 3)
+    FB_ROWS_MMA(1, 4) FB_ROWS_MMA(1, 5) FB_ROWS_MMA(1, 6)
+#undef FB_ROWS_MMA
+  }
   const size_t budget = 96 * 1024 / sizeof(double);
   int64_t NI = (static_cast<int64_t>(budget) - COLS_PER_BLOCK * k) / k;
   NI = NI / 128 * 128;                         // whole 128-row slabs (zero-filled past n)

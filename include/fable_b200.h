@@ -266,6 +266,13 @@ int fable_dev_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alp
 /* symmetric eigen-decomposition of the m x m matrix dG (destroyed): eigenvalues descending in
  * dW (m), eigenvectors in the columns of dQ (m x m). */
 int fable_dev_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps);
+/* Row pass of the conjugate posterior / rank criterion on resident inputs (cpp:371-379 == :470-479 == :564-573,
+ * and the residual of CPPCriterionFunction :161-166): for every variable j, with c = YtU (p x k, ldc),
+ *   resid[j] = sum_i (Y[i,j] - sum_l U[i,l] c[j,l])^2      (NOT divided by n)
+ *   s[j]     = sum_i Y[i,j]^2                              (s may be NULL)
+ * One streaming read of Y (8 n p bytes): the HBM-read-bound kernel of SURVEY 8(d) "Row-posterior". */
+int fable_dev_rowstats(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, const double* dU,
+                       const double* dC, int64_t ldc, int k, double* ds, double* dresid);
 
 #ifdef __cplusplus
 }

@@ -386,6 +386,44 @@ def test_syrk_gram(ctx, M, K, akf):
     assert np.array_equal(got, got.T)
 
 
+@pytest.mark.parametrize("n,p,k", [
+    (1000, 2003, 10),     # C2/C3 geometry: 32 items, all 16 warps on a tile with two items each, ragged last tile
+    (500, 1000, 10),      # C1: 16 items, one per warp
+    (200, 777, 3),        # 7 items (last one 8 rows): 7 warps per tile, two tiles at a time, two warps without a group
+    (64, 100, 1), (2, 5, 1), (66, 9, 4),   # 2, 1 and 3 items: 8, 16 and 5 tiles at a time
+    (320, 4100, 7),       # 10 items, two k-steps
+    (500, 300, 24),       # six k-steps, one item per warp
+    (2000, 300, 4),       # 63 items: up to four per warp
+    (3000, 100, 4),       # 94 items: up to six per warp
+    (1100, 1200, 8),      # 35 items, two k-steps, three per warp
+    (130, 50, 32), (2000, 300, 12), (1000, 1200, 17), (4000, 150, 3),    # fragments beyond the register budget -> DFMA kernel
+    (501, 300, 10),       # odd n: rows are not 16-byte aligned -> DFMA kernel
+    (5000, 200, 10),      # DFMA kernel, U_k staged in two row chunks
+])
+def test_dev_rowstats_both_kernels(ctx, n, p, k, monkeypatch):
+    """fable_dev_rowstats (cpp:371-379 / :161-166): the tensor-core pass and the DFMA pass against numpy."""
+    import torch
+    rng = np.random.default_rng(n * 7 + p + k)
+    Y = np.asfortranarray(rng.standard_normal((n, p)))
+    U = np.asfortranarray(np.linalg.qr(rng.standard_normal((n, k)))[0]) if n >= k else np.asfortranarray(rng.standard_normal((n, k)))
+    c = np.asfortranarray(Y.T @ U + 0.1 * rng.standard_normal((p, k)))
+    want_r = np.sum((Y - U @ c.T) ** 2, axis=0)
+    want_s = np.sum(Y ** 2, axis=0)
+    dY = torch.from_numpy(np.ascontiguousarray(Y.T)).cuda(); dU = torch.from_numpy(np.ascontiguousarray(U.T)).cuda()
+    dc = torch.from_numpy(np.ascontiguousarray(c.T)).cuda()
+    for mma in ("1", "0"):
+        monkeypatch.setenv("FABLE_B200_ROWS_MMA", mma)
+        ds = torch.full((p,), -1.0, dtype=torch.float64, device="cuda"); dr = torch.full((p,), -1.0, dtype=torch.float64, device="cuda")
+        fb.api.dev_rowstats(ctx, dY.data_ptr(), n, p, dU.data_ptr(), dc.data_ptr(), p, k, ds.data_ptr(), dr.data_ptr())
+        ctx.synchronize()
+        assert relerr_vec(dr.cpu().numpy(), want_r) < 1e-12, mma
+        assert relerr_vec(ds.cpu().numpy(), want_s) < 1e-12, mma
+        dr.fill_(-1.0)
+        fb.api.dev_rowstats(ctx, dY.data_ptr(), n, p, dU.data_ptr(), dc.data_ptr(), p, k, 0, dr.data_ptr())   # s not wanted
+        ctx.synchronize()
+        assert relerr_vec(dr.cpu().numpy(), want_r) < 1e-12, mma
+
+
 @pytest.mark.parametrize("p,k", [(1, 1), (16, 1), (48, 4), (63, 1), (64, 2), (65, 3), (80, 2), (96, 7), (112, 5), (130, 13),
                                  (200, 20), (257, 33), (320, 10), (1040, 3)])
 def test_rankk_cov_ragged_shapes(ctx, p, k):
