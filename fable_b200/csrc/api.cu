@@ -148,10 +148,12 @@ int check_dims(fable_ctx* ctx, const void* Y, int64_t n, int64_t p, const void* 
   return FABLE_OK;
 }
 
+int upload_bytes(fable_ctx* ctx, void* dptr, const void* h, size_t bytes);
+int copy_threads();
+
 int upload(fable_ctx* ctx, DevBuf& b, const double* h, size_t count) {
   FB_CUDA(ctx, b.alloc(count * sizeof(double)));
-  FB_CUDA(ctx, cudaMemcpyAsync(b.ptr, h, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  return FABLE_OK;
+  return upload_bytes(ctx, b.ptr, h, count * sizeof(double));
 }
 
 // U is n x r and V is p x r column-major, so their first kcols columns are one contiguous block.
@@ -328,9 +330,7 @@ int download(fable_ctx* ctx, double* h, const double* dptr, size_t count) {
       FB_CUDA(ctx, cudaHostAlloc(&ctx->stage[s], kStageBytes, cudaHostAllocDefault));
       FB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[s], cudaEventDisableTiming));
     }
-  unsigned hw = std::thread::hardware_concurrency();
-  int nthreads = hw >= 16 ? 8 : (hw >= 4 ? static_cast<int>(hw / 2) : 1);
-  if (const char* e = getenv("FABLE_B200_COPY_THREADS")) nthreads = atoi(e);
+  const int nthreads = copy_threads();
   if (nthreads <= 0) {                 // 0: leave the copy to the driver
     FB_CUDA(ctx, cudaMemcpyAsync(h, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return FABLE_OK;
@@ -350,6 +350,43 @@ int download(fable_ctx* ctx, double* h, const double* dptr, size_t count) {
     FB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[i & 1]));
     const size_t off = i * kStageBytes, len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
     parallel_memcpy(dst + off, static_cast<const char*>(ctx->stage[i & 1]), len, nthreads);
+  }
+  return FABLE_OK;
+}
+
+// Host -> device, the mirror image: R hands over PAGEABLE matrices (Y is 160 MB at C3, V_kMax another 150 MB), which
+// a plain cudaMemcpyAsync stages through the driver's single bounce buffer.  Large pageable sources are copied by
+// several host threads into the two pinned staging buffers and sent from there, chunk i + 1 being gathered while
+// chunk i crosses PCIe.
+int copy_threads() {
+  unsigned hw = std::thread::hardware_concurrency();
+  // measured on the 16-thread host of the B200 box, 3.2 GB p x p result into fresh pageable memory: 4 threads 15 GB/s,
+  // 8 threads 25 GB/s, 16 threads 32 GB/s (the copy-out and its first-touch page faults are the limit, not PCIe)
+  int nthreads = hw >= 16 ? 16 : (hw >= 4 ? static_cast<int>(hw / 2) : 1);
+  if (const char* e = getenv("FABLE_B200_COPY_THREADS")) nthreads = atoi(e);
+  return nthreads;
+}
+
+int upload_bytes(fable_ctx* ctx, void* dptr, const void* h, size_t bytes) {
+  const int nthreads = copy_threads();
+  if (bytes < kFastCopyMin || nthreads <= 0 || !is_pageable(h)) {
+    FB_CUDA(ctx, cudaMemcpyAsync(dptr, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return FABLE_OK;
+  }
+  for (int s = 0; s < 2; ++s)
+    if (!ctx->stage[s]) {
+      FB_CUDA(ctx, cudaHostAlloc(&ctx->stage[s], kStageBytes, cudaHostAllocDefault));
+      FB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[s], cudaEventDisableTiming));
+    }
+  const char* src = static_cast<const char*>(h);
+  char* dst = static_cast<char*>(dptr);
+  const size_t nchunks = (bytes + kStageBytes - 1) / kStageBytes;
+  for (size_t i = 0; i < nchunks; ++i) {
+    const size_t off = i * kStageBytes, len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+    FB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[i & 1]));        // the transfer that last used this buffer is done
+    parallel_memcpy(static_cast<char*>(ctx->stage[i & 1]), src + off, len, nthreads);
+    FB_CUDA(ctx, cudaMemcpyAsync(dst + off, ctx->stage[i & 1], len, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(ctx, cudaEventRecord(ctx->stage_ev[i & 1], ctx->stream));
   }
   return FABLE_OK;
 }
@@ -1263,8 +1300,8 @@ int fable_post_processing(fable_ctx* ctx, const double* LambdaSamples, const dou
   FB_CUDA(ctx, dI.alloc(static_cast<size_t>(S) * sizeof(int64_t)));
   for (auto* b : {&dM, &dLo, &dUp}) FB_CUDA(ctx, b->alloc(static_cast<size_t>(S) * S * sizeof(double)));
   if (!selected) {
-    FB_CUDA(ctx, cudaMemcpyAsync(dL.ptr, LambdaSamples, static_cast<size_t>(p) * k * MC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    FB_CUDA(ctx, cudaMemcpyAsync(dS.ptr, SigmaSqSamples, static_cast<size_t>(p) * MC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    FB_TRY(upload_bytes(ctx, dL.ptr, LambdaSamples, static_cast<size_t>(p) * k * MC * sizeof(double)));
+    FB_TRY(upload_bytes(ctx, dS.ptr, SigmaSqSamples, static_cast<size_t>(p) * MC * sizeof(double)));
   } else {
     for (int64_t i = 0; i < S; ++i) {   // the k factor columns of one variable are contiguous in the reference layout
       FB_CUDA(ctx, cudaMemcpyAsync(dL.d() + i * k * MC, LambdaSamples + idx[i] * k * MC, static_cast<size_t>(k) * MC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

@@ -168,9 +168,22 @@ k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int6
       for (int e = 0; e < 2; ++e) H[(wa + i * 8 + g) + PW * (wb + j * 8 + 2 * t + e)] = c[i][j][e];
 }
 
-// two-sided cyclic Jacobi on H (64 x 64, shared memory), rotations accumulated in R; one CTA per pair
-__global__ void __launch_bounds__(256)
-k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, double* __restrict__ Rout, int* __restrict__ nrot) {
+// two-sided cyclic Jacobi on H (64 x 64, shared memory), rotations accumulated in R; one CTA per pair.
+// This kernel is 85-90 % of a round (ncu: gram 10 us, apply 10 us, first version of this one 187 us), i.e. of the
+// whole SVD at n <= 1000, and it is pure latency: 63 dependent steps.  Per step: one warp computes the 32 rotations
+// (one sqrt, one division, one rsqrt: t = 2 h_pq / (d + sign(d) sqrt(d^2 + 4 h_pq^2)), d = h_qq - h_pp, c = rsqrt(1 +
+// t^2) -- the textbook zeta form costs two sqrt and three divisions in sequence), then every 2 x 2 block {p_i, q_i} x
+// {p_j, q_j} of H is rotated from both sides by the one thread that owns it (no barrier between the column and the
+// row update, half the shared-memory traffic) while R <- R J proceeds pair by pair: two barriers per step, 1024
+// threads so that each owns one block and two R pairs (512 threads: +12 %).
+// cross_only: only the 32 x 32 pairs (column of block I, column of block J) are rotated, 32 steps instead of 63.  The
+// pairs inside a block need one visit per outer sweep, not one per round: round 0 of every sweep runs the full 63-step
+// ordering, the other rounds the cross pairs, so an outer sweep is an exact cyclic sweep over all element pairs.  Same
+// 14-15 outer sweeps, 40 % less time (measured at n = 500, 1000, 2000).
+constexpr int EIGT = 1024;
+__global__ void __launch_bounds__(EIGT)
+k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, int cross_only, double* __restrict__ Rout,
+         int* __restrict__ nrot) {
   constexpr int S = PW + 1;
   extern __shared__ double dsm[];
   double* H = dsm;
@@ -179,8 +192,10 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, do
   __shared__ int pp[BW], qq[BW];
   __shared__ int any_rot, need;
   const int tid = threadIdx.x;
+  const int nsteps = cross_only ? BW : PW - 1;
+  const double tol2 = tol * tol;
   const double* src = Hpart + static_cast<int64_t>(blockIdx.x) * nsplit * (PW * PW);
-  for (int idx = tid; idx < PW * PW; idx += 256) {
+  for (int idx = tid; idx < PW * PW; idx += EIGT) {
     double v = 0.0;
     for (int s = 0; s < nsplit; ++s) v += src[static_cast<int64_t>(s) * (PW * PW) + idx];
     const int a = idx & (PW - 1), b = idx >> 6;
@@ -189,12 +204,12 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, do
   }
   if (tid == 0) { any_rot = 0; need = 0; }
   __syncthreads();
-  // does this pair need work at all?  (outer convergence test)
-  for (int idx = tid; idx < PW * PW; idx += 256) {
+  // does this pair need work at all?  (outer convergence test: |h_ab| > tol sqrt(h_aa h_bb))
+  for (int idx = tid; idx < PW * PW; idx += EIGT) {
     const int a = idx & (PW - 1), b = idx >> 6;
     if (a < b) {
       const double h = H[a * S + b];
-      if (h != 0.0 && fabs(h) > tol * sqrt(H[a * S + a]) * sqrt(H[b * S + b])) need = 1;
+      if (h != 0.0 && h * h > tol2 * H[a * S + a] * H[b * S + b]) need = 1;
     }
   }
   __syncthreads();
@@ -203,54 +218,54 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, do
     for (int sweep = 0; sweep < inner; ++sweep) {
       if (tid == 0) any_rot = 0;
       __syncthreads();
-      for (int step = 0; step < PW - 1; ++step) {
+      for (int step = 0; step < nsteps; ++step) {
         if (tid < BW) {
           int a, b;
-          if (tid == 0) { a = PW - 1; b = step; }
+          if (cross_only) { a = tid; b = BW + ((tid + step) & (BW - 1)); }       // column of block I x column of block J
+          else if (tid == 0) { a = PW - 1; b = step; }
           else { a = (step + tid) % (PW - 1); b = (step - tid + (PW - 1)) % (PW - 1); }
           const int p = a < b ? a : b, q = a < b ? b : a;
           const double hpq = H[p * S + q], hpp = H[p * S + p], hqq = H[q * S + q];
           double c_ = 1.0, s_ = 0.0;
-          if (hpq != 0.0 && fabs(hpq) > tol * sqrt(hpp) * sqrt(hqq)) {
-            const double zeta = (hqq - hpp) / (2.0 * hpq);
-            const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            c_ = 1.0 / sqrt(1.0 + tt * tt); s_ = c_ * tt;
+          if (hpq != 0.0 && hpq * hpq > tol2 * hpp * hqq) {
+            const double d = hqq - hpp, h2 = 2.0 * hpq, r2 = fma(d, d, h2 * h2);
+            const double tt = h2 * (1.0 / (d + copysign(r2 * rsqrt(r2), d)));      // rsqrt, reciprocal, rsqrt: no general division
+            c_ = rsqrt(fma(tt, tt, 1.0)); s_ = c_ * tt;
             any_rot = 1;
           }
           cs[tid] = c_; sn[tid] = s_; pp[tid] = p; qq[tid] = q;
         }
         __syncthreads();
-        // columns: H <- H J, R <- R J
-        for (int idx = tid; idx < BW * PW; idx += 256) {
+        // H <- J' H J, block by block
+        for (int blk = tid; blk < BW * BW; blk += EIGT) {
+          const int ri = blk >> 5, rj = blk & (BW - 1);
+          const double c1 = cs[ri], s1 = sn[ri], c2 = cs[rj], s2 = sn[rj];
+          if (s1 != 0.0 || s2 != 0.0) {
+            const int p1 = pp[ri], q1 = qq[ri], p2 = pp[rj], q2 = qq[rj];
+            const double hpp_ = H[p1 * S + p2], hpq_ = H[p1 * S + q2], hqp_ = H[q1 * S + p2], hqq_ = H[q1 * S + q2];
+            const double ap = c2 * hpp_ - s2 * hpq_, bp = s2 * hpp_ + c2 * hpq_;     // columns, row p1
+            const double aq = c2 * hqp_ - s2 * hqq_, bq = s2 * hqp_ + c2 * hqq_;     // columns, row q1
+            H[p1 * S + p2] = c1 * ap - s1 * aq; H[q1 * S + p2] = s1 * ap + c1 * aq;  // rows
+            H[p1 * S + q2] = c1 * bp - s1 * bq; H[q1 * S + q2] = s1 * bp + c1 * bq;
+          }
+        }
+        // R <- R J
+        for (int idx = tid; idx < BW * PW; idx += EIGT) {
           const int r = idx >> 6, i = idx & (PW - 1);
           const double c_ = cs[r], s_ = sn[r];
           if (s_ != 0.0) {
             const int p = pp[r], q = qq[r];
-            const double hp = H[i * S + p], hq = H[i * S + q];
-            H[i * S + p] = c_ * hp - s_ * hq; H[i * S + q] = s_ * hp + c_ * hq;
             const double rp = R[i * S + p], rq = R[i * S + q];
             R[i * S + p] = c_ * rp - s_ * rq; R[i * S + q] = s_ * rp + c_ * rq;
           }
         }
         __syncthreads();
-        // rows: H <- J' H
-        for (int idx = tid; idx < BW * PW; idx += 256) {
-          const int r = idx >> 6, j = idx & (PW - 1);
-          const double c_ = cs[r], s_ = sn[r];
-          if (s_ != 0.0) {
-            const int p = pp[r], q = qq[r];
-            const double hp = H[p * S + j], hq = H[q * S + j];
-            H[p * S + j] = c_ * hp - s_ * hq; H[q * S + j] = s_ * hp + c_ * hq;
-          }
-        }
-        __syncthreads();
       }
       if (!any_rot) break;
-      __syncthreads();
     }
   }
   double* Rg = Rout + static_cast<int64_t>(blockIdx.x) * (PW * PW);
-  for (int idx = tid; idx < PW * PW; idx += 256) {
+  for (int idx = tid; idx < PW * PW; idx += EIGT) {
     const int a = idx & (PW - 1), b = idx >> 6;
     Rg[a + PW * b] = R[a * S + b];          // column-major 64 x 64
   }
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(256) k_bj_copy_in(const double* __restrict__ G
 int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps_out) {
   FB_REQUIRE(ctx, m > 0 && m < (1 << 30), "syevj: bad dimension");
   const int N = static_cast<int>(m + (m & 1));
-  const double tol = std::sqrt(static_cast<double>(m)) * 2.220446049250313e-16;
+  const double tol = std::sqrt(static_cast<double>(m)) * 2.220446049250313e-16 * (getenv("FABLE_B200_BJ_TOL") ? atof(getenv("FABLE_B200_BJ_TOL")) : 1.0);
   DevBuf cnt, nrm, perm;
   FB_CUDA(ctx, cnt.alloc(sizeof(int)));
   FB_CUDA(ctx, nrm.alloc(m * sizeof(double)));
@@ -334,6 +349,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     const int64_t ld = round_up(m, 16), ncols = static_cast<int64_t>(NB) * BW;
     const int npairs = NB / 2;
     const int inner = getenv("FABLE_B200_BJ_INNER") ? atoi(getenv("FABLE_B200_BJ_INNER")) : 1;
+    const int cross = getenv("FABLE_B200_BJ_CROSS") ? atoi(getenv("FABLE_B200_BJ_CROSS")) : 1;
     int64_t nsplit = ceil_div(2 * static_cast<int64_t>(ctx->sms), npairs);
     if (nsplit > ld / 64) nsplit = ld / 64 > 0 ? ld / 64 : 1;
     const int64_t rows_per_split = round_up(ceil_div(ld, nsplit), GKT);
@@ -359,7 +375,8 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
       for (int r = 0; r < NB - 1; ++r) {
         k_bj_gram<<<dim3(npairs, static_cast<unsigned>(nsplit)), 128, 0, ctx->stream>>>(Wbuf.d(), ld, rows_per_split, ld, r, NB,
                                                                                          Hpart.d());
-        k_bj_eig<<<npairs, 256, eig_smem, ctx->stream>>>(Hpart.d(), static_cast<int>(nsplit), tol, inner, Rall.d(), static_cast<int*>(cnt.ptr));
+        k_bj_eig<<<npairs, EIGT, eig_smem, ctx->stream>>>(Hpart.d(), static_cast<int>(nsplit), tol, inner, (cross && r > 0) ? 1 : 0, Rall.d(),
+                                                         static_cast<int*>(cnt.ptr));
         k_bj_apply<<<dim3(npairs, static_cast<unsigned>(ceil_div(ld, 128))), 256, apply_smem, ctx->stream>>>(Wbuf.d(), ld, r, NB,
                                                                                                              Rall.d());
         ctx->launches += 3;
