@@ -195,12 +195,31 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, in
   const int nsteps = cross_only ? BW : PW - 1;
   const double tol2 = tol * tol;
   const double* src = Hpart + static_cast<int64_t>(blockIdx.x) * nsplit * (PW * PW);
-  for (int idx = tid; idx < PW * PW; idx += EIGT) {
-    double v = 0.0;
-    for (int s = 0; s < nsplit; ++s) v += src[static_cast<int64_t>(s) * (PW * PW) + idx];
-    const int a = idx & (PW - 1), b = idx >> 6;
-    H[a * S + b] = v;
-    R[a * S + b] = (a == b) ? 1.0 : 0.0;
+  {
+    // partial Grams of the row splits, added in split order; the loads of a thread's four entries go out together,
+    // eight splits at a time (one load per iteration = nsplit x 4 serial L2 round trips, 20 us of a 50 us kernel)
+    constexpr int NE = PW * PW / EIGT;
+    double v[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) v[e] = 0.0;
+    for (int s0 = 0; s0 < nsplit; s0 += 8) {
+      double x[8][NE];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+          x[u][e] = (s0 + u < nsplit) ? __ldg(src + static_cast<int64_t>(s0 + u) * (PW * PW) + tid + e * EIGT) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) v[e] += x[u][e];
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int idx = tid + e * EIGT, a = idx & (PW - 1), b = idx >> 6;
+      H[a * S + b] = v[e];
+      R[a * S + b] = (a == b) ? 1.0 : 0.0;
+    }
   }
   if (tid == 0) { any_rot = 0; need = 0; }
   __syncthreads();
@@ -340,7 +359,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
   FB_CUDA(ctx, perm.alloc(m * sizeof(int)));
   int sweeps = 0;
   const int max_sweeps = 40;
-  constexpr int64_t kBlockMin = 256;
+  const int64_t kBlockMin = getenv("FABLE_B200_BJ_MIN") ? atoll(getenv("FABLE_B200_BJ_MIN")) : 16;      // block path from m = 17 on: 2x the scalar rounds even at m = 64 (measured)
   DevBuf Wbuf;
   double* Acols = dG;          // matrix whose columns end up as lambda_i q_i, leading dimension lda
   int64_t lda = m;
