@@ -188,6 +188,7 @@ def run_b200(args, w, wname):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        parallel.share_host_threads(int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         torch.cuda.set_device(local)
         # NCCL prints its version banner to stdout when the communicator is created: keep stdout to the one
         # JSON line by pointing fd 1 at stderr while the group and its first collective come up

@@ -22,7 +22,18 @@ only its MC loop (src/updated-FABLE-functions.cpp:599-618) and pair loop (:650-6
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
+
+
+def share_host_threads(local_world, cpu_count=None):
+    """One process per GPU on one host: split the host cores between the ranks' copy pipelines.  The library moves large
+    results into pageable caller memory with up to 16 host threads per context (`FABLE_B200_COPY_THREADS`); N ranks
+    doing so at once would run 16 N threads.  Sets the variable only if the user has not; returns the value in force."""
+    n = cpu_count if cpu_count is not None else (os.cpu_count() or 1)
+    per_rank = max(1, min(16, n // max(1, int(local_world))))
+    return int(os.environ.setdefault("FABLE_B200_COPY_THREADS", str(per_rank)))
 
 
 def draw_range(MC, rank, world):

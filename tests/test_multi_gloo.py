@@ -118,3 +118,15 @@ def test_column_shards_allreduce_and_gather(tmp_path):
         np.testing.assert_array_equal(got[g]["vec"], np.arange(p, dtype=np.float64))
         for key in ("gram", "s"):
             np.testing.assert_array_equal(got[g][key], got[0][key])           # same bits on every rank
+
+
+def test_share_host_threads(monkeypatch):
+    from fable_b200 import parallel
+    monkeypatch.delenv("FABLE_B200_COPY_THREADS", raising=False)
+    assert parallel.share_host_threads(8, cpu_count=16) == 2
+    assert os.environ["FABLE_B200_COPY_THREADS"] == "2"
+    assert parallel.share_host_threads(1, cpu_count=64) == 2          # an explicit / earlier setting is kept
+    monkeypatch.delenv("FABLE_B200_COPY_THREADS")
+    assert parallel.share_host_threads(1, cpu_count=64) == 16
+    monkeypatch.delenv("FABLE_B200_COPY_THREADS")
+    assert parallel.share_host_threads(8, cpu_count=4) == 1
