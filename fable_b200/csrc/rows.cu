@@ -180,8 +180,8 @@ struct RowsMmaCfg {
 // The loop is written for few instructions per item (the first version spent 275 per 2 KB item -- 64-bit index
 // arithmetic and bounds predicates on every copy -- and was bound by the serial latency of that stream with four
 // warps per scheduler, not by memory): per-lane source pointers advance by constants, validity is one flag per
-// tile plus a 32-bit row compare, predicated-off copies keep their pointer and read 0 bytes, the ring depth is a
-// compile-time constant.
+// tile plus a 32-bit row compare, interior items (a warp-uniform test) are copied without any predicate, predicated-off
+// copies of the ragged edges read 0 bytes from a valid address, the ring depth is a compile-time constant.
 template <int KS, int IPW>
 __global__ void __launch_bounds__(MW * 32, 1)
 k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const double* __restrict__ U,
@@ -203,17 +203,36 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
   bool lok = lst < nsuper && lcol < p;
   const double* ytile = Y + ldy * lcol + 2 * t;                    // never dereferenced while !lok
   const int64_t ytile_step = ldy * dcol;
-  const double* cl = c + lcol + ldc * t;
-  const int64_t ldc4 = 4 * ldc;
+  const double* cl = c + lcol;
+  bool lfull = lst < nsuper && lcol - g + 8 <= p;                  // warp-uniform: all 8 columns of the tile exist
   auto issue = [&]() {
     const uint32_t sb = lstage * STB;
     const int r0 = lit * ITEM + 2 * t;
     const double* yp = ytile + lit * ITEM;
+    const bool first = lit == wr;                        // first item of a tile: its c fragments ride along
+    if (lfull && lit * ITEM + ITEM <= n) {               // interior item (warp-uniform): no predicates at all
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) cp16_zfill(ring + sb + nb * 512, yp + nb * 8, (lok && r0 + nb * 8 < n) ? 16 : 0);
-    if (lit == wr) {                                     // first item of a tile: its c fragments ride along
+      for (int nb = 0; nb < 4; ++nb) cp16_zfill(ring + sb + nb * 512, yp + nb * 8, 16);
+      if (first) {
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) cp8_zfill(ring_a + sb + ks * 256, cl + ks * ldc4, (lok && ks * 4 + t < k) ? 8 : 0);
+        for (int ks = 0; ks < KS; ++ks) {
+          const int l = ks * 4 + t;
+          cp8_zfill(ring_a + sb + ks * 256, cl + ldc * (l < k ? l : k - 1), l < k ? 8 : 0);
+        }
+      }
+    } else {                                             // ragged rows / columns / past the last tile: predicated-off
+#pragma unroll                                           // copies read 0 bytes from a valid address
+      for (int nb = 0; nb < 4; ++nb) {
+        const bool ok = lok && r0 + nb * 8 < n;
+        cp16_zfill(ring + sb + nb * 512, ok ? yp + nb * 8 : Y, ok ? 16 : 0);
+      }
+      if (first) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const bool ok = lok && ks * 4 + t < k;
+          cp8_zfill(ring_a + sb + ks * 256, ok ? cl + ldc * (ks * 4 + t) : c, ok ? 8 : 0);
+        }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     lstage = lstage == S - 1 ? 0 : lstage + 1;
@@ -221,6 +240,7 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
     if (lit >= nitems) {
       lit = wr; lst += sstep; lcol += dcol; ytile += ytile_step; cl += dcol;
       lok = lst < nsuper && lcol < p;
+      lfull = lst < nsuper && lcol - g + 8 <= p;
     }
   };
 #pragma unroll
