@@ -369,7 +369,8 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     const int npairs = NB / 2;
     const int inner = getenv("FABLE_B200_BJ_INNER") ? atoi(getenv("FABLE_B200_BJ_INNER")) : 1;
     const int cross = getenv("FABLE_B200_BJ_CROSS") ? atoi(getenv("FABLE_B200_BJ_CROSS")) : 1;
-    int64_t nsplit = ceil_div(2 * static_cast<int64_t>(ctx->sms), npairs);
+    const int64_t splitf = getenv("FABLE_B200_BJ_SPLITF") ? atoll(getenv("FABLE_B200_BJ_SPLITF")) : 8;   // CTAs of the panel Gram per SM: its 16-row k loop is latency-bound (n = 5000: 856 -> 722 ms)
+    int64_t nsplit = ceil_div(splitf * static_cast<int64_t>(ctx->sms), npairs);
     if (nsplit > ld / 64) nsplit = ld / 64 > 0 ? ld / 64 : 1;
     const int64_t rows_per_split = round_up(ceil_div(ld, nsplit), GKT);
     nsplit = ceil_div(ld, rows_per_split);
