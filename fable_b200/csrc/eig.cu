@@ -189,6 +189,7 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, in
   double* H = dsm;
   double* R = dsm + PW * S;
   __shared__ double cs[BW], sn[BW];
+  __shared__ double2 rot2[2][BW];
   __shared__ int pp[BW], qq[BW];
   __shared__ int any_rot, need;
   const int tid = threadIdx.x;
@@ -232,7 +233,109 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, in
     }
   }
   __syncthreads();
-  if (need) {
+  if (need && cross_only) {
+    // Cross pairs, software-pipelined: step s rotates (i, 32 + (i + s) % 32), i = 0 .. 31.  While warps 1-31 apply step s
+    // (H_next = J' H_cur J into the OTHER buffer, R <- R J in place), warp 0 derives the rotations of step s + 1: the three
+    // entries it needs of the not-yet-written H_next are formed from H_cur and the current rotations with the block
+    // formulas of the update itself.  One barrier per step.  The kernel is bound by instruction issue (ncu: 1350 warp
+    // instructions per scheduler and step in the first form), so every thread keeps ONE fixed block (warp w: row pair
+    // w - 1, column pair = lane; warp 31 also row pair 31) and fixed R entries, with addresses advanced by increments.
+    if (tid == 0) atomicAdd(nrot, 1);
+    const int lane = tid & 31, w = tid >> 5;
+    int cur = 0, nxt = 2 * PW * S;                       // offsets of H_cur / H_next in dsm (H at 0, second H behind R)
+    auto rotation = [&](double hpq, double hpp, double hqq, double2& cs_) {
+      cs_ = make_double2(1.0, 0.0);
+      if (hpq != 0.0 && hpq * hpq > tol2 * hpp * hqq) {
+        const double d = hqq - hpp, h2 = 2.0 * hpq, r2 = fma(d, d, h2 * h2);
+        const double tt = h2 * (1.0 / (d + copysign(r2 * rsqrt(r2), d)));
+        const double c_ = rsqrt(fma(tt, tt, 1.0));
+        cs_ = make_double2(c_, c_ * tt);
+      }
+    };
+    auto block = [&](const double* Hc, double* Hn, int p1S, int q1S, int p2, int q2, double2 r1, double2 r2) {
+      const double hpp_ = Hc[p1S + p2], hpq_ = Hc[p1S + q2], hqp_ = Hc[q1S + p2], hqq_ = Hc[q1S + q2];
+      const double ap = r2.x * hpp_ - r2.y * hpq_, bp = r2.y * hpp_ + r2.x * hpq_;
+      const double aq = r2.x * hqp_ - r2.y * hqq_, bq = r2.y * hqp_ + r2.x * hqq_;
+      Hn[p1S + p2] = r1.x * ap - r1.y * aq; Hn[q1S + p2] = r1.y * ap + r1.x * aq;
+      Hn[p1S + q2] = r1.x * bp - r1.y * bq; Hn[q1S + q2] = r1.y * bp + r1.x * bq;
+    };
+    for (int sweep = 0; sweep < inner; ++sweep) {
+      if (tid == 0) any_rot = 0;
+      if (tid < BW) {
+        const double* Hc = dsm + cur;
+        const int q = BW + tid;
+        double2 r0;
+        rotation(Hc[tid * S + q], Hc[tid * S + tid], Hc[q * S + q], r0);
+        rot2[0][tid] = r0;
+        if (r0.y != 0.0) any_rot = 1;
+      }
+      __syncthreads();
+      // rotating column offsets: o = (index + step) % 32
+      int o_lane = lane, o_w = (w - 1) & (BW - 1), o_r0 = (tid - BW) >> 6, o_r1 = ((tid - BW) >> 6) + 16;
+      for (int step = 0; step < BW; ++step) {
+        const double2* rr = rot2[step & 1];
+        const double* Hc = dsm + cur;
+        double* Hn = dsm + nxt;
+        if (w == 0) {
+          if (step + 1 < BW) {
+            const int i = lane, i1 = (i + 1) & (BW - 1), qi = BW + o_lane, qn = BW + ((o_lane + 1) & (BW - 1));
+            const double2 r1 = rr[i], r2 = rr[i1];
+            const double ap = r1.x * Hc[i * S + i] - r1.y * Hc[i * S + qi], aq = r1.x * Hc[qi * S + i] - r1.y * Hc[qi * S + qi];
+            const double hii = r1.x * ap - r1.y * aq;                                             // H'[i][i]
+            const double bp1 = r2.y * Hc[i1 * S + i1] + r2.x * Hc[i1 * S + qn], bq1 = r2.y * Hc[qn * S + i1] + r2.x * Hc[qn * S + qn];
+            const double hqq = r2.y * bp1 + r2.x * bq1;                                           // H'[qn][qn]
+            const double bp = r2.y * Hc[i * S + i1] + r2.x * Hc[i * S + qn], bq = r2.y * Hc[qi * S + i1] + r2.x * Hc[qi * S + qn];
+            const double hpq = r1.x * bp - r1.y * bq;                                             // H'[i][qn]
+            double2 rn;
+            rotation(hpq, hii, hqq, rn);
+            rot2[(step + 1) & 1][i] = rn;
+            if (rn.y != 0.0) any_rot = 1;
+          }
+        } else {
+          const int q2 = BW + o_lane;
+          const double2 r2 = rr[lane];
+          block(Hc, Hn, (w - 1) * S, (BW + o_w) * S, lane, q2, rr[w - 1], r2);
+          if (w == BW - 1) block(Hc, Hn, (BW - 1) * S, (BW + ((o_w + 1) & (BW - 1))) * S, lane, q2, rr[BW - 1], r2);
+          // R <- R J: thread u = tid - 32 owns row i = u % 64 of the pairs u / 64 and u / 64 + 16 (u < 992: pairs 15 and 31
+          // have rows 32 .. 63 left over)
+          const int i = (tid - BW) & (PW - 1);
+          {
+            const int r = (tid - BW) >> 6;
+            const double2 cs_ = rr[r];
+            if (cs_.y != 0.0) {
+              const int q = BW + ((o_r0 + step) & (BW - 1));
+              const double rp = R[i * S + r], rq = R[i * S + q];
+              R[i * S + r] = cs_.x * rp - cs_.y * rq; R[i * S + q] = cs_.y * rp + cs_.x * rq;
+            }
+          }
+          {
+            const int r = ((tid - BW) >> 6) + 16;
+            if (r < BW) {
+              const double2 cs_ = rr[r];
+              if (cs_.y != 0.0) {
+                const int q = BW + ((o_r1 + step) & (BW - 1));
+                const double rp = R[i * S + r], rq = R[i * S + q];
+                R[i * S + r] = cs_.x * rp - cs_.y * rq; R[i * S + q] = cs_.y * rp + cs_.x * rq;
+              }
+            }
+          }
+          if (w <= 2) {                                   // left over: rows 32 .. 63 of pairs 15 (warp 1) and 31 (warp 2)
+            const int i2 = BW + lane, r = w == 1 ? 15 : BW - 1;
+            const double2 cs_ = rr[r];
+            if (cs_.y != 0.0) {
+              const int q = BW + ((r + step) & (BW - 1));
+              const double rp = R[i2 * S + r], rq = R[i2 * S + q];
+              R[i2 * S + r] = cs_.x * rp - cs_.y * rq; R[i2 * S + q] = cs_.y * rp + cs_.x * rq;
+            }
+          }
+        }
+        __syncthreads();
+        const int tswap = cur; cur = nxt; nxt = tswap;
+        o_lane = (o_lane + 1) & (BW - 1); o_w = (o_w + 1) & (BW - 1);
+      }
+      if (!any_rot) break;
+    }
+  } else if (need) {
     if (tid == 0) atomicAdd(nrot, 1);
     for (int sweep = 0; sweep < inner; ++sweep) {
       if (tid == 0) any_rot = 0;
@@ -382,7 +485,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
         dG, m, Wbuf.d(), ld, ncols);
     FB_LAUNCHED(ctx);
     const size_t apply_smem = static_cast<size_t>(PW * ASTR + PW * RSTR) * sizeof(double);
-    const size_t eig_smem = static_cast<size_t>(2 * PW * (PW + 1)) * sizeof(double);
+    const size_t eig_smem = static_cast<size_t>(3 * PW * (PW + 1)) * sizeof(double);       // H, R, second H of the pipelined cross steps
     static bool attr_dev[64] = {};
     bool& attr = attr_dev[ctx->device & 63];
     if (!attr) {
