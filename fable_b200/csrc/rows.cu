@@ -286,7 +286,7 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
         stage = stage == S - 1 ? 0 : stage + 1;
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) { as0 = fma(acc[nb].x, acc[nb].x, as0); as1 = fma(acc[nb].y, acc[nb].y, as1); }
-#ifndef ROWS_LAB_NOMATH
+#ifndef ROWS_LAB_NOMATH               // switch-off lab (-DROWS_LAB_NOMATH): the stream, the ring and the sums without the DMMAs
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
