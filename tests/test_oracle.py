@@ -258,3 +258,95 @@ def test_native_stream_moments_and_batch_invariance():
     np.testing.assert_array_equal(g2, gam[1000:1050]); np.testing.assert_array_equal(z2, z[1000:1050])
     g3, _ = c_oracle.rng_fill(43, 0, 10, p, k, shape, want_z=False)
     assert not np.array_equal(g3, gam[:10])
+
+
+# ---- schedule of the block-Jacobi eigensolver (fable_b200/csrc/eig.cu): a restatement of its index maps ----------
+def _bj_pair(i, rnd, NB):
+    """bj_pair of eig.cu: block pair number i of round rnd (round-robin over an even number NB of blocks)."""
+    if i == 0:
+        ca, cb = NB - 1, rnd
+    else:
+        ca, cb = (rnd + i) % (NB - 1), (rnd - i + (NB - 1)) % (NB - 1)
+    return (ca, cb) if ca < cb else (cb, ca)
+
+
+def _inner_pairs(step, cross_only, BW=32):
+    """column pairs (within the 64-column panel of a block pair) rotated in parallel at one step of k_bj_eig"""
+    PW = 2 * BW
+    out = []
+    for t in range(BW):
+        if cross_only:
+            a, b = t, BW + ((t + step) % BW)
+        elif t == 0:
+            a, b = PW - 1, step
+        else:
+            a, b = (step + t) % (PW - 1), (step - t + (PW - 1)) % (PW - 1)
+        out.append((min(a, b), max(a, b)))
+    return out
+
+
+@pytest.mark.parametrize("NB", [2, 4, 8, 32])
+def test_block_jacobi_sweep_visits_every_column_pair(NB):
+    """One outer sweep = rounds 0 .. NB-2; round 0 runs the full 63-step ordering inside every block pair, the other
+    rounds only the 32 x 32 cross pairs.  Claim checked here: every pair of the 32 NB columns is
+    rotated at least once per sweep, pairs inside a block exactly once, and the rotations of one step are disjoint."""
+    BW = 32
+    seen = {}
+    for rnd in range(NB - 1):
+        blocks = [_bj_pair(i, rnd, NB) for i in range(NB // 2)]
+        assert sorted(b for pr in blocks for b in pr) == list(range(NB))            # every block in exactly one pair
+        cross_only = rnd > 0
+        for bi, bj in blocks:
+            col = lambda a: (bi if a < BW else bj) * BW + (a % BW)
+            for step in range(BW if cross_only else 2 * BW - 1):
+                pairs = _inner_pairs(step, cross_only)
+                cols = [c for pr in pairs for c in pr]
+                assert len(set(cols)) == 2 * BW                                     # disjoint rotations within a step
+                for a, b in pairs:
+                    key = tuple(sorted((col(a), col(b))))
+                    seen[key] = seen.get(key, 0) + 1
+    m = NB * BW
+    assert len(seen) == m * (m - 1) // 2                                            # every column pair visited
+    for (a, b), cnt in seen.items():
+        assert cnt == 1, (a, b, cnt)                                                # ... exactly once: a cyclic sweep
+
+
+# ---- work split of the tensor-core row pass (fable_b200/csrc/rows.cu, k_rowstats_mma): restated index maps -------
+@pytest.mark.parametrize("n,p,grid", [(1000, 20000, 148), (500, 1000, 148), (200, 777, 148), (66, 9, 148), (2, 5, 148),
+                                      (2000, 300, 148), (3000, 100, 7), (1000, 2003, 3)])
+def test_row_pass_work_split_covers_every_item_once(n, p, grid):
+    """16 warps per CTA; G = min(16, items) warps share a tile (8 columns), 16 // G tiles at a time; warp r of a group
+    owns items r, r + G, ...; CTA b takes tile groups b, b + grid, ...  Every (tile, item) with tile < ceil(p / 8) must be
+    worked on exactly once, and the load cursor must produce the same sequence as the work cursor (the cp.async ring
+    is consumed in issue order)."""
+    MW, ITEM = 16, 32
+    nitems = -(-n // ITEM)
+    G = min(nitems, MW)
+    TC = MW // G
+    ntiles = -(-p // 8)
+    nsuper = -(-ntiles // TC)
+    grid = min(grid, nsuper)
+    IPW = -(-nitems // MW)
+    seen = {}
+    for b in range(grid):
+        for w in range(MW):
+            ts, wr = divmod(w, G)
+            if ts >= TC:
+                continue
+            work = []
+            for st in range(b, nsuper, grid):                       # work cursor: tiles, then the warp's items
+                for q in range(IPW):
+                    if q == 0 or wr + q * G < nitems:
+                        work.append((st * TC + ts, wr + q * G))
+            lst, lit, load = b, wr, []                              # load cursor of issue()
+            while len(load) < len(work):
+                load.append((lst * TC + ts, lit))
+                lit += G
+                if lit >= nitems:
+                    lit, lst = wr, lst + grid
+            assert load == work
+            for tile, it in work:
+                assert it < nitems
+                if tile < ntiles:
+                    seen[(tile, it)] = seen.get((tile, it), 0) + 1
+    assert len(seen) == ntiles * nitems and set(seen.values()) == {1}
