@@ -355,6 +355,9 @@ int download(fable_ctx* ctx, double* h, const double* dptr, size_t count) {
   char* dst = reinterpret_cast<char*>(h);
   hint_huge_pages(dst, bytes);
   const size_t nchunks = (bytes + kStageBytes - 1) / kStageBytes;
+  // the staging buffers are shared with the uploads, which may have run on the context's other stream: whatever last
+  // used them must have finished before a transfer of this stream writes into them
+  for (int s = 0; s < 2; ++s) FB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[s]));
   auto issue = [&](size_t i) -> cudaError_t {
     const size_t off = i * kStageBytes, len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
     cudaError_t e = cudaMemcpyAsync(ctx->stage[i & 1], src + off, len, cudaMemcpyDeviceToHost, ctx->stream);
