@@ -488,14 +488,29 @@ class Posterior:
         """f3 (R/FABLE_code.R:212-298): materialised draws become G + B o (Lambda Lambda' - G) + diag(sigma2)."""
         self.ctx.check(_load().fable_posterior_set_entrywise_correction(self._h, C.c_int(1 if on else 0)))
 
+    def draw_batch_tiles(self, m0, B, dev_psi_tiles=0, psi_slots=0, accumulate=True, dev_gam=0, dev_z=0):
+        """draw_batch with the draws materialised compactly for the posterior's tile slice (partition B): per slot
+        2 * tile_count(p, *slice) * 4096 doubles, tile c as the pair (block (I, J), mirrored block (J, I))."""
+        self.ctx.check(_load().fable_posterior_draw_batch_tiles(self._h, _i64(m0), C.c_int(B), C.c_void_p(dev_psi_tiles or None),
+                                                                C.c_int(psi_slots), C.c_int(1 if accumulate else 0),
+                                                                C.c_void_p(dev_gam or None), C.c_void_p(dev_z or None)))
+
     def tile_slots(self):
         n = C.c_int64()
         self.ctx.check(_load().fable_posterior_tile_slots(self._h, C.byref(n)))
         return n.value
 
     def set_tile_range(self, t_begin, t_end):
-        """Partition B: restrict draw_batch to a slice of the tile enumeration (0, 0 = everything)."""
+        """Partition B: restrict draw_batch to a slice of the tile enumeration (0, 0 = everything); the accumulators
+        of the previous slice are dropped."""
         self.ctx.check(_load().fable_posterior_set_tile_range(self._h, _i64(t_begin), _i64(t_end)))
+        self._slice = (int(t_begin), int(t_end))
+
+    def tiles_to_dense(self, dev_tiles, paired, col0, ncols, dev_out):
+        """compact tiles of the slice (device address) -> columns [col0, col0 + ncols) of the dense p x p matrix
+        (device address, p x ncols, ld p); zeros outside the slice."""
+        self.ctx.check(_load().fable_posterior_tiles_to_dense(self._h, C.c_void_p(dev_tiles), C.c_int(1 if paired else 0),
+                                                              _i64(col0), _i64(ncols), C.c_void_p(dev_out)))
 
     def samples(self, m0, MC, gam=None, z=None, want_lambda=True, want_sigma=True):
         L = np.empty((MC, self.k * self.p), order="F") if want_lambda else None
@@ -506,30 +521,73 @@ class Posterior:
                                                        _ptr(g), _ptr(zz)))
         return L, S
 
+    def sample_range(self, m0, MC, out_lambda=None, out_sigma=None, gam=None, z=None, psi_pass=True):
+        """fable_posterior_sample_range: draws m0 .. m0+MC-1 -- reference-layout samples into the given column-major
+        host arrays (MC x k p, MC x p; None to skip), the covariance pass into the device-resident accumulators."""
+        g = None if gam is None else np.ascontiguousarray(gam, dtype=np.float64)
+        zz = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        for a, cols in ((out_lambda, self.k * self.p), (out_sigma, self.p)):
+            if a is not None and (a.shape != (MC, cols) or not a.flags.f_contiguous or a.dtype != np.float64):
+                raise FableError(1, "sample_range: outputs must be column-major float64 arrays of MC rows")
+        self.ctx.check(_load().fable_posterior_sample_range(self._h, _i64(MC), _i64(m0), _i64(MC), _ptr(g), _ptr(zz),
+                                                            _ptr(out_lambda), _ptr(out_sigma), C.c_int(1 if psi_pass else 0)))
+
     def accum_dev(self):
-        a = C.c_void_p(); b = C.c_void_p()
-        self.ctx.check(_load().fable_posterior_accum_dev(self._h, C.byref(a), C.byref(b)))
-        return int(a.value), int(b.value)
-
-    def accum_pack(self):
-        """(dev_sum, dev_sumsq, count): packed upper triangles for the multi-GPU reduction."""
+        """(dev_sum, dev_sumsq, count): the compact upper tiles of the slice, `count` doubles each -- what the NCCL sum
+        of the draw partition reduces, as it is."""
         a = C.c_void_p(); b = C.c_void_p(); n = C.c_int64()
-        self.ctx.check(_load().fable_posterior_accum_pack(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        self.ctx.check(_load().fable_posterior_accum_dev(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return int(a.value), int(b.value), n.value
-
-    def accum_unpack(self):
-        self.ctx.check(_load().fable_posterior_accum_unpack(self._h))
 
     def accum_reset(self):
         self.ctx.check(_load().fable_posterior_accum_reset(self._h))
 
-    def accum_mirror(self):
-        self.ctx.check(_load().fable_posterior_accum_mirror(self._h))
-
-    def accum_fetch(self):
-        s1 = np.empty((self.p, self.p), order="F"); s2 = np.empty((self.p, self.p), order="F")
+    def accum_fetch(self, out=None):
+        """Dense symmetric p x p sum / sumsq on the host (zeros outside the posterior's tile slice)."""
+        s1, s2 = out if out is not None else (np.empty((self.p, self.p), order="F"), np.empty((self.p, self.p), order="F"))
         self.ctx.check(_load().fable_posterior_accum_fetch(self._h, _ptr(s1), _ptr(s2)))
         return s1, s2
+
+    def accum_fetch_tiles(self):
+        """The compact tiles as stored: two arrays (tiles, 64, 64), element [c, v, u] = entry (u, v) of tile c."""
+        _, _, n = self.accum_dev()
+        s1 = np.empty(n); s2 = np.empty(n)
+        self.ctx.check(_load().fable_posterior_accum_fetch_tiles(self._h, _ptr(s1), _ptr(s2)))
+        return s1.reshape(-1, 64, 64), s2.reshape(-1, 64, 64)
+
+
+# ------------------------------------------------------------------------------------------------
+# tile layout of the covariance pass (host-only helpers of the C-ABI; no GPU needed)
+# ------------------------------------------------------------------------------------------------
+def tile_slots(p):
+    n = C.c_int64()
+    if _load().fable_tile_slots(_i64(p), C.byref(n)) != 0:
+        raise FableError(1, "tile_slots: p must be >= 1")
+    return n.value
+
+
+def tile_count(p, t_begin=0, t_end=0):
+    """Valid (stored) tiles in the slice [t_begin, t_end) of the enumeration (0, 0 = everything)."""
+    n = C.c_int64()
+    if _load().fable_tile_count(_i64(p), _i64(t_begin), _i64(t_end), C.byref(n)) != 0:
+        raise FableError(1, "tile_count: slice out of bounds")
+    return n.value
+
+
+def tile_partition(p, rank, world):
+    """[t_begin, t_end) of rank `rank`: slices with equal shares of the valid tiles."""
+    a = C.c_int64(); b = C.c_int64()
+    if _load().fable_tile_partition(_i64(p), C.c_int(rank), C.c_int(world), C.byref(a), C.byref(b)) != 0:
+        raise FableError(1, "tile_partition: need p >= 1 and 0 <= rank < world")
+    return a.value, b.value
+
+
+def tile_locate(p, I, J):
+    """(slot, compact index) of tile (I, J), I <= J."""
+    a = C.c_int64(); b = C.c_int64()
+    if _load().fable_tile_locate(_i64(p), _i64(I), _i64(J), C.byref(a), C.byref(b)) != 0:
+        raise FableError(1, "tile_locate: need 0 <= I <= J < ceil(p / 64)")
+    return a.value, b.value
 
 
 # ------------------------------------------------------------------------------------------------

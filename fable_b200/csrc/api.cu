@@ -13,6 +13,7 @@
 #include <sys/mman.h>
 
 #include "common.cuh"
+#include "tiles.cuh"
 
 // ---- device block cache (see common.cuh) ----------------------------------------------------------
 #include <mutex>
@@ -432,12 +433,16 @@ struct fable_posterior {
   RowPosterior rp;
   DevBuf Lw, s2w;
   int Bcap = 0;
-  DevBuf acc_sum, acc_sq;
-  DevBuf pack_sum, pack_sq;     // packed upper triangles for the multi-GPU reduction
+  DevBuf acc_sum, acc_sq;       // compact upper tiles of the slice [tile_begin, tile_end) (tiles.cuh): acc_tiles x 4096 doubles
+  int64_t acc_tiles = 0;
   DevBuf cc_gdiag;              // entry-wise coverage correction (f3): diag(G0 G0'); NULL = off
   bool cc = false;
-  bool mirrored = false;
-  int64_t tile_begin = 0, tile_end = 0;
+  int64_t tile_begin = 0, tile_end = 0;   // tile_end == 0: every tile
+  int64_t slice_tiles() const {
+    const int nT = static_cast<int>(fbt::n_tiles(p));
+    const int64_t hi = tile_end > 0 ? tile_end : fbt::n_slots(p);
+    return fbt::cidx(hi, nT) - fbt::cidx(tile_begin, nT);
+  }
 };
 
 // row posterior (shrunk G0, cpp:564-597) from inputs already resident in HBM
@@ -924,20 +929,23 @@ static SampleArgs sample_args(const fable_posterior* post, const double* dgam, c
   return a;
 }
 
+// The sum / sumsq accumulators hold the upper 64 x 64 tiles of the posterior's tile slice only, tile-major and compact
+// (tiles.cuh): p(p+1)/2-ish doubles instead of p^2, a rank of the tile partition holds just its share, and a slice of
+// the enumeration is one contiguous range (the payload of the draw partition's NCCL sum needs no packing).
 static int ensure_accum(fable_posterior* post) {
   fable_ctx* ctx = post->ctx;
   if (post->acc_sum.ptr) return FABLE_OK;
-  const size_t bytes = static_cast<size_t>(post->p) * post->p * sizeof(double);
+  post->acc_tiles = post->slice_tiles();
+  const size_t bytes = static_cast<size_t>(post->acc_tiles) * fbt::TILE_DOUBLES * sizeof(double);
   FB_CUDA(ctx, post->acc_sum.alloc(bytes));
   FB_CUDA(ctx, post->acc_sq.alloc(bytes));
   FB_CUDA(ctx, cudaMemsetAsync(post->acc_sum.ptr, 0, bytes, ctx->stream));
   FB_CUDA(ctx, cudaMemsetAsync(post->acc_sq.ptr, 0, bytes, ctx->stream));
-  post->mirrored = false;
   return FABLE_OK;
 }
 
-int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots,
-                               int accumulate, const double* dev_gam, const double* dev_z) {
+static int draw_batch_impl(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots, bool compact,
+                           int accumulate, const double* dev_gam, const double* dev_z) {
   if (!post) return FABLE_ERR_INVALID;
   fable_ctx* ctx = post->ctx;
   FB_REQUIRE(ctx, B >= 1 && m0 >= 0, "draw_batch: need B >= 1 and m0 >= 0");
@@ -953,7 +961,7 @@ int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double*
     FB_CUDA(ctx, post->s2w.alloc(static_cast<size_t>(B) * post->pp * sizeof(double)));
     post->Bcap = B;
   }
-  if (accumulate) { FB_TRY(ensure_accum(post)); post->mirrored = false; }
+  if (accumulate) FB_TRY(ensure_accum(post));
   double* draws = post->Lw.d() + static_cast<size_t>(post->KP) * post->pp;      // slots 1..B
   FB_TRY(fb_sample_work(ctx, sample_args(post, dev_gam, dev_z, m0), m0, B, post->pp, post->KP, draws, post->s2w.d()));
   PsiArgs a;
@@ -963,10 +971,20 @@ int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double*
     a.cc_gdiag = post->cc_gdiag.d(); a.cc_sig = post->rp.sig.d();
   }
   a.Lw = post->cc ? post->Lw.d() : draws; a.s2w = post->s2w.d(); a.pp = post->pp; a.p = post->p; a.k = post->k; a.KP = post->KP;
-  a.B = B; a.psi = dev_psi; a.psi_slots = psi_slots; a.slot0 = 0;
+  a.B = B; a.psi = dev_psi; a.psi_slots = psi_slots; a.slot0 = 0; a.out_compact = compact;
   a.acc_sum = accumulate ? post->acc_sum.d() : nullptr; a.acc_sq = accumulate ? post->acc_sq.d() : nullptr;
   a.tile_begin = post->tile_begin; a.tile_end = post->tile_end;
   return fb_psi(ctx, a);
+}
+
+int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots,
+                               int accumulate, const double* dev_gam, const double* dev_z) {
+  return draw_batch_impl(post, m0, B, dev_psi, psi_slots, false, accumulate, dev_gam, dev_z);
+}
+
+int fable_posterior_draw_batch_tiles(fable_posterior* post, int64_t m0, int B, double* dev_psi_tiles, int psi_slots,
+                                     int accumulate, const double* dev_gam, const double* dev_z) {
+  return draw_batch_impl(post, m0, B, dev_psi_tiles, psi_slots, true, accumulate, dev_gam, dev_z);
 }
 
 int fable_posterior_set_entrywise_correction(fable_posterior* post, int on) {
@@ -983,16 +1001,77 @@ int fable_posterior_set_entrywise_correction(fable_posterior* post, int on) {
 
 int fable_posterior_tile_slots(fable_posterior* post, int64_t* slots) {
   if (!post || !slots) return FABLE_ERR_INVALID;
-  *slots = fb_psi_tile_slots(post->p);
+  *slots = fbt::n_slots(post->p);
+  return FABLE_OK;
+}
+
+int fable_tile_slots(int64_t p, int64_t* slots) {
+  if (!slots || p < 1) return FABLE_ERR_INVALID;
+  *slots = fbt::n_slots(p);
+  return FABLE_OK;
+}
+
+int fable_tile_count(int64_t p, int64_t t_begin, int64_t t_end, int64_t* tiles) {
+  if (!tiles || p < 1) return FABLE_ERR_INVALID;
+  const int64_t total = fbt::n_slots(p);
+  if (t_end == 0 && t_begin == 0) t_end = total;
+  if (t_begin < 0 || t_begin > t_end || t_end > total) return FABLE_ERR_INVALID;
+  const int nT = static_cast<int>(fbt::n_tiles(p));
+  *tiles = fbt::cidx(t_end, nT) - fbt::cidx(t_begin, nT);
+  return FABLE_OK;
+}
+
+// slice g of `world` slices of the enumeration with (almost) equal numbers of VALID tiles: boundary g is the first slot
+// t with cidx(t) >= g * valid / world
+int fable_tile_partition(int64_t p, int rank, int world, int64_t* t_begin, int64_t* t_end) {
+  if (!t_begin || !t_end || p < 1 || world < 1 || rank < 0 || rank >= world) return FABLE_ERR_INVALID;
+  const int nT = static_cast<int>(fbt::n_tiles(p));
+  const int64_t total = fbt::n_slots(p), valid = fbt::n_valid(p);
+  auto boundary = [&](int g) -> int64_t {
+    if (g <= 0) return 0;
+    if (g >= world) return total;
+    const int64_t want = valid / world * g + (valid % world) * g / world;
+    int64_t lo = 0, hi = total;                        // smallest t with cidx(t) >= want
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if (fbt::cidx(mid, nT) >= want) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  *t_begin = boundary(rank); *t_end = boundary(rank + 1);
+  return FABLE_OK;
+}
+
+int fable_tile_locate(int64_t p, int64_t I, int64_t J, int64_t* slot, int64_t* compact_index) {
+  const int64_t nT = p >= 1 ? fbt::n_tiles(p) : 0;
+  if (I < 0 || I > J || J >= nT) return FABLE_ERR_INVALID;
+  const int64_t t = fbt::slot_of(static_cast<int>(I), static_cast<int>(J));
+  if (slot) *slot = t;
+  if (compact_index) *compact_index = fbt::cidx(t, static_cast<int>(nT));
   return FABLE_OK;
 }
 
 int fable_posterior_set_tile_range(fable_posterior* post, int64_t t_begin, int64_t t_end) {
   if (!post) return FABLE_ERR_INVALID;
   fable_ctx* ctx = post->ctx;
-  FB_REQUIRE(ctx, t_begin >= 0 && t_begin <= t_end && t_end <= fb_psi_tile_slots(post->p), "tile range out of bounds");
+  FB_REQUIRE(ctx, t_begin >= 0 && t_begin <= t_end && t_end <= fbt::n_slots(post->p), "tile range out of bounds");
+  if (t_begin == post->tile_begin && t_end == post->tile_end) return FABLE_OK;
+  if (post->acc_sum.ptr) {              // the accumulators cover one slice: a new slice starts from zero
+    FB_CUDA(ctx, cudaSetDevice(ctx->device));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    post->acc_sum.release(); post->acc_sq.release(); post->acc_tiles = 0;
+  }
   post->tile_begin = t_begin; post->tile_end = t_end;
   return FABLE_OK;
+}
+
+int fable_posterior_tiles_to_dense(fable_posterior* post, const double* dev_tiles, int paired, int64_t col0, int64_t ncols,
+                                   double* dev_out) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, dev_tiles && dev_out, "tiles_to_dense: NULL pointer");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return fb_tiles_to_dense(ctx, dev_tiles, post->p, post->tile_begin, post->tile_end, paired, col0, ncols, dev_out);
 }
 
 int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64_t ldm, double* LambdaSamples,
@@ -1039,12 +1118,13 @@ int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64
   return FABLE_OK;
 }
 
-int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** dev_sumsq) {
+int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** dev_sumsq, int64_t* count) {
   if (!post) return FABLE_ERR_INVALID;
   FB_CUDA(post->ctx, cudaSetDevice(post->ctx->device));
   FB_TRY(ensure_accum(post));
   if (dev_sum) *dev_sum = post->acc_sum.d();
   if (dev_sumsq) *dev_sumsq = post->acc_sq.d();
+  if (count) *count = post->acc_tiles * fbt::TILE_DOUBLES;
   return FABLE_OK;
 }
 
@@ -1053,62 +1133,53 @@ int fable_posterior_accum_reset(fable_posterior* post) {
   fable_ctx* ctx = post->ctx;
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!post->acc_sum.ptr) return ensure_accum(post);
-  const size_t bytes = static_cast<size_t>(post->p) * post->p * sizeof(double);
+  const size_t bytes = static_cast<size_t>(post->acc_tiles) * fbt::TILE_DOUBLES * sizeof(double);
   FB_CUDA(ctx, cudaMemsetAsync(post->acc_sum.ptr, 0, bytes, ctx->stream));
   FB_CUDA(ctx, cudaMemsetAsync(post->acc_sq.ptr, 0, bytes, ctx->stream));
-  post->mirrored = false;
   return FABLE_OK;
 }
 
-int fable_posterior_accum_mirror(fable_posterior* post) {
-  if (!post) return FABLE_ERR_INVALID;
-  fable_ctx* ctx = post->ctx;
-  FB_CUDA(ctx, cudaSetDevice(ctx->device));
-  FB_TRY(ensure_accum(post));
-  FB_TRY(fb_mirror_upper(ctx, post->acc_sum.d(), post->p));
-  FB_TRY(fb_mirror_upper(ctx, post->acc_sq.d(), post->p));
-  post->mirrored = true;
-  return FABLE_OK;
-}
-
-// Multi-GPU partition A: only the upper triangle of the accumulators carries information, so the one
-// collective of the path moves p(p+1)/2 doubles per accumulator instead of p^2.
-int fable_posterior_accum_pack(fable_posterior* post, double** dev_sum, double** dev_sumsq, int64_t* count) {
-  if (!post) return FABLE_ERR_INVALID;
-  fable_ctx* ctx = post->ctx;
-  FB_CUDA(ctx, cudaSetDevice(ctx->device));
-  FB_TRY(ensure_accum(post));
-  const int64_t p = post->p, cnt = p * (p + 1) / 2;
-  if (!post->pack_sum.ptr) {
-    FB_CUDA(ctx, post->pack_sum.alloc(static_cast<size_t>(cnt) * sizeof(double)));
-    FB_CUDA(ctx, post->pack_sq.alloc(static_cast<size_t>(cnt) * sizeof(double)));
-  }
-  FB_TRY(fb_pack_upper(ctx, post->acc_sum.d(), p, post->pack_sum.d(), 0));
-  FB_TRY(fb_pack_upper(ctx, post->acc_sq.d(), p, post->pack_sq.d(), 0));
-  if (dev_sum) *dev_sum = post->pack_sum.d();
-  if (dev_sumsq) *dev_sumsq = post->pack_sq.d();
-  if (count) *count = cnt;
-  return FABLE_OK;
-}
-
-int fable_posterior_accum_unpack(fable_posterior* post) {
-  if (!post) return FABLE_ERR_INVALID;
-  fable_ctx* ctx = post->ctx;
-  FB_REQUIRE(ctx, post->pack_sum.ptr && post->acc_sum.ptr, "accum_unpack: nothing was packed");
-  FB_CUDA(ctx, cudaSetDevice(ctx->device));
-  FB_TRY(fb_pack_upper(ctx, post->acc_sum.d(), post->p, post->pack_sum.d(), 1));
-  FB_TRY(fb_pack_upper(ctx, post->acc_sq.d(), post->p, post->pack_sq.d(), 1));
-  post->mirrored = false;
-  return FABLE_OK;
-}
-
+// Dense symmetric p x p copies of the accumulators in caller (host) memory: the compact upper tiles are expanded on
+// the device into column panels (both triangles; blocks outside the posterior's tile slice are zeros, so the results
+// of the ranks of a tile partition add up) and each panel -- a contiguous run of columns of the dense matrix -- goes
+// out as one copy.  No dense p x p buffer exists on the device.
 int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sumsq) {
   if (!post) return FABLE_ERR_INVALID;
   fable_ctx* ctx = post->ctx;
-  if (!post->mirrored) FB_TRY(fable_posterior_accum_mirror(post));
-  const size_t cnt = static_cast<size_t>(post->p) * post->p;
-  FB_TRY(download(ctx, sum, post->acc_sum.d(), cnt));
-  FB_TRY(download(ctx, sumsq, post->acc_sq.d(), cnt));
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_TRY(ensure_accum(post));
+  const int64_t p = post->p;
+  int64_t W = (int64_t(256) << 20) / (8 * p) / fbt::TILE * fbt::TILE;      // ~256 MB panels
+  if (W < fbt::TILE) W = fbt::TILE;
+  if (W > post->pp) W = post->pp;
+  DevBuf panel[2];
+  for (auto& b : panel) FB_CUDA(ctx, b.alloc(static_cast<size_t>(p) * W * sizeof(double)));
+  int turn = 0;
+  for (int which = 0; which < 2; ++which) {
+    double* h = which ? sumsq : sum;
+    if (!h) continue;
+    const double* tiles = which ? post->acc_sq.d() : post->acc_sum.d();
+    for (int64_t c0 = 0; c0 < p; c0 += W, turn ^= 1) {
+      const int64_t nc = p - c0 < W ? p - c0 : W;
+      // (two panels: a pageable destination makes download() return while its last chunk is still being copied out
+      // of the pinned staging, never while the device buffer is still being read)
+      FB_TRY(fb_tiles_to_dense(ctx, tiles, p, post->tile_begin, post->tile_end, 0, c0, nc, panel[turn].d()));
+      FB_TRY(download(ctx, h + c0 * p, panel[turn].d(), static_cast<size_t>(p) * nc));
+    }
+  }
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+// the compact tiles as they are (acc_tiles x 4096 doubles each): the raw share of a rank of the tile partition
+int fable_posterior_accum_fetch_tiles(fable_posterior* post, double* sum_tiles, double* sumsq_tiles) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_TRY(ensure_accum(post));
+  const size_t cnt = static_cast<size_t>(post->acc_tiles) * fbt::TILE_DOUBLES;
+  FB_TRY(download(ctx, sum_tiles, post->acc_sum.d(), cnt));
+  FB_TRY(download(ctx, sumsq_tiles, post->acc_sq.d(), cnt));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FABLE_OK;
 }
@@ -1133,27 +1204,26 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
 
 }  // extern "C"
 
-// everything CPPFABLESampler returns (cpp:599-627) from a resident row posterior
-static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_inj, const double* z_inj, int64_t m0,
-                           double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
-                           double* tausq, double* G, double* psi_sum, double* psi_sumsq) {
+// The draw loop of CPPFABLESampler (cpp:599-618) for draws m0 .. m0 + MC - 1 from a resident row posterior: the
+// reference-layout samples go to the host (rows 0 .. MC-1 of arrays with leading dimension ldm), and with psi_pass the
+// covariance pass adds the same draws into the posterior's device-resident sum / sumsq accumulators (and materialises
+// them into the context's ring when one is set) -- nothing p x p crosses PCIe here, so the ranks of a draw partition can
+// sum their accumulators on the device before anyone fetches them.
+static int sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t ldm, const double* gam_inj, const double* z_inj,
+                        double* LambdaSamples, double* SigmaSqSamples, bool psi_pass) {
   fable_ctx* ctx = post->ctx;
   const int64_t p = post->p;
   const int kEst = post->k;
-  FB_TRY(download(ctx, SigmaPostMean, post->rp.sigmahat.d(), p));              // cpp:622
-  FB_TRY(download(ctx, SigmaPlugIn, post->rp.sig.d(), p));                     // cpp:623
-  if (tausq) *tausq = post->rp.tausq;                                          // cpp:626
-  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // The Psi pass (draw loop on the main stream) is enqueued first; the reference-layout samples are
   // then generated and copied out on the copy stream, so their D2H traffic (8 p (k+1) bytes per draw)
   // overlaps the covariance kernels.  Both read the same immutable row posterior.
   DevBuf dgam, dz;
-  if (psi_sum) {
+  if (psi_pass) {
     if (gam_inj) {
       FB_TRY(upload(ctx, dgam, gam_inj, static_cast<size_t>(MC) * p));
       FB_TRY(upload(ctx, dz, z_inj, static_cast<size_t>(MC) * p * kEst));
     }
-    FB_TRY(fable_posterior_accum_reset(post));
+    FB_TRY(ensure_accum(post));
     if (ctx->ring_slots > 0) {
       const size_t need = static_cast<size_t>(ctx->ring_slots) * p * p * sizeof(double);
       if (need != ctx->ring_bytes) {
@@ -1186,12 +1256,39 @@ static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_
       explicit StreamSwap(fable_ctx* cx) : c(cx), main(cx->stream) { c->stream = c->copy_stream; }
       ~StreamSwap() { c->stream = main; }
     } swap(ctx);
-    const int rc = fable_posterior_samples(post, m0, MC, MC, LambdaSamples, SigmaSqSamples, gam_inj, z_inj);
+    const int rc = fable_posterior_samples(post, m0, MC, ldm, LambdaSamples, SigmaSqSamples, gam_inj, z_inj);
     if (rc != FABLE_OK) { cudaStreamSynchronize(swap.main); return rc; }
   }
-  if (psi_sum) FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
-  if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), p, nullptr, p, kEst, G));   // cpp:627
+  if (psi_pass) FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // dgam / dz go out of scope
   return FABLE_OK;
+}
+
+// everything CPPFABLESampler returns (cpp:599-627) from a resident row posterior
+static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_inj, const double* z_inj, int64_t m0,
+                           double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
+                           double* tausq, double* G, double* psi_sum, double* psi_sumsq) {
+  fable_ctx* ctx = post->ctx;
+  const int64_t p = post->p;
+  FB_TRY(download(ctx, SigmaPostMean, post->rp.sigmahat.d(), p));              // cpp:622
+  FB_TRY(download(ctx, SigmaPlugIn, post->rp.sig.d(), p));                     // cpp:623
+  if (tausq) *tausq = post->rp.tausq;                                          // cpp:626
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (psi_sum) FB_TRY(fable_posterior_accum_reset(post));
+  FB_TRY(sample_range(post, MC, m0, MC, gam_inj, z_inj, LambdaSamples, SigmaSqSamples, psi_sum != nullptr));
+  if (psi_sum) FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
+  if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), p, nullptr, p, post->k, G));   // cpp:627
+  return FABLE_OK;
+}
+
+extern "C" int fable_posterior_sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t ldm, const double* gam_inj,
+                                            const double* z_inj, double* LambdaSamples, double* SigmaSqSamples, int psi_pass) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, MC >= 1 && m0 >= 0, "sample_range: need MC >= 1 and m0 >= 0");
+  FB_REQUIRE(ctx, (gam_inj == nullptr) == (z_inj == nullptr), "injected draws need both gam and z");
+  FB_REQUIRE(ctx, (!LambdaSamples && !SigmaSqSamples) || ldm >= MC, "sample_range: ldm must be >= MC");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return sample_range(post, MC, m0, ldm < MC ? MC : ldm, gam_inj, z_inj, LambdaSamples, SigmaSqSamples, psi_pass != 0);
 }
 
 // ---- a11: the two R wrappers as single calls (Y crosses PCIe once, nothing round-trips) -------------

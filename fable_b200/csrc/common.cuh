@@ -163,20 +163,25 @@ struct PsiArgs {
   int64_t p;
   int k, KP;           // rank and its zero-padded size (multiple of 4)
   int B;               // draws in this batch
-  double* psi;         // materialised output, slot stride p*p (NULL: none)
+  double* psi;         // materialised output (NULL: none): dense p x p per slot, or (out_compact) the tiles of the slice
   int psi_slots;
   int slot0;           // draw b goes to slot slot0 + b (< psi_slots)
-  double* acc_sum;     // p x p accumulators (NULL: none); upper tiles only
+  bool out_compact = false;   // psi holds, per slot, the slice's tiles compactly: direct tile c at 2c, mirrored at 2c + 1
+  double* acc_sum;     // accumulators (NULL: none): COMPACT upper tiles of the slice (tiles.cuh), 4096 doubles per tile
   double* acc_sq;
   const double* cc_gdiag = nullptr;   // entry-wise coverage correction (f3): diag(G) and sig_hat (length p);
   const double* cc_sig = nullptr;     // Lw then carries G0 in slot 0 ahead of the B draws
   int64_t tile_begin = 0, tile_end = 0;   // slice of the tile enumeration (tile_end == 0: all tiles)
-  int tma_mode = 0;    // set by fb_psi: 1 = 4-D whole-tile TMA boxes, 2 = 3-D sub-boxes, 0 = plain stores
+  int tma_mode = 0;    // set by fb_psi (materialised output): 1 = 4-D whole-tile TMA boxes, 2 = 3-D sub-boxes, 0 = plain stores
+  int nT = 0;          // set by fb_psi: tiles per side
+  int64_t cbase = 0;   // set by fb_psi: compact index of the slice's first tile
 };
 int fb_psi(fable_ctx* ctx, const PsiArgs& a);
-int64_t fb_psi_tile_slots(int64_t p);   // length of the (super-block padded) tile enumeration
-int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p);
-int fb_pack_upper(fable_ctx* ctx, double* dA, int64_t p, double* d_packed, int unpack);
+// compact tiles of the slice [t_lo, t_hi) (t_hi == 0: all) -> columns [col0, col0 + ncols) of the dense symmetric p x p
+// matrix (d_out: p x ncols, ld p; col0 a multiple of 64); blocks outside the slice become zeros.  paired: the buffer
+// holds (direct, mirrored) tile pairs (materialised draws) instead of upper tiles only (accumulators).
+int fb_tiles_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t p, int64_t t_lo, int64_t t_hi, int paired, int64_t col0,
+                      int64_t ncols, double* d_out);
 // dst (k rows of pp, zero-padded) <- src (k rows of lds, p valid)
 int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, int KP, double* dst);
 // post.cu: Lsel [S][k][MC], Ssel [S][MC], idx [S] (0-based selected variables); outputs S x S column-major

@@ -421,6 +421,31 @@ int workspace(fable_ctx* ctx, size_t bytes, double** out) {
 }
 }  // namespace
 
+// copy the strict upper triangle (element (u,v), u<v, at u + p*v) onto the lower one.
+__global__ void __launch_bounds__(256) k_mirror_upper(double* __restrict__ A, int64_t p) {
+  __shared__ double t[32][33];
+  const int I = blockIdx.x, J = blockIdx.y;
+  if (I > J) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t u = static_cast<int64_t>(I) * 32 + tx, v = static_cast<int64_t>(J) * 32 + r;
+    t[r][tx] = (u < p && v < p) ? A[u + p * v] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    // write element (row v, col u) = A[v + p*u] for v = J*32+tx, u = I*32+r, where u < v
+    const int64_t v = static_cast<int64_t>(J) * 32 + tx, u = static_cast<int64_t>(I) * 32 + r;
+    if (u < p && v < p && u < v) A[v + p * u] = t[tx][r];
+  }
+}
+
+static int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p) {
+  const unsigned nT = static_cast<unsigned>(ceil_div(p, 32));
+  k_mirror_upper<<<dim3(nT, nT), 256, 0, ctx->stream>>>(dA, p);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
 // C (M x M, upper triangle + mirrored) = alpha * A A',  A: M x K (K-slow or K-fast)
 int fb_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alpha, const double* dA, int64_t lda,
             double* dC, int64_t ldc) {

@@ -36,6 +36,9 @@ __device__ double quantile5(const double* x, int N, double P) {
   const double h = dn * P + 0.5;
   const int kk = static_cast<int>(floor(h));
   const double w = h - static_cast<double>(kk);
+  // P == P_max exactly (alpha MC == 1 for the upper level): kk == N, w == 0 -- the value is the maximum; x[N] is the
+  // +inf padding of the sort (or past the buffer when N is a power of two) and 0 * inf would be NaN
+  if (kk >= N) return x[N - 1];
   return (1.0 - w) * x[kk - 1] + w * x[kk];
 }
 

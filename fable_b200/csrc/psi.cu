@@ -31,6 +31,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "tiles.cuh"
 
 // PSI_LAB: diagnostic builds only (tools/psi_lab.sh, profiles/r01_psi_lab.md): 1 skips the DMMA loop, 2 the operand
 // prefetch, 4 the staging stores, 16 the accumulator loads, 32 makes every draw read the operands of draw 0 (L2-resident) -- results are then wrong by construction; never defined
@@ -41,7 +42,7 @@
 
 namespace {
 
-constexpr int TILE = 64;
+constexpr int TILE = fbt::TILE;
 constexpr int KC = 16;             // rank chunk per pipeline step (multiple of 4)
 constexpr int OSTR = TILE + 4;     // operand row stride: 68 = 4 mod 16 -> conflict-free DMMA fragment loads
 constexpr int BOXW = 16;           // TMA box row: 16 doubles = 128 bytes = one swizzle row
@@ -76,28 +77,7 @@ __device__ __forceinline__ int m_off(int u, int v) {
   return (v >> 4) * BOX_DOUBLES + u * BOXW + ((((v & 15) >> 1) ^ (u & 7)) << 1) + (v & 1);
 }
 
-__device__ __forceinline__ void tri_of(int64_t t, int& I, int& J) {
-  // column-major enumeration of an upper triangle: t = J(J+1)/2 + I, 0 <= I <= J
-  int64_t j = static_cast<int64_t>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
-  while (j * (j + 1) / 2 > t) --j;
-  while ((j + 1) * (j + 2) / 2 <= t) ++j;
-  J = static_cast<int>(j);
-  I = static_cast<int>(t - j * (j + 1) / 2);
-}
-
-// Tile order: super-blocks of SB x SB tiles (the super-blocks enumerated over their own upper triangle,
-// tiles column-major inside).  The CTAs resident at any time then share 2*SB operand row blocks, which
-// are re-read after ~SB tiles instead of after a whole block column, so the operand rows stay in L2
-// under the write stream.  Returns false for the padding slots (below the diagonal / past the edge).
-constexpr int SB = 16;
-__device__ __forceinline__ bool tile_of(int64_t t, int nT, int& I, int& J) {
-  int sI, sJ;
-  tri_of(t / (SB * SB), sI, sJ);
-  const int r = static_cast<int>(t % (SB * SB));
-  I = sI * SB + (r % SB);
-  J = sJ * SB + (r / SB);
-  return I <= J && J < nT;
-}
+constexpr int SB = fbt::SB;        // tile order: super-blocks of SB x SB tiles (tiles.cuh)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -137,12 +117,6 @@ __device__ __forceinline__ void tma_store_subbox(const CUtensorMap* tmap, int ro
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(
                    reinterpret_cast<uint64_t>(tmap)),
                "r"(row), "r"(col), "r"(slot), "r"(smem_u32(ssrc)), "l"(pol)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_subbox(const CUtensorMap* tmap, int row, int col, const double* ssrc) {
-  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
-                   reinterpret_cast<uint64_t>(tmap)),
-               "r"(row), "r"(col), "r"(0), "r"(smem_u32(ssrc))
                : "memory");
 }
 // 64 x 64 box added (FP64, in L2) into a p x p accumulator: each entry is touched by exactly one CTA
@@ -201,16 +175,26 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   double* M = D + G_::STAGE_DOUBLES;                                // mirrored staging (swizzled sub-boxes)
 
   int I, J;
-  if (!tile_of(tile_begin + blockIdx.x / HALVES, static_cast<int>((a.p + TILE - 1) / TILE), I, J)) return;
+  const int64_t tslot = tile_begin + blockIdx.x / HALVES;
+  if (!fbt::tile_of(tslot, a.nT, I, J)) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wu = warp % G_::NWU, wv = warp / G_::NWU;
-  const int64_t u0 = static_cast<int64_t>(I) * TILE, v0 = static_cast<int64_t>(J) * TILE + (blockIdx.x % HALVES) * TV;
+  const int vh = (blockIdx.x % HALVES) * TV;     // column offset of this CTA's part inside the tile
+  const int64_t u0 = static_cast<int64_t>(I) * TILE, v0 = static_cast<int64_t>(J) * TILE + vh;
   const int64_t p = a.p;
   if (v0 >= p) return;                           // second half of an edge tile
   const bool diag = (I == J);
-  const bool even = a.tma_mode != 0;             // TMA tensor maps exist (1: 4-D whole-tile boxes, 2: 3-D sub-boxes)
-  const bool bulk = MAT && even;
+  const bool bulk = MAT && a.tma_mode != 0;      // output tensor maps exist (1: 4-D whole-tile boxes, 2: 3-D sub-boxes)
+  // TMA coordinates (column, 16-row block).  Accumulators are always COMPACT (tiles.cuh): tile c = columns [64c, 64c+64)
+  // of a 64-row matrix.  The materialised draws are either dense p x p matrices (direct tile at (u0, v0), mirrored at
+  // (v0, u0)) or, under a tile partition, compact per rank: direct tile at 2c, mirrored at 2c + 1.
+  const int cl = static_cast<int>(fbt::cidx(tslot, a.nT) - a.cbase);
+  const int acol = cl * TILE + vh;
+  const int dcol = a.out_compact ? 2 * cl * TILE + vh : static_cast<int>(v0);
+  const int drb = a.out_compact ? 0 : static_cast<int>(u0 >> 4);
+  const int mcol = a.out_compact ? (2 * cl + 1) * TILE : static_cast<int>(u0);
+  const int mrb = a.out_compact ? (vh >> 4) : static_cast<int>(v0 >> 4);
   const int K4 = a.KP;
   const int nch = (K4 + KC - 1) / KC;
   const int nsteps = (a.B + (CC ? 1 : 0)) * nch;
@@ -248,14 +232,14 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   // Materialising kernels with whole-box tensor maps: the running accumulator tiles are fetched by two TMA tensor
   // loads into the (still unused) staging buffers and folded into the registers when draw 0 is accumulated.
   __shared__ uint64_t acc_bar;
-  const bool acc_tma = MAT && ACC && a.tma_mode == 1 && !(PSI_LAB & 16);
+  const bool acc_tma = MAT && ACC && !(PSI_LAB & 16);
   if (acc_tma) {
     if (tid == 0) mbar_init(&acc_bar, 1);
     __syncthreads();
     if (tid == 0) {
       mbar_expect_tx(&acc_bar, 2 * G_::STAGE_DOUBLES * sizeof(double));
-      tma_load_tile(&tmap_sum, static_cast<int>(v0), static_cast<int>(u0 >> 4), D, &acc_bar);
-      tma_load_tile(&tmap_sq, static_cast<int>(v0), static_cast<int>(u0 >> 4), M, &acc_bar);
+      tma_load_tile(&tmap_sum, acol, 0, D, &acc_bar);
+      tma_load_tile(&tmap_sq, acol, 0, M, &acc_bar);
     }
   }
 
@@ -269,16 +253,10 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         c[i][j][e] = 0.0;
-        if (ACC) {
-          // without whole-box tensor maps the running HBM accumulators are loaded into the register accumulators
-          // up front; either way they are first needed when draw 0 is folded in, and the batch ends with a plain
-          // store (no read-modify-write, no L2 atomics).  (Materialising kernels only; the accumulate-only
-          // kernel is FP64-bound and keeps zero-init + one TMA reduce-add per batch.)
-          const int64_t u = u0 + wu * WR + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
-          const bool in = MAT && !acc_tma && !(PSI_LAB & 16) && u < p && v < p;
-          acc_s[i][j][e] = in ? __ldcs(a.acc_sum + v * p + u) : 0.0;
-          acc_q[i][j][e] = in ? __ldcs(a.acc_sq + v * p + u) : 0.0;
-        }
+        // the running HBM accumulators (materialising kernels) arrive by TMA and are first needed when draw 0 is folded
+        // in; the batch ends with a plain store (no read-modify-write, no L2 atomics).  The accumulate-only kernel is
+        // FP64-bound and keeps zero-init + one TMA reduce-add per batch.
+        if (ACC) { acc_s[i][j][e] = 0.0; acc_q[i][j][e] = 0.0; }
       }
 
   if (nch == 1 && a.k < K4) {
@@ -421,8 +399,8 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
         // after the next draw has been computed.
         if (tid == 0) {
           if (a.tma_mode == 1) {
-            tma_store_tile(&tmap, static_cast<int>(v0), static_cast<int>(u0 >> 4), a.slot0 + b, D, pol_stream);
-            if (!diag) tma_store_tile(&tmap_m, static_cast<int>(u0), static_cast<int>(v0 >> 4), a.slot0 + b, M, pol_stream);
+            tma_store_tile(&tmap, dcol, drb, a.slot0 + b, D, pol_stream);
+            if (!diag) tma_store_tile(&tmap_m, mcol, mrb, a.slot0 + b, M, pol_stream);
           } else {
             for (int q = 0; q < TILE / BOXW; ++q) {
               if (u0 + q * BOXW < p)
@@ -454,9 +432,10 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   }
   if (bulk && tid == 0) bulk_wait_read();             // staging must stay valid until the last stores have read it
 
-  if (ACC && even) {
-    // one update of the HBM accumulators per batch (upper tiles only): the register accumulators
-    // (old value + batch) are staged as two swizzled tiles and leave as plain TMA tensor stores
+  if (ACC) {
+    // one update of the HBM accumulators per batch: the register accumulators (old value + batch) are staged as two
+    // swizzled tiles and leave as plain TMA tensor stores into the compact tile-major buffers (any p: a tile's 32 KB
+    // are always whole and aligned; rows / columns past p hold zeros)
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NI; ++i)
@@ -471,61 +450,52 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-      if (a.tma_mode == 1) {
-        if (MAT) {
-          tma_store_tile(&tmap_sum, static_cast<int>(v0), static_cast<int>(u0 >> 4), 0, D, pol_stream);
-          tma_store_tile(&tmap_sq, static_cast<int>(v0), static_cast<int>(u0 >> 4), 0, M, pol_stream);
-        } else {
-          tma_reduce_add_tile(&tmap_sum, static_cast<int>(v0), static_cast<int>(u0 >> 4), D);
-          tma_reduce_add_tile(&tmap_sq, static_cast<int>(v0), static_cast<int>(u0 >> 4), M);
-        }
+      if (MAT) {
+        tma_store_tile(&tmap_sum, acol, 0, 0, D, pol_stream);
+        tma_store_tile(&tmap_sq, acol, 0, 0, M, pol_stream);
       } else {
-        for (int q = 0; q < TILE / BOXW; ++q)
-          if (u0 + q * BOXW < p) {
-            if (MAT) {
-              tma_store_subbox(&tmap_sum, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), 0, D + q * BOX_DOUBLES, pol_stream);
-              tma_store_subbox(&tmap_sq, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), 0, M + q * BOX_DOUBLES, pol_stream);
-            } else {
-              tma_reduce_add_subbox(&tmap_sum, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), D + q * BOX_DOUBLES);
-              tma_reduce_add_subbox(&tmap_sq, static_cast<int>(u0) + q * BOXW, static_cast<int>(v0), M + q * BOX_DOUBLES);
-            }
-          }
+        tma_reduce_add_tile(&tmap_sum, acol, 0, D);
+        tma_reduce_add_tile(&tmap_sq, acol, 0, M);
       }
       bulk_commit();
       bulk_wait_read();
     }
-  } else if (ACC) {
-    // odd p (no tensor maps): the register accumulators hold old + batch (MAT) or the batch alone
-#pragma unroll
-    for (int i = 0; i < NI; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int64_t u = u0 + wu * WR + i * 8 + g, v = v0 + wv * 16 + j * 8 + 2 * t + e;
-          if (v < p && u < p) {
-            if (MAT) { a.acc_sum[v * p + u] = acc_s[i][j][e]; a.acc_sq[v * p + u] = acc_q[i][j][e]; }
-            else { a.acc_sum[v * p + u] += acc_s[i][j][e]; a.acc_sq[v * p + u] += acc_q[i][j][e]; }
-          }
-        }
   }
 }
 
-// copy the strict upper triangle (element (u,v), u<v, at u + p*v) onto the lower one.
-__global__ void __launch_bounds__(256) k_mirror_upper(double* __restrict__ A, int64_t p) {
-  __shared__ double t[32][33];
-  const int I = blockIdx.x, J = blockIdx.y;
-  if (I > J) return;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t u = static_cast<int64_t>(I) * 32 + tx, v = static_cast<int64_t>(J) * 32 + r;
-    t[r][tx] = (u < p && v < p) ? A[u + p * v] : 0.0;
+// Compact tiles -> dense column panel.  out is the p x ncols panel (leading dimension p) of columns [col0, col0 + ncols)
+// of the dense symmetric matrix; the CTA of dense block (R, C) reads tile (min, max) of the compact buffer -- transposed
+// when R > C (`paired` = 0: accumulators, upper tiles only) or from the stored mirrored copy (paired = 1: materialised
+// draws, direct tile at 2c, mirrored at 2c + 1).  Blocks whose tile lies outside the slice [t_lo, t_hi) are written as
+// zeros, so the panels of the ranks of a tile partition add up to the full matrix.
+__global__ void __launch_bounds__(256) k_tiles_to_dense(const double* __restrict__ tiles, int nT, int64_t t_lo, int64_t t_hi,
+                                                        int64_t cbase, int paired, int64_t p, int64_t col0, int64_t ncols,
+                                                        double* __restrict__ out) {
+  __shared__ double sm[TILE][TILE + 1];
+  const int R = blockIdx.x;                                        // dense row block
+  const int64_t cb0 = col0 + static_cast<int64_t>(blockIdx.y) * TILE;  // first dense column of this block
+  const int C = static_cast<int>(cb0 / TILE);                     // col0 is a multiple of 64
+  const int I = R < C ? R : C, J = R < C ? C : R;
+  const int64_t ts = fbt::slot_of(I, J);
+  const bool own = ts >= t_lo && ts < t_hi;
+  const bool lower = R > C;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;          // 64 x 4
+  const double* src = nullptr;
+  if (own) {
+    const int64_t c = fbt::cidx(ts, nT) - cbase;
+    src = tiles + (paired ? 2 * c + (lower ? 1 : 0) : c) * fbt::TILE_DOUBLES;
   }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    // write element (row v, col u) = A[v + p*u] for v = J*32+tx, u = I*32+r, where u < v
-    const int64_t v = static_cast<int64_t>(J) * 32 + tx, u = static_cast<int64_t>(I) * 32 + r;
-    if (u < p && v < p && u < v) A[v + p * u] = t[tx][r];
+  const bool transpose = lower && !paired;
+  if (own && transpose) {
+    for (int cc = ty; cc < TILE; cc += 4) sm[cc][tx] = src[cc * TILE + tx];      // sm[v][u] = tile(u, v)
+    __syncthreads();
+  }
+  for (int cc = ty; cc < TILE; cc += 4) {
+    const int64_t col = cb0 + cc, row = static_cast<int64_t>(R) * TILE + tx;
+    if (col >= col0 + ncols || col >= p || row >= p) continue;
+    double v = 0.0;
+    if (own) v = transpose ? sm[tx][cc] : src[cc * TILE + tx];      // dense (row, col) = tile(col - .., row - ..) transposed
+    out[(col - col0) * p + row] = v;
   }
 }
 
@@ -542,12 +512,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// p x p x slots FP64 tensor of column-major matrices, 128-byte swizzle.
-//   p % 16 == 0: 4-D (r_lo 16, column p, r_hi p/16, slot), box {16, 64, 4, 1} = a whole tile per store
-//   p %  2 == 0: 3-D (row p, column p, slot),              box {16, 64, 1}    = one sub-box per store
-//   box_cols x (16 * box_rblk) rows per 4-D store: {64, 4} whole 64 x 64 tiles; {32, 4} / {64, 2} the direct / mirrored
-//   image of a 64 x 32 half tile
-int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorMap* out, int box_cols = TILE,
+// `slots` column-major FP64 matrices of rows x cols (slot stride rows * cols), 128-byte swizzle.
+//   rows % 16 == 0: 4-D (r_lo 16, column, r_hi rows/16, slot), box {16, box_cols, box_rblk, 1}: {64, 4} whole 64 x 64 tiles,
+//                   {32, 4} / {64, 2} the direct / mirrored image of a 64 x 32 half tile
+//   rows %  2 == 0: 3-D (row, column, slot),                    box {16, 64, 1} = one sub-box per store
+// Dense draws: rows = cols = p.  Compact tile buffers (tiles.cuh): rows = 64, cols = 64 x tiles.
+int make_output_map(fable_ctx* ctx, double* base, int64_t rows, int64_t cols, int slots, CUtensorMap* out, int box_cols = TILE,
                     int box_rblk = TILE / BOXW) {
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
@@ -557,20 +527,20 @@ int make_output_map(fable_ctx* ctx, double* psi, int64_t p, int slots, CUtensorM
     if (!fn || q != cudaDriverEntryPointSuccess) return ctx->fail(FABLE_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  const cuuint64_t up = static_cast<cuuint64_t>(p);
+  const cuuint64_t ur = static_cast<cuuint64_t>(rows), uc = static_cast<cuuint64_t>(cols);
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r;
-  if (p % BOXW == 0) {
-    const cuuint64_t dims[4] = {BOXW, up, up / BOXW, static_cast<cuuint64_t>(slots)};
-    const cuuint64_t strides[3] = {up * 8, BOXW * 8, up * up * 8};
+  if (rows % BOXW == 0) {
+    const cuuint64_t dims[4] = {BOXW, uc, ur / BOXW, static_cast<cuuint64_t>(slots)};
+    const cuuint64_t strides[3] = {ur * 8, BOXW * 8, ur * uc * 8};
     const cuuint32_t box[4] = {BOXW, static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rblk), 1};
-    r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, psi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
-    const cuuint64_t dims[3] = {up, up, static_cast<cuuint64_t>(slots)};
-    const cuuint64_t strides[2] = {up * 8, up * up * 8};
+    const cuuint64_t dims[3] = {ur, uc, static_cast<cuuint64_t>(slots)};
+    const cuuint64_t strides[2] = {ur * 8, ur * uc * 8};
     const cuuint32_t box[3] = {BOXW, TILE, 1};
-    r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, psi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) return ctx->fail(FABLE_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
@@ -594,8 +564,8 @@ int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned slots, int64_t t0, con
 }
 
 // TV = 32 (half tiles, three CTAs per SM) is used for the materialising kernels whenever whole-tile 4-D stores
-// exist (p % 16 == 0): the batch is bound by how evenly the SMs keep HBM's write queues fed, and three
-// staggered store streams per SM do that better than two (tools/store_lab.cu lab 2).  FABLE_B200_PSI_TV=64
+// exist (dense p % 16 == 0, or compact output): the batch is bound by how evenly the SMs keep HBM's write queues fed,
+// and three staggered store streams per SM do that better than two (tools/store_lab.cu lab 2).  FABLE_B200_PSI_TV=64
 // forces the whole-tile kernel (A/B measurements).
 int psi_tv(const PsiArgs& a, bool mat) {
   static int forced = -1;
@@ -611,7 +581,8 @@ int psi_tv(const PsiArgs& a, bool mat) {
 
 int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
   PsiArgs a = a_in;
-  a.tma_mode = (a.p % BOXW == 0) ? 1 : ((a.p & 1) == 0 ? 2 : 0);
+  a.nT = static_cast<int>(fbt::n_tiles(a.p));
+  a.tma_mode = (a.out_compact || a.p % BOXW == 0) ? 1 : ((a.p & 1) == 0 ? 2 : 0);
   FB_REQUIRE(ctx, a.p > 0 && a.k > 0 && a.B > 0, "psi: empty problem");
   FB_REQUIRE(ctx, (a.acc_sum == nullptr) == (a.acc_sq == nullptr), "psi: need both accumulators");
   const bool mat = a.psi != nullptr, acc = a.acc_sum != nullptr;
@@ -623,8 +594,18 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
              "psi: operand rows must be zero-padded to a multiple of 64 and 16-byte aligned");
   FB_REQUIRE(ctx, a.KP % 4 == 0 && a.KP >= a.k, "psi: operand rank must be zero-padded to a multiple of 4");
   FB_REQUIRE(ctx, !mat || a.psi_slots >= a.slot0 + a.B, "psi: one output slot per draw of the batch");
-  const int64_t nT = ceil_div(a.p, TILE), nSB = ceil_div(nT, SB);
-  const int64_t tiles = nSB * (nSB + 1) / 2 * SB * SB;    // super-block order, padding slots exit at once
+  const int64_t tiles = fbt::n_slots(a.p);    // super-block order, padding slots exit at once
+  // slice of the tile enumeration (multi-GPU partition B: every rank processes all draws for its own tiles; no
+  // collective); compact buffers start at the first tile of the slice
+  int64_t t_lo = 0, t_hi = tiles;
+  if (a.tile_end > 0) {
+    FB_REQUIRE(ctx, a.tile_begin >= 0 && a.tile_begin <= a.tile_end && a.tile_end <= tiles, "psi: tile range out of bounds");
+    t_lo = a.tile_begin; t_hi = a.tile_end;
+  }
+  a.cbase = fbt::cidx(t_lo, a.nT);
+  const int64_t ntile = fbt::cidx(t_hi, a.nT) - a.cbase;          // valid tiles of the slice
+  if (ntile == 0) return FABLE_OK;
+  FB_REQUIRE(ctx, ntile < (int64_t(1) << 24), "psi: more than 2^24 tiles in one slice");
   const int64_t chunk = 1 << 29;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->timing) {
@@ -640,25 +621,17 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
   PsiMaps m;
   memset(&m, 0, sizeof(m));
   const int tv = psi_tv(a, mat);
-  if (a.tma_mode != 0) {
-    if (mat) {
-      FB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(a.psi) & 15) == 0, "psi: the output buffer must be 16-byte aligned");
-      FB_TRY(make_output_map(ctx, a.psi, a.p, a.psi_slots, &m.out, tv, TILE / BOXW));
-      FB_TRY(make_output_map(ctx, a.psi, a.p, a.psi_slots, &m.out_m, TILE, tv / BOXW));
-    }
-    if (acc) {
-      FB_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(a.acc_sum) | reinterpret_cast<uintptr_t>(a.acc_sq)) & 15) == 0,
-                 "psi: the accumulators must be 16-byte aligned");
-      FB_TRY(make_output_map(ctx, a.acc_sum, a.p, 1, &m.sum, tv, TILE / BOXW));
-      FB_TRY(make_output_map(ctx, a.acc_sq, a.p, 1, &m.sq, tv, TILE / BOXW));
-    }
+  if (mat && a.tma_mode != 0) {
+    FB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(a.psi) & 15) == 0, "psi: the output buffer must be 16-byte aligned");
+    const int64_t rows = a.out_compact ? TILE : a.p, cols = a.out_compact ? 2 * ntile * TILE : a.p;
+    FB_TRY(make_output_map(ctx, a.psi, rows, cols, a.psi_slots, &m.out, tv, TILE / BOXW));
+    FB_TRY(make_output_map(ctx, a.psi, rows, cols, a.psi_slots, &m.out_m, TILE, tv / BOXW));
   }
-  // optional slice of the tile enumeration (multi-GPU partition B: every rank processes all draws for
-  // its own tiles; no collective)
-  int64_t t_lo = 0, t_hi = tiles;
-  if (a.tile_end > 0) {
-    FB_REQUIRE(ctx, a.tile_begin >= 0 && a.tile_begin <= a.tile_end && a.tile_end <= tiles, "psi: tile range out of bounds");
-    t_lo = a.tile_begin; t_hi = a.tile_end;
+  if (acc) {
+    FB_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(a.acc_sum) | reinterpret_cast<uintptr_t>(a.acc_sq)) & 15) == 0,
+               "psi: the accumulators must be 16-byte aligned");
+    FB_TRY(make_output_map(ctx, a.acc_sum, TILE, ntile * TILE, 1, &m.sum, tv, TILE / BOXW));
+    FB_TRY(make_output_map(ctx, a.acc_sq, TILE, ntile * TILE, 1, &m.sq, tv, TILE / BOXW));
   }
   for (int64_t t0 = t_lo; t0 < t_hi; t0 += chunk) {
     const unsigned g = static_cast<unsigned>(t_hi - t0 < chunk ? t_hi - t0 : chunk);
@@ -680,30 +653,13 @@ int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64
   return FABLE_OK;
 }
 
-// upper triangle (u <= v) of a column-major p x p matrix <-> packed vector, element (u, v) at v(v+1)/2 + u
-__global__ void __launch_bounds__(256) k_pack_upper(double* __restrict__ A, int64_t p, double* __restrict__ packed, int unpack) {
-  const int64_t v = blockIdx.y;
-  const int64_t u = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (u > v) return;
-  const int64_t i = v * (v + 1) / 2 + u;
-  if (unpack) A[u + p * v] = packed[i]; else packed[i] = A[u + p * v];
-}
-
-int fb_pack_upper(fable_ctx* ctx, double* dA, int64_t p, double* d_packed, int unpack) {
-  dim3 grid(static_cast<unsigned>(ceil_div(p, 256)), static_cast<unsigned>(p));
-  k_pack_upper<<<grid, 256, 0, ctx->stream>>>(dA, p, d_packed, unpack);
-  FB_LAUNCHED(ctx);
-  return FABLE_OK;
-}
-
-int64_t fb_psi_tile_slots(int64_t p) {
-  const int64_t nT = ceil_div(p, TILE), nSB = ceil_div(nT, SB);
-  return nSB * (nSB + 1) / 2 * SB * SB;
-}
-
-int fb_mirror_upper(fable_ctx* ctx, double* dA, int64_t p) {
-  const unsigned nT = static_cast<unsigned>(ceil_div(p, 32));
-  k_mirror_upper<<<dim3(nT, nT), 256, 0, ctx->stream>>>(dA, p);
+int fb_tiles_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t p, int64_t t_lo, int64_t t_hi, int paired, int64_t col0,
+                      int64_t ncols, double* d_out) {
+  FB_REQUIRE(ctx, col0 % TILE == 0 && col0 >= 0 && ncols >= 1 && col0 + ncols <= p, "tiles_to_dense: bad column panel");
+  const int nT = static_cast<int>(fbt::n_tiles(p));
+  if (t_hi <= 0) { t_lo = 0; t_hi = fbt::n_slots(p); }
+  dim3 grid(static_cast<unsigned>(nT), static_cast<unsigned>(ceil_div(ncols, TILE)));
+  k_tiles_to_dense<<<grid, 256, 0, ctx->stream>>>(d_tiles, nT, t_lo, t_hi, fbt::cidx(t_lo, nT), paired, p, col0, ncols, d_out);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
 }

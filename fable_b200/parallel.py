@@ -47,19 +47,18 @@ def draw_range(MC, rank, world):
 
 def tile_slots(p, tile=64, sb=16):
     """Length of the covariance kernel's tile enumeration: upper-triangle 64 x 64 tiles in 16 x 16
-    super-block order, padding slots included (same count as fable_posterior_tile_slots)."""
+    super-block order, padding slots included (same count as fable_tile_slots)."""
     nT = -(-int(p) // tile)
     nSB = -(-nT // sb)
     return nSB * (nSB + 1) // 2 * sb * sb
 
 
-def tile_range(p, rank, world, tile=64, sb=16):
-    """Contiguous [t_begin, t_end) of the tile enumeration owned by `rank` (multiples of a super-block
-    so every rank keeps the operand locality of the kernel's order)."""
-    total = tile_slots(p, tile, sb)
-    blocks = total // (sb * sb)
-    lo, hi = draw_range(blocks, rank, world)
-    return lo * sb * sb, hi * sb * sb
+def tile_range(p, rank, world):
+    """Contiguous [t_begin, t_end) of the tile enumeration owned by `rank`: equal shares of the VALID tiles
+    (fable_tile_partition; a contiguous slice keeps the operand locality of the kernel's order and owns a
+    contiguous range of the compact tile storage)."""
+    from . import api
+    return api.tile_partition(p, rank, world)
 
 
 class _DevArray:
@@ -86,15 +85,15 @@ def allreduce_moments(tensors, group=None):
 
 def reduce_posterior_accumulators(post, device, dst=0, group=None):
     """The one exchange step of partition A: sum the device-resident sum / sumsq accumulators of a
-    fable_posterior over ranks.  Only their upper triangles carry information, so those are packed
-    (p(p+1)/2 doubles each) and reduced to rank `dst` (dst=None: all-reduce, every rank gets the sums);
-    the result is unpacked in place on the receiving rank(s).  The library's stream is drained first and
-    torch's current stream after, so the two stream domains never overlap on the buffers."""
+    fable_posterior over ranks.  They are stored as compact upper tiles (the lower triangle is never kept), so
+    the buffers are reduced in place as they are, to rank `dst` (dst=None: all-reduce, every rank gets the
+    sums).  The library's stream is drained first and torch's current stream after, so the two stream domains
+    never overlap on the buffers."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    a, b, n = post.accum_pack()
+    a, b, n = post.accum_dev()
     post.ctx.synchronize()
     ts = [as_torch(a, n, device), as_torch(b, n, device)]
     for t in ts:
@@ -103,9 +102,6 @@ def reduce_posterior_accumulators(post, device, dst=0, group=None):
         else:
             dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
     torch.cuda.synchronize(device)
-    if dst is None or dist.get_rank(group) == dst:
-        post.accum_unpack()
-        post.ctx.synchronize()
 
 
 def allreduce_posterior_accumulators(post, device, group=None):

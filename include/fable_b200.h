@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FABLE_B200_ABI_VERSION 1
+#define FABLE_B200_ABI_VERSION 2
 
 typedef enum {
   FABLE_OK = 0,
@@ -213,39 +213,73 @@ int fable_posterior_get(fable_posterior* post, double* G0s, double* gnd, double*
 /* One batch of B draws m0..m0+B-1 entirely on the device:
  *   sampler kernel -> Lambda_m, sigma2_m (working layout) -> covariance kernel.
  * dev_psi: device buffer of `psi_slots` >= B dense p x p matrices (NULL = do not materialise); draw m
- * lands in slot m - m0 (tiles are processed batch-major, so every draw of a launch needs its own slot).  accumulate != 0 adds the batch into the posterior's own sum / sumsq
- * accumulators (upper tiles; mirrored on fetch).  gam/z: injected DEVICE buffers or NULL. */
+ * lands in slot m - m0 (tiles are processed batch-major, so every draw of a launch needs its own slot).
+ * accumulate != 0 adds the batch into the posterior's own sum / sumsq accumulators (compact upper tiles, see
+ * "tile layout" below).  gam/z: injected DEVICE buffers or NULL. */
 int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi,
                                int psi_slots, int accumulate, const double* dev_gam,
                                const double* dev_z);
+/* The same batch with the draws materialised COMPACTLY for the posterior's tile slice (multi-GPU partition B: a rank
+ * stores only what it owns).  dev_psi_tiles: `psi_slots` >= B slots of 2 * tiles * 4096 doubles, tiles =
+ * fable_tile_count(p, t_begin, t_end); in a slot, the slice's tile number c (compact order) is stored as the pair
+ * (block (I, J) of Psi_m at 2c, its mirror image block (J, I) at 2c + 1), each a column-major 64 x 64 block -- the
+ * rank's share of the dense symmetric matrix, 8 p^2 / world bytes per draw.  Works for any p (edge tiles are padded
+ * with zeros).  fable_posterior_tiles_to_dense(.., paired = 1, ..) expands a slot. */
+int fable_posterior_draw_batch_tiles(fable_posterior* post, int64_t m0, int B, double* dev_psi_tiles,
+                                     int psi_slots, int accumulate, const double* dev_gam,
+                                     const double* dev_z);
 /* f3: CCFABLE_DirectSampler (R/FABLE_code.R:212-298).  on != 0: the draws materialised by draw_batch become
  *   Psi_m = G + B o (Lambda_m Lambda_m' - G) + diag(sigma2_m),  B = cov_correct_matrix(sig_hat, G)  (R:251, 282-290),
  * the entry-wise coverage correction of the R prototype, with G = G0 G0' (shrunk G0) and B formed per tile
  * on the fly (never stored).  The prototype uses a_n = 1/sqrt(n + 1/tau^2): create the posterior with
  * varInflation = 1.  Accumulators, when requested, sum the corrected draws. */
 int fable_posterior_set_entrywise_correction(fable_posterior* post, int on);
-/* Multi-GPU partition B (tiles): restrict draw_batch to the slice [t_begin, t_end) of the kernel's tile
- * enumeration (64 x 64 upper-triangle tiles in 16 x 16 super-block order; fable_posterior_tile_slots
- * gives its length, padding slots included).  Ranks owning disjoint slices and processing the same
- * draws produce disjoint parts of every Psi_m and of the accumulators: no collective is needed.
- * t_end == 0 restores the full range.  (Only upper tiles are written; mirror / fetch as usual.) */
+/* ---- tile layout and multi-GPU partition B (tiles) ----------------------------------------------------------
+ * The covariance pass cuts Psi into 64 x 64 tiles and computes the tiles (I, J), I <= J -- the reference's pair loop
+ * j1 <= j2 (updated-FABLE-functions.cpp:650, 662) -- enumerated in 16 x 16 super-blocks (super-blocks over their own
+ * upper triangle, column-major; tiles column-major inside).  The enumeration has fable_tile_slots(p) slots, padding
+ * slots (below the diagonal of diagonal super-blocks, past the edge) included; storage is COMPACT: valid tiles only, in
+ * enumeration order, 4096 doubles (a column-major 64 x 64 block) each.  A slice [t_begin, t_end) of the enumeration
+ * therefore owns a contiguous range of compact tiles (fable_tile_count of them): the sum / sumsq accumulators of a
+ * posterior hold exactly the upper tiles of its slice.
+ * fable_posterior_set_tile_range restricts draw_batch / draw_batch_tiles to a slice (t_end == 0: everything) and
+ * drops the accumulators of the previous slice.  Ranks owning disjoint slices and processing the same draws produce
+ * disjoint parts of every Psi_m and of the accumulators: no collective is needed (the reference's answer to large p
+ * is likewise to work on sub-matrices, :716-818).  fable_tile_partition gives rank `rank` of `world` a slice with an
+ * equal share of the valid tiles; fable_tile_locate the slot and compact index (counted from the start of the
+ * enumeration) of tile (I, J). */
+int fable_tile_slots(int64_t p, int64_t* slots);
+int fable_tile_count(int64_t p, int64_t t_begin, int64_t t_end, int64_t* tiles);
+int fable_tile_partition(int64_t p, int rank, int world, int64_t* t_begin, int64_t* t_end);
+int fable_tile_locate(int64_t p, int64_t I, int64_t J, int64_t* slot, int64_t* compact_index);
 int fable_posterior_tile_slots(fable_posterior* post, int64_t* slots);
 int fable_posterior_set_tile_range(fable_posterior* post, int64_t t_begin, int64_t t_end);
+/* compact tiles of the posterior's slice -> columns [col0, col0 + ncols) of the dense symmetric p x p matrix (DEVICE
+ * pointers; dev_out is p x ncols with leading dimension p; col0 a multiple of 64).  paired = 0: upper tiles only (the
+ * accumulators), the lower triangle is the transpose; paired = 1: (direct, mirrored) pairs as draw_batch_tiles writes
+ * them.  Blocks outside the slice are written as zeros, so the panels of the ranks of a partition add up. */
+int fable_posterior_tiles_to_dense(fable_posterior* post, const double* dev_tiles, int paired, int64_t col0,
+                                   int64_t ncols, double* dev_out);
 /* reference-layout samples for draws m0..m0+MC-1 into HOST arrays with leading dimension ldm
  * (>= MC; rows m-m0) -- NULL to skip either. */
 int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64_t ldm,
                             double* LambdaSamples, double* SigmaSqSamples,
                             const double* gam_inj, const double* z_inj);
-/* accumulators: device pointers (full p x p, upper tiles valid until mirrored), reset, fetch. */
-int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** dev_sumsq);
+/* The draw loop of CPPFABLESampler (:599-618) for draws m0 .. m0 + MC - 1: the reference-layout samples go to HOST
+ * arrays with leading dimension ldm (rows 0 .. MC-1; NULL to skip), and with psi_pass != 0 the covariance pass adds
+ * the same draws into the device-resident accumulators (no reset, nothing p x p crosses PCIe).  This is what one
+ * rank of multi-GPU partition A runs for its share of the MC axis; the accumulators are then summed on the device
+ * (fable_posterior_accum_dev + NCCL) and fetched once by whoever needs them.  fable_posterior_sampler_outputs is
+ * accum_reset + this + accum_fetch + G. */
+int fable_posterior_sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t ldm, const double* gam_inj,
+                                 const double* z_inj, double* LambdaSamples, double* SigmaSqSamples, int psi_pass);
+/* accumulators: device pointers to the compact upper tiles of the slice (count doubles each = tiles * 4096; the
+ * one NCCL sum of multi-GPU partition A -- draws sharded over ranks -- reduces these buffers as they are), reset,
+ * fetch as dense symmetric p x p host matrices (zeros outside the slice), fetch as raw compact tiles. */
+int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** dev_sumsq, int64_t* count);
 int fable_posterior_accum_reset(fable_posterior* post);
-int fable_posterior_accum_mirror(fable_posterior* post); /* make both triangles valid (device) */
-int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sumsq); /* host out  */
-/* Multi-GPU partition A (draws sharded over ranks): pack the upper triangles (element (u,v), u <= v, at
- * v(v+1)/2 + u; count = p(p+1)/2) into device vectors for the one NCCL sum of the path, and write the
- * reduced vectors back.  Only the upper triangle carries information (mirrored on fetch). */
-int fable_posterior_accum_pack(fable_posterior* post, double** dev_sum, double** dev_sumsq, int64_t* count);
-int fable_posterior_accum_unpack(fable_posterior* post);
+int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sumsq);            /* host out */
+int fable_posterior_accum_fetch_tiles(fable_posterior* post, double* sum_tiles, double* sumsq_tiles);
 
 /* ---- device-pointer primitives ------------------------------------------------------------------ */
 /* out[u + p*v] = sum_l A[u + lda*l] A[v + lda*l] + (u==v ? s[u] : 0), dense symmetric p x p

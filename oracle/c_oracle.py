@@ -44,6 +44,18 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n=None):
+    """OpenMP threads of the timed CPU arm: all host cores this process may run on unless told otherwise
+    (torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently make the baseline single-threaded)."""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def philox4x32_10(ctr, key):
     c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
     lib().orc_philox4x32_10(c, k, o)

@@ -222,3 +222,12 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the timed CPU arm sets its thread count itself */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}

@@ -278,6 +278,8 @@ def arma_quantile(x, prob):
     h = N * prob + 0.5
     kk = int(math.floor(h))
     w = h - kk
+    if kk >= x.size:           # prob == P_max exactly: weight 0 on the (non-existent) upper neighbour -> the maximum
+        return float(x[-1])
     return float((1.0 - w) * x[kk - 1] + w * x[kk])
 
 

@@ -259,7 +259,7 @@ inline mat quantile(const mat& v, const mat& P) {
     else {
       const uword k = static_cast<uword>(std::floor(N * p + 0.5));
       const double Pk = (static_cast<double>(k) - 0.5) / N, w = (p - Pk) * N;
-      val = (1.0 - w) * y[k - 1] + w * y[k];
+      val = k >= y.size() ? y.back() : (1.0 - w) * y[k - 1] + w * y[k];   // p == P_max exactly: w == 0, the maximum
     }
     out.mem[q] = val;
   }

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     lib = api._load()
     missing = [s for s in _declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
-    assert lib.fable_abi_version() == 1
+    assert lib.fable_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_gpu():

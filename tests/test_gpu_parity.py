@@ -276,16 +276,19 @@ def test_posterior_batches_accumulate_like_one_pass(ctx, c1):
     post.draw_batch(0, MC, accumulate=True)
     t1, t2 = post.accum_fetch()
     assert relerr_mat(t1, s1) < 1e-13 and relerr_mat(t2, s2) < 1e-13
-    # pack / unpack of the upper triangles (the payload of the multi-GPU reduction) is lossless
-    a_, b_, cnt = post.accum_pack()
-    assert cnt == p * (p + 1) // 2
+    # the accumulators are stored as compact upper tiles (the payload of the multi-GPU reduction, reduced in place):
+    # tile c of the enumeration holds block (I, J) column-major; doubling the device buffer doubles the fetched sums
+    a_, b_, cnt = post.accum_dev()
+    nT = -(-p // 64)
+    assert cnt == nT * (nT + 1) // 2 * 4096 == fb.api.tile_count(p) * 4096
     from fable_b200 import parallel
     ctx.synchronize()
-    packed = parallel.as_torch(a_, cnt, "cuda").clone()
-    iu = np.triu_indices(p); order = np.lexsort((iu[0], iu[1]))
-    np.testing.assert_array_equal(packed.cpu().numpy(), t1[iu[0][order], iu[1][order]])
+    tiles1, tiles2 = post.accum_fetch_tiles()
+    pad = np.zeros((nT * 64, nT * 64)); pad[:p, :p] = t1
+    for I, J in ((0, 0), (0, nT - 1), (nT - 1, nT - 1), (3, 7)):
+        slot, c = fb.api.tile_locate(p, I, J)
+        np.testing.assert_array_equal(tiles1[c].T, pad[64 * I:64 * I + 64, 64 * J:64 * J + 64])
     parallel.as_torch(a_, cnt, "cuda").mul_(2.0); torch.cuda.synchronize()
-    post.accum_unpack()
     u1, u2 = post.accum_fetch()
     np.testing.assert_array_equal(u1, 2.0 * t1); np.testing.assert_array_equal(u2, t2)
     post.close()
@@ -337,27 +340,45 @@ def test_entrywise_corrected_draws_f3(ctx, n, p, k):
     post.close()
 
 
-def test_tile_partition_needs_no_collective(ctx):
-    """Partition B: two 'ranks' owning disjoint tile slices and processing the same draws fill disjoint
-    parts of the accumulators and of every Psi_m; their union is the single-GPU result (p % 16 == 0:
-    the whole-tile TMA path)."""
+@pytest.mark.parametrize("p,world", [(1600, 2), (1600, 3), (1000, 2), (333, 2), (2100, 8)])
+def test_tile_partition_needs_no_collective(ctx, p, world):
+    """Partition B (BASELINE configs[3]): 'ranks' owning disjoint slices of the tile enumeration and processing the same
+    draws hold disjoint shares of every Psi_m and of the accumulators, each stored compactly (only the rank's tiles);
+    expanded to dense with zeros elsewhere, the shares add up to the one-GPU result bit for bit.  p on and off the
+    16-row TMA boxes, odd p, slices that cut super-blocks."""
     import torch
     from fable_b200 import parallel
-    n, p, k, B = 60, 1600, 3, 4
+    n, k, B = 60, 3, 4
     Y, u, d, v = _svd_inputs(n, p, k, 31)
     post = fb.Posterior(Y, 1.0, 1.0, u, v, d, k, 1.4, ctx=ctx)
     assert post.tile_slots() == parallel.tile_slots(p)
     full = torch.zeros((B, p, p), dtype=torch.float64, device="cuda")
     post.draw_batch(0, B, dev_psi=full.data_ptr(), psi_slots=B, accumulate=True)
     f1, f2 = post.accum_fetch()
+    g1 = np.zeros_like(f1); g2 = np.zeros_like(f2)
     parts = torch.zeros((B, p, p), dtype=torch.float64, device="cuda")
-    post.accum_reset()
-    for rank in range(2):
-        post.set_tile_range(*parallel.tile_range(p, rank, 2))
-        post.draw_batch(0, B, dev_psi=parts.data_ptr(), psi_slots=B, accumulate=True)
+    dense = torch.empty((p, p), dtype=torch.float64, device="cuda")
+    owned = 0
+    for rank in range(world):
+        lo, hi = parallel.tile_range(p, rank, world)
+        post.set_tile_range(lo, hi)
+        nt = fb.api.tile_count(p, lo, hi)
+        owned += nt
+        ring = torch.full((B, 2 * nt, 64, 64), float("nan"), dtype=torch.float64, device="cuda")   # the rank's share only
+        post.draw_batch_tiles(0, B, dev_psi_tiles=ring.data_ptr(), psi_slots=B, accumulate=True)
+        _, _, cnt = post.accum_dev()
+        assert cnt == nt * 4096
+        a1, a2 = post.accum_fetch()
+        assert not (np.any(g1 * a1) or np.any(g2 * a2))        # disjoint supports
+        g1 += a1; g2 += a2
+        for b in range(B):
+            post.tiles_to_dense(ring[b].data_ptr(), True, 0, p, dense.data_ptr())
+            ctx.synchronize()
+            assert not torch.any(parts[b] * dense)
+            parts[b] += dense
+    nT = -(-p // 64)
+    assert owned == nT * (nT + 1) // 2
     post.set_tile_range(0, 0)
-    g1, g2 = post.accum_fetch()
-    ctx.synchronize()
     assert torch.equal(full, parts)
     np.testing.assert_array_equal(g1, f1); np.testing.assert_array_equal(g2, f2)
     L, S = post.samples(0, B)
@@ -496,6 +517,27 @@ def test_post_processing_against_oracle(ctx, MC):
         fb.CCFABLEPostProcessingSubmatrix(o, 0.1, [0, 2], ctx=ctx)
     with pytest.raises(fb.FableError):
         fb.CCFABLEPostProcessingSubmatrix(o, 0.1, [2, p + 1], ctx=ctx)
+
+
+@pytest.mark.parametrize("MC,alpha", [(100, 0.01), (20, 0.05), (10, 0.1), (16, 0.0625), (1024, 1.0 / 1024), (1000, 0.001),
+                                      (32768, 1.0 / 32768)])
+def test_post_processing_upper_level_at_p_max(ctx, MC, alpha):
+    """alpha * MC == 1: the upper level 1 - alpha/2 equals P_max = (N - 0.5)/N exactly, h = N, weight 0 on a neighbour
+    that does not exist -- the result is the maximum (never the sort's +inf padding, never a read past the buffer
+    when MC is a power of two); the lower level is the minimum."""
+    n, p, k = 40, 6, 2
+    Y, u, d, v = _svd_inputs(n, p, k, 43)
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=MC + 1)
+    o = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.3, gam, z)
+    ref = orc.post_processing(o, alpha)
+    got = fb.CPPCCFABLEPostProcessing(o, alpha, ctx=ctx)
+    for key in ("PostMeanMatrix", "LowerQuantileMatrix", "UpperQuantileMatrix"):
+        assert np.all(np.isfinite(got[key])), key
+        assert relerr_mat(got[key], ref[key]) < TOL, key
+    L = o["LambdaSamples"].reshape(MC, p, k)
+    v01 = np.einsum("ml,ml->m", L[:, 0, :], L[:, 1, :])
+    assert got["UpperQuantileMatrix"][0, 1] == pytest.approx(v01.max(), rel=1e-12)
+    assert got["LowerQuantileMatrix"][0, 1] == pytest.approx(v01.min(), rel=1e-12)
 
 
 @pytest.mark.parametrize("MC", [1000, 17000, 26000])

@@ -32,15 +32,51 @@ def test_draw_range_partitions_the_mc_axis():
         parallel.draw_range(10, 2, 2)
 
 
+def _enumerate_tiles(p):
+    """Brute-force statement of the covariance pass's tile order (fable_b200/csrc/tiles.cuh): 16 x 16 super-blocks over
+    their own upper triangle, column-major; tiles column-major inside; None for padding slots."""
+    nT = -(-p // 64); nSB = -(-nT // 16)
+    out = []
+    for sJ in range(nSB):
+        for sI in range(sJ + 1):
+            for r in range(256):
+                I, J = sI * 16 + r % 16, sJ * 16 + r // 16
+                out.append((I, J) if I <= J < nT else None)
+    return out
+
+
 def test_tile_range_partitions_the_upper_triangle():
-    for p in (1, 64, 65, 1000, 20000, 50000):
+    from fable_b200 import api
+    for p in (1, 64, 65, 1000, 1025, 5000, 20000, 50000):
+        enum = _enumerate_tiles(p)
         total = parallel.tile_slots(p)
         nT = -(-p // 64)
-        assert total >= nT * (nT + 1) // 2 and total % 256 == 0
-        for world in (1, 2, 8):
+        assert total == len(enum) == api.tile_slots(p) and total % 256 == 0
+        valid = [e for e in enum if e is not None]
+        assert len(valid) == nT * (nT + 1) // 2 == api.tile_count(p) and len(set(valid)) == len(valid)
+        prefix = np.concatenate([[0], np.cumsum([e is not None for e in enum])])
+        for world in (1, 2, 3, 8):
             r = [parallel.tile_range(p, g, world) for g in range(world)]
             assert r[0][0] == 0 and r[-1][1] == total
             assert all(r[g][1] == r[g + 1][0] for g in range(world - 1))
+            counts = [api.tile_count(p, a, b) if b > a else 0 for a, b in r]
+            assert counts == [int(prefix[b] - prefix[a]) for a, b in r]          # the library counts what the enumeration holds
+            assert sum(counts) == len(valid) and max(counts) - min(counts) <= 1  # equal shares of the stored tiles
+        rng = np.random.default_rng(p)
+        for _ in range(50):                                   # slot and compact index of a tile, slices at arbitrary slots
+            J = int(rng.integers(nT)); I = int(rng.integers(J + 1))
+            slot, c = api.tile_locate(p, I, J)
+            assert enum[slot] == (I, J) and c == prefix[slot]
+            a, b = sorted(int(x) for x in rng.integers(0, total + 1, 2))
+            if b > a:
+                assert api.tile_count(p, a, b) == prefix[b] - prefix[a]
+    with pytest.raises(fb_api_error()):
+        api.tile_locate(100, 1, 0)
+
+
+def fb_api_error():
+    from fable_b200 import api
+    return api.FableError
 
 
 def _free_port():

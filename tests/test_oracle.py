@@ -205,6 +205,16 @@ def test_arma_quantile_definition5():
         assert orc.arma_quantile(y, pr) == pytest.approx(np.quantile(y, pr, method="hazen"), rel=1e-13)
 
 
+def test_arma_quantile_at_p_max_is_the_maximum():
+    """alpha N == 1: the level 1 - alpha/2 is exactly (N - 0.5)/N, h = N, the weight of the missing upper neighbour is
+    0: the value is the maximum (and alpha/2 = 0.5/N gives the minimum)."""
+    rng = np.random.default_rng(5)
+    for N, alpha in ((100, 0.01), (20, 0.05), (10, 0.1), (16, 0.0625), (1000, 0.001)):
+        x = rng.standard_normal(N)
+        assert orc.arma_quantile(x, 1.0 - alpha / 2.0) == x.max()
+        assert orc.arma_quantile(x, alpha / 2.0) == x.min()
+
+
 def test_post_processing_mean_matches_moments():
     n, p, k, MC = 25, 6, 2, 11
     Y = synth.factor_data(n, p, k, rep=9)
