@@ -156,6 +156,12 @@ class Context:
         self.check(_load().fable_ctx_kernel_time(self._h, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
 
+    def measure_fp64_peak(self):
+        """DMMA.8x8x4 issue peak of this device in TFLOP/s (diagnostics; the Gram step's roofline denominator)."""
+        v = C.c_double()
+        self.check(_load().fable_ctx_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
     def set_psi_ring(self, slots):
         """slots > 0: the sampler's Psi pass also materialises every draw into a device ring."""
         self.check(_load().fable_ctx_set_psi_ring(self._h, C.c_int(int(slots))))
@@ -548,10 +554,13 @@ class Posterior:
         self.ctx.check(_load().fable_posterior_accum_fetch(self._h, _ptr(s1), _ptr(s2)))
         return s1, s2
 
-    def accum_fetch_tiles(self):
-        """The compact tiles as stored: two arrays (tiles, 64, 64), element [c, v, u] = entry (u, v) of tile c."""
+    def accum_fetch_tiles(self, out=None):
+        """The compact tiles as stored: two arrays (tiles, 64, 64), element [c, v, u] = entry (u, v) of tile c.
+        `out`: two flat float64 host arrays of the right length (e.g. pinned) to fill instead."""
         _, _, n = self.accum_dev()
-        s1 = np.empty(n); s2 = np.empty(n)
+        s1, s2 = out if out is not None else (np.empty(n), np.empty(n))
+        if s1.size != n or s2.size != n:
+            raise FableError(1, "accum_fetch_tiles: out arrays must hold tiles * 4096 doubles")
         self.ctx.check(_load().fable_posterior_accum_fetch_tiles(self._h, _ptr(s1), _ptr(s2)))
         return s1.reshape(-1, 64, 64), s2.reshape(-1, 64, 64)
 

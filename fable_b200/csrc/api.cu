@@ -485,7 +485,8 @@ static int svd_sharded(fable_ctx* ctx, const double* dY, int64_t n, int64_t p_lo
   FB_TRY(shard_sum(ctx, h.data(), static_cast<int64_t>(h.size())));
   FB_CUDA(ctx, cudaMemcpyAsync(G.d(), h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   int sweeps = 0;
-  FB_TRY(fb_syevj(ctx, G.d(), n, W.d(), dU, &sweeps));                              // replicated, identical bits
+  int64_t defl = 0;      // triplets deflated at the eigensolver's noise floor (rank-deficient Y): d = 0, U completed, V zero
+  FB_TRY(fb_syevj(ctx, G.d(), n, W.d(), dU, &sweeps, &defl));                       // replicated, identical bits
   FB_TRY(fb_gemm(ctx, 1, 1, p_loc, r, n, 1.0, dY, n, dU, n, dV, p_loc));           // T = Y_loc' U
   // d_l = || T[:, l] || over all ranks
   FB_TRY(fb_col_sumsq(ctx, dV, p_loc, p_loc, r, tmp.d()));
@@ -511,7 +512,7 @@ static int svd_sharded(fable_ctx* ctx, const double* dY, int64_t n, int64_t p_lo
       if (slot[0] > bm || (slot[0] == bm && slot[1] < bi)) { bm = slot[0]; bi = slot[1]; bv = slot[2]; }
     }
     const double sgn = bv < 0.0 ? -1.0 : 1.0;
-    const double nv = std::sqrt(ss[l]);
+    const double nv = l >= r - defl ? 0.0 : std::sqrt(ss[l]);     // (a shard cannot complete V: the column is left zero)
     ss[l] = nv;
     scale[l] = nv > 0.0 ? sgn / nv : 0.0;     // V column: normalise and orient
     scale[r + l] = sgn;                       // U column: orient
@@ -634,6 +635,12 @@ int fable_ctx_kernel_time(fable_ctx* ctx, double* total_ms, int64_t* launches) {
   if (total_ms) *total_ms = tot;
   if (launches) *launches = static_cast<int64_t>(ctx->ev_used / 2);
   return FABLE_OK;
+}
+
+int fable_ctx_measure_fp64_peak(fable_ctx* ctx, double* dmma_tflops) {
+  if (!ctx || !dmma_tflops) return FABLE_ERR_INVALID;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return fb_dmma_peak(ctx, dmma_tflops);
 }
 
 int fable_ctx_set_psi_ring(fable_ctx* ctx, int slots) {

@@ -142,11 +142,16 @@ int fb_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int6
             const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc);
 int fb_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alpha, const double* dA, int64_t lda,
             double* dC, int64_t ldc);
+int fb_dmma_peak(fable_ctx* ctx, double* tflops);     // measured DMMA.8x8x4 issue peak of this device
 // residual column sums of squares: d_resid[j] = sum_i (Y[i,j] - sum_l U[i,l] C[j,l])^2, l < k.
 int fb_gemm_resid(fable_ctx* ctx, int64_t n, int64_t p, int k, const double* dY, int64_t ldy,
                   const double* dU, int64_t ldu, const double* dC, int64_t ldc, double* d_resid);
 // eig.cu
-int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps);
+// eigenvalues at the noise floor (<= ~16 m eps lambda_1: exactly singular G) come back as 0 with their vectors replaced by
+// an orthonormal completion; *deflated (may be NULL) = their number
+int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps, int64_t* deflated = nullptr);
+// columns [done, total) of Q (rows x total, ld) <- unit vectors orthogonal to columns [0, done) and to each other
+int fb_complete_orthonormal(fable_ctx* ctx, double* dQ, int64_t rows, int64_t ld, int64_t done, int64_t total);
 // svd.cu: thin SVD of the device matrix dY (n x p, ld n): dU n x r, dd r, dV p x r (dense lds).
 int fb_svd(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, double* dU, double* dd, double* dV);
 // column-wise pieces of the back-multiplication, for the column-sharded SVD: sums of squares, (max |x|, first row

@@ -35,7 +35,7 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c) {
 }
 
 __global__ void __launch_bounds__(JT)
-k_jacobi_round(double* __restrict__ A, int64_t m, int64_t ld, int round, int N, double tol, int* __restrict__ nrot) {
+k_jacobi_round(double* __restrict__ A, int64_t m, int64_t ld, int round, int N, double tol, double floor2, int* __restrict__ nrot) {
   const int i = blockIdx.x;
   int ca, cb;
   if (i == 0) { ca = N - 1; cb = round; }
@@ -50,7 +50,9 @@ k_jacobi_round(double* __restrict__ A, int64_t m, int64_t ld, int round, int N, 
     alpha = fma(xv, xv, alpha); beta = fma(yv, yv, beta); gamma = fma(xv, yv, gamma);
   }
   block_sum3(alpha, beta, gamma);
-  if (gamma == 0.0 || fabs(gamma) <= tol * sqrt(alpha) * sqrt(beta)) return;
+  // a column below the noise floor of the Gram matrix (numerically zero: singular G, e.g. column-centred Y) is left alone:
+  // its inner products are rounding noise, so the relative test would never settle
+  if (gamma == 0.0 || fabs(gamma) <= tol * sqrt(alpha) * sqrt(beta) || alpha <= floor2 || beta <= floor2) return;
   if (threadIdx.x == 0) atomicAdd(nrot, 1);
   const double zeta = (beta - alpha) / (2.0 * gamma);
   const double tt = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -182,7 +184,7 @@ k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int6
 // 14-15 outer sweeps, 40 % less time (measured at n = 500, 1000, 2000).
 constexpr int EIGT = 1024;
 __global__ void __launch_bounds__(EIGT)
-k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, int cross_only, double* __restrict__ Rout,
+k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2, int inner, int cross_only, double* __restrict__ Rout,
          int* __restrict__ nrot) {
   constexpr int S = PW + 1;
   extern __shared__ double dsm[];
@@ -229,7 +231,7 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, in
     const int a = idx & (PW - 1), b = idx >> 6;
     if (a < b) {
       const double h = H[a * S + b];
-      if (h != 0.0 && h * h > tol2 * H[a * S + a] * H[b * S + b]) need = 1;
+      if (h != 0.0 && h * h > tol2 * H[a * S + a] * H[b * S + b] && H[a * S + a] > floor2 && H[b * S + b] > floor2) need = 1;
     }
   }
   __syncthreads();
@@ -245,7 +247,7 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, in
     int cur = 0, nxt = 2 * PW * S;                       // offsets of H_cur / H_next in dsm (H at 0, second H behind R)
     auto rotation = [&](double hpq, double hpp, double hqq, double2& cs_) {
       cs_ = make_double2(1.0, 0.0);
-      if (hpq != 0.0 && hpq * hpq > tol2 * hpp * hqq) {
+      if (hpq != 0.0 && hpq * hpq > tol2 * hpp * hqq && hpp > floor2 && hqq > floor2) {
         const double d = hqq - hpp, h2 = 2.0 * hpq, r2 = fma(d, d, h2 * h2);
         const double tt = h2 * (1.0 / (d + copysign(r2 * rsqrt(r2), d)));
         const double c_ = rsqrt(fma(tt, tt, 1.0));
@@ -349,7 +351,7 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, int inner, in
           const int p = a < b ? a : b, q = a < b ? b : a;
           const double hpq = H[p * S + q], hpp = H[p * S + p], hqq = H[q * S + q];
           double c_ = 1.0, s_ = 0.0;
-          if (hpq != 0.0 && hpq * hpq > tol2 * hpp * hqq) {
+          if (hpq != 0.0 && hpq * hpq > tol2 * hpp * hqq && hpp > floor2 && hqq > floor2) {
             const double d = hqq - hpp, h2 = 2.0 * hpq, r2 = fma(d, d, h2 * h2);
             const double tt = h2 * (1.0 / (d + copysign(r2 * rsqrt(r2), d)));      // rsqrt, reciprocal, rsqrt: no general division
             c_ = rsqrt(fma(tt, tt, 1.0)); s_ = c_ * tt;
@@ -450,16 +452,102 @@ __global__ void __launch_bounds__(256) k_bj_copy_in(const double* __restrict__ G
   W[i + ld * j] = (i < m && j < m) ? G[i + m * j] : 0.0;
 }
 
+// ---- completion of an orthonormal basis (deflated eigen / singular vectors) ---------------------------------
+// lev[r] = sum_{i < done} Q[r, i]^2: e_r keeps 1 - lev[r] of its length after projection on the complement
+__global__ void __launch_bounds__(256) k_leverage(const double* __restrict__ Q, int64_t rows, int64_t ld, int64_t done, double* __restrict__ lev) {
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  double a = 0.0;
+  for (int64_t i = 0; i < done; ++i) { const double x = Q[r + ld * i]; a = fma(x, x, a); }
+  lev[r] = a;
+}
+__global__ void __launch_bounds__(256) k_unit_vector(double* __restrict__ v, int64_t rows, int64_t j) {
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (r < rows) v[r] = r == j ? 1.0 : 0.0;
+}
+// coef[i] = Q[:, i] . v   (one CTA per column)
+__global__ void __launch_bounds__(JT) k_proj_coef(const double* __restrict__ Q, int64_t rows, int64_t ld, const double* __restrict__ v,
+                                                  double* __restrict__ coef) {
+  const double* x = Q + ld * blockIdx.x;
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int64_t r = threadIdx.x; r < rows; r += JT) a = fma(x[r], v[r], a);
+  block_sum3(a, b, c);
+  if (threadIdx.x == 0) coef[blockIdx.x] = a;
+}
+// v -= Q[:, :done] coef
+__global__ void __launch_bounds__(256) k_proj_sub(const double* __restrict__ Q, int64_t rows, int64_t ld, int64_t done,
+                                                  const double* __restrict__ coef, double* __restrict__ v) {
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  double a = v[r];
+  for (int64_t i = 0; i < done; ++i) a = fma(-coef[i], Q[r + ld * i], a);
+  v[r] = a;
+}
+__global__ void __launch_bounds__(JT) k_unit_norm(double* __restrict__ v, int64_t rows) {
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int64_t r = threadIdx.x; r < rows; r += JT) a = fma(v[r], v[r], a);
+  block_sum3(a, b, c);
+  const double inv = a > 0.0 ? 1.0 / sqrt(a) : 0.0;
+  for (int64_t r = threadIdx.x; r < rows; r += JT) v[r] *= inv;
+}
+
 }  // namespace
 
-int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps_out) {
+// Columns [done, total) of Q (rows x total, ld) are replaced by unit vectors orthogonal to columns [0, done) and to each
+// other: column c starts from the coordinate vector that is furthest from the span of the columns before it and is
+// projected three times (classical Gram-Schmidt with re-orthogonalisation).  Used for the singular / eigen vectors of
+// numerically zero values, which the Gram route leaves undetermined (LAPACK returns an orthonormal basis there).
+int fb_complete_orthonormal(fable_ctx* ctx, double* dQ, int64_t rows, int64_t ld, int64_t done, int64_t total) {
+  if (done >= total) return FABLE_OK;
+  FB_REQUIRE(ctx, total <= rows, "orthonormal completion: more columns than rows");
+  DevBuf lev, coef;
+  FB_CUDA(ctx, lev.alloc(static_cast<size_t>(rows) * sizeof(double)));
+  FB_CUDA(ctx, coef.alloc(static_cast<size_t>(total) * sizeof(double)));
+  std::vector<double> h(rows);
+  const unsigned gr = static_cast<unsigned>(ceil_div(rows, 256));
+  for (int64_t c = done; c < total; ++c) {
+    double* v = dQ + ld * c;
+    k_leverage<<<gr, 256, 0, ctx->stream>>>(dQ, rows, ld, c, lev.d());
+    FB_LAUNCHED(ctx);
+    FB_CUDA(ctx, cudaMemcpyAsync(h.data(), lev.d(), rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t j = 0;
+    for (int64_t r = 1; r < rows; ++r) if (h[r] < h[j]) j = r;
+    k_unit_vector<<<gr, 256, 0, ctx->stream>>>(v, rows, j);
+    FB_LAUNCHED(ctx);
+    if (c > 0)
+      for (int pass = 0; pass < 3; ++pass) {
+        k_proj_coef<<<static_cast<unsigned>(c), JT, 0, ctx->stream>>>(dQ, rows, ld, v, coef.d());
+        k_proj_sub<<<gr, 256, 0, ctx->stream>>>(dQ, rows, ld, c, coef.d(), v);
+        k_unit_norm<<<1, JT, 0, ctx->stream>>>(v, rows);
+        ctx->launches += 3;
+      }
+    FB_CUDA(ctx, cudaGetLastError());
+  }
+  return FABLE_OK;
+}
+
+int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int* sweeps_out, int64_t* deflated_out) {
   FB_REQUIRE(ctx, m > 0 && m < (1 << 30), "syevj: bad dimension");
   const int N = static_cast<int>(m + (m & 1));
-  const double tol = std::sqrt(static_cast<double>(m)) * 2.220446049250313e-16 * (getenv("FABLE_B200_BJ_TOL") ? atof(getenv("FABLE_B200_BJ_TOL")) : 1.0);
+  const double eps = 2.220446049250313e-16;
+  const double tol = std::sqrt(static_cast<double>(m)) * eps * (getenv("FABLE_B200_BJ_TOL") ? atof(getenv("FABLE_B200_BJ_TOL")) : 1.0);
   DevBuf cnt, nrm, perm;
   FB_CUDA(ctx, cnt.alloc(sizeof(int)));
   FB_CUDA(ctx, nrm.alloc(m * sizeof(double)));
   FB_CUDA(ctx, perm.alloc(m * sizeof(int)));
+  std::vector<double> h(m);
+  // Noise floor: the working columns converge to lambda_i q_i, so a column whose norm is below ~ m eps lambda_1 belongs
+  // to a numerically zero eigenvalue (the Gram matrix of column-centred data is exactly singular, reference cpp:296).  Such
+  // columns are not rotated any more (their inner products are rounding noise) and their eigenpairs are deflated below.
+  // lambda_1 is bounded by the largest column norm of G from below up to sqrt(m) and from above by it: use that norm.
+  k_colnorm<<<static_cast<unsigned>(m), JT, 0, ctx->stream>>>(dG, m, m, nrm.d());
+  FB_LAUNCHED(ctx);
+  FB_CUDA(ctx, cudaMemcpyAsync(h.data(), nrm.d(), m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  double gmax = 0.0;
+  for (double x : h) gmax = x > gmax ? x : gmax;
+  const double floor1 = 4.0 * static_cast<double>(m) * eps * gmax, floor2 = floor1 * floor1;
   int sweeps = 0;
   const int max_sweeps = 40;
   const int64_t kBlockMin = getenv("FABLE_B200_BJ_MIN") ? atoll(getenv("FABLE_B200_BJ_MIN")) : 16;      // block path from m = 17 on: 2x the scalar rounds even at m = 64 (measured)
@@ -498,7 +586,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
       for (int r = 0; r < NB - 1; ++r) {
         k_bj_gram<<<dim3(npairs, static_cast<unsigned>(nsplit)), 128, 0, ctx->stream>>>(Wbuf.d(), ld, rows_per_split, ld, r, NB,
                                                                                          Hpart.d());
-        k_bj_eig<<<npairs, EIGT, eig_smem, ctx->stream>>>(Hpart.d(), static_cast<int>(nsplit), tol, inner, (cross && r > 0) ? 1 : 0, Rall.d(),
+        k_bj_eig<<<npairs, EIGT, eig_smem, ctx->stream>>>(Hpart.d(), static_cast<int>(nsplit), tol, floor2, inner, (cross && r > 0) ? 1 : 0, Rall.d(),
                                                          static_cast<int*>(cnt.ptr));
         k_bj_apply<<<dim3(npairs, static_cast<unsigned>(ceil_div(ld, 128))), 256, apply_smem, ctx->stream>>>(Wbuf.d(), ld, r, NB,
                                                                                                              Rall.d());
@@ -516,7 +604,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     for (; sweeps < max_sweeps; ++sweeps) {
       FB_CUDA(ctx, cudaMemsetAsync(cnt.ptr, 0, sizeof(int), ctx->stream));
       for (int r = 0; r < N - 1; ++r) {
-        k_jacobi_round<<<N / 2, JT, 0, ctx->stream>>>(dG, m, m, r, N, tol, static_cast<int*>(cnt.ptr));
+        k_jacobi_round<<<N / 2, JT, 0, ctx->stream>>>(dG, m, m, r, N, tol, floor2, static_cast<int*>(cnt.ptr));
         ++ctx->launches;
       }
       FB_CUDA(ctx, cudaGetLastError());
@@ -529,7 +617,6 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
   }
   k_colnorm<<<static_cast<unsigned>(m), JT, 0, ctx->stream>>>(Acols, m, lda, nrm.d());
   FB_LAUNCHED(ctx);
-  std::vector<double> h(m);
   FB_CUDA(ctx, cudaMemcpyAsync(h.data(), nrm.d(), m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   std::vector<int> order(m);
@@ -539,7 +626,17 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
   k_gather_normalise<<<static_cast<unsigned>(m), JT, 0, ctx->stream>>>(Acols, m, lda, static_cast<const int*>(perm.ptr),
                                                                       nrm.d(), dQ, dW);
   FB_LAUNCHED(ctx);
+  // Deflation: eigenvalues at the noise floor are set to exactly 0 and their vectors -- normalised rounding noise at this
+  // point -- are replaced by an orthonormal completion of the others.
+  int64_t good = m;
+  const double top = h[order[0]];
+  while (good > 0 && h[order[good - 1]] <= 4.0 * floor1 + 16.0 * static_cast<double>(m) * eps * top) --good;
+  if (good < m) {
+    FB_CUDA(ctx, cudaMemsetAsync(dW + good, 0, static_cast<size_t>(m - good) * sizeof(double), ctx->stream));
+    FB_TRY(fb_complete_orthonormal(ctx, dQ, m, m, good, m));
+  }
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (sweeps_out) *sweeps_out = sweeps;
+  if (deflated_out) *deflated_out = m - good;
   return FABLE_OK;
 }

@@ -484,6 +484,48 @@ int fb_syrk(fable_ctx* ctx, int a_kfast, int64_t M, int64_t K, double alpha, con
   return fb_mirror_upper(ctx, dC, M);
 }
 
+// Register-resident issue peak of the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA.8x8x4): the denominator of the Gram
+// step's roofline, measured on the device the bench runs on (MEASURED_PEAKS.json has no FP64 entry).  8 independent
+// accumulator pairs per warp, 8 warps per CTA, 8 CTAs per SM; 512 flops per warp-level MMA.
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, double a0, double b0) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+  const double a = a0 + threadIdx.x * 1e-9, b = b0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma(c[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int fb_dmma_peak(fable_ctx* ctx, double* tflops) {
+  const int ctas = ctx->sms * 8, iters = 4096;
+  DevBuf out;
+  FB_CUDA(ctx, out.alloc(static_cast<size_t>(ctas) * 256 * sizeof(double)));
+  cudaEvent_t e0, e1;
+  FB_CUDA(ctx, cudaEventCreate(&e0));
+  FB_CUDA(ctx, cudaEventCreate(&e1));
+  float best = 0.f;
+  for (int rep = 0; rep < 6; ++rep) {                 // first launches warm the clocks up; best of the rest
+    cudaEventRecord(e0, ctx->stream);
+    k_dmma_peak<<<ctas, 256, 0, ctx->stream>>>(out.d(), iters, 1.0, 1e-3);
+    cudaEventRecord(e1, ctx->stream);
+    ++ctx->launches;
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); FB_CUDA(ctx, e); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep >= 2 && (best == 0.f || ms < best)) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = static_cast<double>(ctas) * 8 /*warps*/ * iters * 8 /*mma*/ * 512.0 / (best * 1e-3) / 1e12;
+  return FABLE_OK;
+}
+
 int fb_gemm(fable_ctx* ctx, int a_kfast, int b_kfast, int64_t M, int64_t N, int64_t K, double alpha,
             const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc) {
   FB_REQUIRE(ctx, M > 0 && N > 0 && K > 0, "gemm: empty problem");

@@ -7,6 +7,10 @@
 // d is taken from the back-multiplied column norms (a Rayleigh quotient: second-order accurate
 // in the eigenvector error) rather than sqrt(lambda), and the back-multiplied side has exactly
 // unit columns.  Sign convention: the largest-|entry| of each V column is positive.
+// Rank-deficient Y (the reference expects column-centred data, cpp:296, which makes one singular value exactly 0
+// when n <= p): the eigensolver deflates Gram eigenvalues at its noise floor (sigma <~ 4 sqrt(m eps) sigma_1 cannot be
+// resolved through the Gram matrix in any case) -- those triplets get d = 0 exactly and singular vectors that complete
+// the others to orthonormal bases on both sides, as LAPACK's do.
 #include "common.cuh"
 
 namespace {
@@ -136,18 +140,27 @@ int fb_svd(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, double* dU, d
   FB_CUDA(ctx, G.alloc(static_cast<size_t>(r) * r * sizeof(double)));
   FB_CUDA(ctx, W.alloc(static_cast<size_t>(r) * sizeof(double)));
   int sweeps = 0;
+  int64_t defl = 0;
   if (n <= p) {
     FB_TRY(fb_syrk(ctx, 0, n, p, 1.0, dY, n, G.d(), n));                        // Y Y' (upper tiles + mirror)
-    FB_TRY(fb_syevj(ctx, G.d(), n, W.d(), dU, &sweeps));                        // U (n x n)
+    FB_TRY(fb_syevj(ctx, G.d(), n, W.d(), dU, &sweeps, &defl));                 // U (n x n)
     FB_TRY(fb_gemm(ctx, 1, 1, p, r, n, 1.0, dY, n, dU, n, dV, p));             // T = Y'U
     k_norm_scale<<<static_cast<unsigned>(r), ST, 0, ctx->stream>>>(dV, p, p, dd);
     FB_LAUNCHED(ctx);
+    if (defl > 0) {                        // Y'u = 0 for the deflated u: d = 0, V completed
+      FB_CUDA(ctx, cudaMemsetAsync(dd + (r - defl), 0, static_cast<size_t>(defl) * sizeof(double), ctx->stream));
+      FB_TRY(fb_complete_orthonormal(ctx, dV, p, p, r - defl, r));
+    }
   } else {
     FB_TRY(fb_syrk(ctx, 1, p, n, 1.0, dY, n, G.d(), p));                        // Y'Y (upper tiles + mirror)
-    FB_TRY(fb_syevj(ctx, G.d(), p, W.d(), dV, &sweeps));                        // V (p x p)
+    FB_TRY(fb_syevj(ctx, G.d(), p, W.d(), dV, &sweeps, &defl));                 // V (p x p)
     FB_TRY(fb_gemm(ctx, 0, 1, n, r, p, 1.0, dY, n, dV, p, dU, n));             // T = Y V
     k_norm_scale<<<static_cast<unsigned>(r), ST, 0, ctx->stream>>>(dU, n, n, dd);
     FB_LAUNCHED(ctx);
+    if (defl > 0) {
+      FB_CUDA(ctx, cudaMemsetAsync(dd + (r - defl), 0, static_cast<size_t>(defl) * sizeof(double), ctx->stream));
+      FB_TRY(fb_complete_orthonormal(ctx, dU, n, n, r - defl, r));
+    }
   }
   k_sign_canon<<<static_cast<unsigned>(r), ST, 0, ctx->stream>>>(dU, n, dV, p);
   FB_LAUNCHED(ctx);

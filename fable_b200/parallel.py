@@ -108,6 +108,49 @@ def allreduce_posterior_accumulators(post, device, group=None):
     reduce_posterior_accumulators(post, device, dst=None, group=group)
 
 
+def distributed_sampler(Y, gamma0, delta0sq, MC, U_Y, V_Y, svalsY, kEst, varInflation, ctx, device, m0=0, out=None,
+                        dst=0, group=None, psi_moments=True):
+    """CPPFABLESampler (cpp:532-629) on the draw partition, through the C-ABI with host buffers: every rank calls this
+    with the same inputs.  Rank g uploads them, draws its contiguous share [lo, hi) of the MC axis (its rows of
+    LambdaSamples / SigmaSqSamples land in its own host arrays; the union over ranks is what one GPU would draw),
+    the sum / sumsq accumulators are summed ON THE DEVICE (one NCCL reduce of the compact tiles) and only rank `dst`
+    (None: every rank) downloads the dense p x p PsiSum / PsiSumSq.  `out` may supply column-major host arrays
+    ("LambdaSamples" (hi-lo) x k p, "SigmaSqSamples" (hi-lo) x p, "PsiSum" / "PsiSumSq" p x p)."""
+    import torch.distributed as dist
+    from . import api
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    lo, hi = draw_range(MC, rank, world)
+    out = out or {}
+    post = api.Posterior(Y, gamma0, delta0sq, U_Y, V_Y, svalsY, kEst, varInflation, ctx=ctx)
+    try:
+        p, k = post.p, post.k
+        L = out.get("LambdaSamples"); S = out.get("SigmaSqSamples")
+        if L is None:
+            L = np.empty((hi - lo, k * p), order="F")
+        if S is None:
+            S = np.empty((hi - lo, p), order="F")
+        if psi_moments:
+            post.accum_reset()
+        if hi > lo:
+            post.sample_range(m0 + lo, hi - lo, L, S, psi_pass=psi_moments)
+        res = {"LambdaSamples": L, "SigmaSqSamples": S, "draw_range": (lo, hi), "EstimatedRank": k,
+               "VarianceInflation": float(varInflation)}
+        if psi_moments:
+            reduce_posterior_accumulators(post, device, dst=dst, group=group)
+            if dst is None or rank == dst:
+                s1 = out.get("PsiSum"); s2 = out.get("PsiSumSq")
+                if s1 is None:
+                    s1 = np.empty((p, p), order="F")
+                if s2 is None:
+                    s2 = np.empty((p, p), order="F")
+                res["PsiSum"], res["PsiSumSq"] = post.accum_fetch(out=(s1, s2))
+        return res
+    finally:
+        post.close()
+
+
 def gather_sample_rows(local, MC, rank, world, group=None):
     """Assemble the MC x q sample matrix on every rank from disjoint contiguous row ranges
     (host tensors; used by tests and small runs -- large runs keep the ranges where they are)."""

@@ -84,6 +84,9 @@ void* fable_ctx_stream(fable_ctx* ctx);
  * time in milliseconds and the number of launches recorded since it was enabled. */
 int fable_ctx_kernel_timing(fable_ctx* ctx, int enable);
 int fable_ctx_kernel_time(fable_ctx* ctx, double* total_ms, int64_t* launches);
+/* Diagnostics: register-resident issue rate of the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA.8x8x4) on this
+ * device, in TFLOP/s -- the denominator bench.py divides the Gram step by (no reference counterpart). */
+int fable_ctx_measure_fp64_peak(fable_ctx* ctx, double* dmma_tflops);
 /* slots > 0: fable_sampler's Psi pass also MATERIALISES every draw Psi_m (dense p x p) into a device
  * ring of `slots` matrices owned by the context (batches of min(slots, 32) draws, draw b of a batch in slot b), next to the sum / sumsq
  * accumulators -- the block-wise covariance formation named by the north star, left resident for

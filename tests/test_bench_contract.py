@@ -32,5 +32,14 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 
+def test_reference_arm_uses_all_cores_under_torchrun():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not inherit that (round 1's
+    multi-GPU reference lines ran on one core)."""
+    d = json.loads(_run({"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}).strip())
+    want = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == want
+    assert "draws sharded over ranks" in d["config"]["workload"]
+
+
 def test_reference_arm_other_ranks_are_silent():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}).strip() == ""

@@ -698,6 +698,66 @@ def test_c2_full_size_properties(ctx):
     post.close()
 
 
+# ---- full size against the oracle (BASELINE.json configs[2] and configs[3] on one GPU) -----------------
+@pytest.mark.parametrize("n,p,k,maxProp", [(1000, 20000, 10, 0.5), (500, 50000, 20, 0.5)], ids=["c3", "c4"])
+def test_full_size_against_oracle(ctx, n, p, k, maxProp):
+    """The whole path at the size the metric is quoted on (c3) and at the high-dimensional size (c4), against the CPU
+    oracle on the same inputs: singular values and kMax (LAPACK dgesdd), kEst (bisection replayed by the oracle), the
+    plug-in variances / G0 / tauSq, and -- with injected draws -- sampled entries of every materialised draw (dense
+    p x p) and of the sum / sumsq accumulators."""
+    import torch
+    Y = synth.factor_data(n, p, k, rep=0)
+    u, d, v = orc.svd_thin(Y)
+    s = fb.svd(Y, ctx=ctx)
+    assert relerr_vec(s["d"], d) < TOL
+    kMax = orc.kmax_rule(d, maxProp)
+    assert fb.kmax_rule(s["d"], maxProp) == kMax
+    kref = orc.rank_estimator(Y, u, v, d, kMax)
+    assert kref == k
+    assert fb.CPPRankEstimator(Y, u, v, d, kMax, ctx=ctx) == kref                       # the oracle's SVD as shared input
+    assert fb.CPPRankEstimator(Y, s["u"], s["v"], s["d"], kMax, ctx=ctx) == kref        # the library's own SVD
+    del s
+    hg = fb.FABLEHyperParameters(Y, u, v, d, kref, ctx=ctx, want_G=False)
+    hr = orc.hyper_parameters(Y, u, v, d, kref, want_G=False)
+    assert relerr_vec(hg["SigmaSqEstimate"], hr["SigmaSqEstimate"]) < TOL and relerr_mat(hg["G0"], hr["G0"]) < TOL
+    assert abs(hg["tauSqEstimate"] / hr["tauSqEstimate"] - 1) < TOL
+    vi = fb.var_inflation(hg["SigmaSqEstimate"], hg["G0"], "script", ctx=ctx)
+    post = fb.Posterior(Y, 1.0, 1.0, u, v, d, kref, vi, ctx=ctx)
+    st = orc._shrunk_stats(Y, u, v, d, kref, 1.0, 1.0)
+    got = post.get()
+    assert relerr_mat(got["G0"], st["G0"]) < TOL and relerr_vec(got["gnd"], st["gnd"]) < TOL
+    B = 3 if p <= 20000 else 2
+    gam, z = synth.injected_draws(B, p, kref, 0.5 * (1.0 + n), seed=p)
+    o = orc.sampler(Y, 1.0, 1.0, B, u, v, d, kref, vi, gam, z)
+    dg = torch.from_numpy(np.ascontiguousarray(gam)).cuda(); dz = torch.from_numpy(np.ascontiguousarray(z)).cuda()
+    psi = torch.empty((B, p, p), dtype=torch.float64, device="cuda")
+    post.draw_batch(0, B, dev_psi=psi.data_ptr(), psi_slots=B, accumulate=True, dev_gam=dg.data_ptr(), dev_z=dz.data_ptr())
+    ctx.synchronize()
+    rng = np.random.default_rng(p)
+    idx = np.unique(np.concatenate([[0, 1, 15, 16, 63, 64, 65, 1023, 1024, p - 65, p - 64, p - 17, p - 16, p - 1], rng.integers(0, p, 500)]))
+    ti = torch.from_numpy(idx).cuda()
+    want1 = np.zeros((idx.size, idx.size)); want2 = np.zeros_like(want1)
+    for m in range(B):
+        Lm = o["LambdaSamples"][m].reshape(p, kref)[idx]
+        want = orc.psi_draw(Lm.reshape(-1), o["SigmaSqSamples"][m][idx], kref)          # the entries' own rows suffice
+        want1 += want; want2 += want * want
+        sub = psi[m].index_select(0, ti).index_select(1, ti).cpu().numpy()
+        assert relerr_mat(sub.T, want) < TOL and np.array_equal(sub, sub.T)
+    del psi
+    torch.cuda.empty_cache()
+    a_sum, a_sq, cnt = post.accum_dev()
+    dense = torch.empty((p, p), dtype=torch.float64, device="cuda")
+    for ptr, want in ((a_sum, want1), (a_sq, want2)):
+        post.tiles_to_dense(ptr, False, 0, p, dense.data_ptr())
+        ctx.synchronize()
+        sub = dense.index_select(0, ti).index_select(1, ti).cpu().numpy()
+        assert relerr_mat(sub.T, want) < TOL and np.array_equal(sub, sub.T)
+    del dense
+    post.close()
+    ctx.trim_cache()
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("threads", [None, "3", "0"])
 def test_pipelined_host_copies_round_trip(ctx, threads, monkeypatch):
     """Pageable inputs / outputs above 64 MB cross PCIe in staged chunks gathered and scattered by host threads
