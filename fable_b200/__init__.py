@@ -7,7 +7,7 @@ parity tests read like calls into the R package.  There is no CPU fallback: impo
 anywhere, but every call raises `FableError` when the library or a B200 is missing.
 """
 from .api import (  # noqa: F401
-    FableError, Context, Posterior,
+    FableError, Context, MultiContext, Posterior,
     FABLEPosteriorMean, FABLEPosteriorSampler,
     CPPRankEstimator, CPPCriterionFunction, CPPBisectionRecursion, CPPLogLikelihoodEval,
     FABLEHyperParameters, CPPcov_correct_matrix, cov_correct_matrix, var_inflation,
@@ -18,7 +18,7 @@ from .api import (  # noqa: F401
 from . import synth  # noqa: F401
 
 __all__ = [
-    "FableError", "Context", "Posterior", "FABLEPosteriorMean", "FABLEPosteriorSampler",
+    "FableError", "Context", "MultiContext", "Posterior", "FABLEPosteriorMean", "FABLEPosteriorSampler",
     "CPPRankEstimator", "CPPCriterionFunction", "CPPBisectionRecursion", "CPPLogLikelihoodEval", "FABLEHyperParameters",
     "CPPcov_correct_matrix", "cov_correct_matrix", "var_inflation", "CPPFABLEPostMean",
     "CPPFABLESampler", "CPPsvd", "svd", "kmax_rule", "CPPCCFABLEPostProcessing",

@@ -54,6 +54,12 @@ def _load():
     lib.fable_ctx_destroy.argtypes = [C.c_void_p]
     lib.fable_posterior_destroy.restype = None
     lib.fable_posterior_destroy.argtypes = [C.c_void_p]
+    lib.fable_multi_destroy.restype = None
+    lib.fable_multi_destroy.argtypes = [C.c_void_p]
+    lib.fable_multi_last_error.restype = C.c_char_p
+    lib.fable_multi_last_error.argtypes = [C.c_void_p]
+    lib.fable_multi_ctx.restype = C.c_void_p
+    lib.fable_multi_ctx.argtypes = [C.c_void_p, C.c_int]
     _lib = lib
     return lib
 
@@ -73,6 +79,7 @@ def _ptr(a):
 
 
 _ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int64)
+_ALLREDUCE_DEV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 class Context:
@@ -118,15 +125,18 @@ class Context:
 
     shard = None
 
-    def set_column_shard(self, p_total, col_offset=0, rank=0, world=1, allreduce=None):
+    def set_column_shard(self, p_total, col_offset=0, rank=0, world=1, allreduce=None, allreduce_dev=None):
         """Column-sharded estimation (fable_ctx_set_column_shard): this context holds columns
         [col_offset, col_offset + p_local) of a p_total-column problem; `allreduce(a)` must sum the float64 numpy
-        array `a` over all ranks in place, with identical bits on every rank.  p_total = 0 switches it off."""
+        array `a` over all ranks in place, with identical bits on every rank.  Optional `allreduce_dev(ptr, count,
+        stream)`: the same for `count` doubles at a DEVICE address, ordered on the given CUDA stream (the n x n Gram
+        then never leaves HBM).  p_total = 0 switches it off."""
         lib = _load()
         if not p_total:
             self.check(lib.fable_ctx_set_column_shard(self._h, _i64(0), _i64(0), C.c_int(0), C.c_int(1), None, None))
             self.shard = None
             self._shard_cb = None
+            self._shard_dev_cb = None
             return
 
         def _cb(_user, vals, count):
@@ -141,6 +151,19 @@ class Context:
         self.check(lib.fable_ctx_set_column_shard(self._h, _i64(p_total), _i64(col_offset), C.c_int(rank), C.c_int(world), cb, None))
         self._shard_cb = cb             # keep the trampoline alive as long as the context uses it
         self.shard = (int(p_total), int(col_offset), int(rank), int(world))
+        self._shard_dev_cb = None
+        if allreduce_dev is not None:
+            def _dcb(_user, ptr, count, stream):
+                try:
+                    allreduce_dev(int(ptr), int(count), int(stream or 0))
+                    return 0
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            dcb = _ALLREDUCE_DEV_FN(_dcb)
+            self.check(lib.fable_ctx_set_column_shard_dev(self._h, dcb, None))
+            self._shard_dev_cb = dcb
 
     def trim_cache(self):
         """Return the library's idle cached device blocks to the driver (they are reused across calls otherwise)."""
@@ -165,6 +188,43 @@ class Context:
     def set_psi_ring(self, slots):
         """slots > 0: the sampler's Psi pass also materialises every draw into a device ring."""
         self.check(_load().fable_ctx_set_psi_ring(self._h, C.c_int(int(slots))))
+
+
+class MultiContext:
+    """fable_multi: several devices of one box driven from this process (one context per device, peer access all
+    round).  Pass it as `ctx` to CPPFABLESampler: the draws are sharded over the devices and the accumulators are summed
+    over NVLink peer memory (fable_multi_sampler)."""
+
+    def __init__(self, devices, seed=12345):
+        lib = _load()
+        devs = list(range(devices)) if isinstance(devices, int) else [int(x) for x in devices]
+        arr = (C.c_int * len(devs))(*devs)
+        h = C.c_void_p()
+        rc = lib.fable_multi_create(C.c_int(len(devs)), arr, C.c_uint64(seed), C.byref(h))
+        if rc != 0:
+            raise FableError(rc, lib.fable_multi_last_error(None).decode())
+        self._h = h
+        self.devices = devs
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _load().fable_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise FableError(rc, _load().fable_multi_last_error(self._h).decode())
+
+    @property
+    def launches(self):
+        lib = _load()
+        return sum(int(lib.fable_ctx_launch_count(C.c_void_p(lib.fable_multi_ctx(self._h, g)))) for g in range(len(self.devices)))
 
 
 _default_ctx = None
@@ -208,8 +268,16 @@ def svd(Y, ctx=None):
 
 
 def CPPsvd(X, flag=4, ctx=None):
-    """CPPsvd (updated-FABLE-functions.cpp:40-74): list(U, d, V); `flag` selected a LAPACK driver
-    there and has no effect here (one algorithm)."""
+    """CPPsvd (updated-FABLE-functions.cpp:40-74): list(U, d, V).  flag 1 / 2: the full decomposition (arma::svd: U n x n,
+    V p x p); any other flag: the economy form (svd_econ).  The LAPACK driver `flag` also selected there ("std" /
+    "dc") has no counterpart: one algorithm."""
+    if int(flag) in (1, 2):
+        ctx = _ctx(ctx)
+        X = _F(X, "X")
+        n, p = X.shape
+        U = np.empty((n, n), order="F"); d = np.empty(min(n, p)); V = np.empty((p, p), order="F")
+        ctx.check(_load().fable_svd_full(ctx._h, _ptr(X), _i64(n), _i64(p), _ptr(U), _ptr(d), _ptr(V)))
+        return {"U": U, "d": d, "V": V}
     s = svd(X, ctx)
     return {"U": s["u"], "d": s["d"], "V": s["v"]}
 
@@ -382,7 +450,8 @@ def CPPFABLESampler(Y, gamma0, delta0sq, MC, U_Y, V_Y, svalsY, kEst, varInflatio
     G = _buf("G", (p, p), want_G)
     s1 = _buf("PsiSum", (p, p), psi_moments)
     s2 = _buf("PsiSumSq", (p, p), psi_moments)
-    ctx.check(_load().fable_sampler(ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq),
+    entry = _load().fable_multi_sampler if isinstance(ctx, MultiContext) else _load().fable_sampler
+    ctx.check(entry(ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq),
                                     _i64(MC), _ptr(U), _ptr(V), _ptr(d), _i64(r), C.c_int(k),
                                     C.c_double(varInflation), _ptr(g), _ptr(zz), _i64(m0), _ptr(L), _ptr(S),
                                     _ptr(pm), _ptr(pi), C.byref(tau), _ptr(G), _ptr(s1), _ptr(s2)))
@@ -684,23 +753,23 @@ def FABLEPosteriorSampler(Y, gamma0=1.0, delta0sq=1.0, maxProp=0.95, MC=1000, ct
             raise FableError(1, "MC must be >= 1")
         U = np.empty((n, r), order="F"); d = np.empty(r); V = np.empty((p, r), order="F")
         k = C.c_int(); kM = C.c_int(); htau = C.c_double(); vi = C.c_double(); tau = C.c_double()
-        hsig = np.empty(p); hG0 = np.empty((p, r), order="F")            # first kEst columns are written
+        hsig = np.empty(p)
         hG = np.empty((p, p), order="F") if want_G else None
         G = np.empty((p, p), order="F") if want_G else None
         # step 1 (wrapper:20-44): everything up to varInflation, row posterior left resident
         ph = C.c_void_p()
         ctx.check(_load().fable_wrapper_sampler_begin(
             ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq), C.c_double(maxProp),
-            _ptr(U), _ptr(d), _ptr(V), C.byref(kM), C.byref(k), _ptr(hsig), _ptr(hG0), C.byref(htau), _ptr(hG), C.byref(vi),
+            _ptr(U), _ptr(d), _ptr(V), C.byref(kM), C.byref(k), _ptr(hsig), None, C.byref(htau), _ptr(hG), C.byref(vi),
             C.byref(ph)))
         kEst = k.value; varInfl = vi.value
-        hyp = {"SigmaSqEstimate": hsig, "G": hG, "EstimatedRank": kEst,
-               "G0": np.asfortranarray(hG0.reshape(-1, order="F")[: p * kEst].reshape((p, kEst), order="F")),
-               "tauSqEstimate": htau.value}
         svdY = {"d": d, "u": U, "v": V}
-        # step 2 (wrapper:46-54): the caller sizes LambdaSamples now that k is known
+        # step 2 (wrapper:46-54): the caller sizes FABLEHyperParameters$G0 and LambdaSamples now that k is known
+        hG0 = np.empty((p, kEst), order="F")
         L = np.empty((MC, kEst * p), order="F"); S = np.empty((MC, p), order="F"); pm = np.empty(p); pi = np.empty(p)
         try:
+            ctx.check(_load().fable_posterior_hyper_G0(ph, _ptr(hG0)))
+            hyp = {"SigmaSqEstimate": hsig, "G": hG, "EstimatedRank": kEst, "G0": hG0, "tauSqEstimate": htau.value}
             ctx.check(_load().fable_posterior_sampler_outputs(ph, _i64(MC), _i64(0), None, None, _ptr(L), _ptr(S), _ptr(pm),
                                                               _ptr(pi), C.byref(tau), _ptr(G), None, None))
         finally:

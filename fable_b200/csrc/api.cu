@@ -24,7 +24,29 @@ struct MemCache {
   struct Block { int device; size_t bytes; };
   std::unordered_map<void*, Block> live;                         // handed out
   std::multimap<std::pair<int, size_t>, void*> idle;             // (device, rounded bytes) -> block
+  // A released block may still be in use by work queued on the library's streams.  Instead of draining the device at
+  // every release (a full barrier, also across the copy stream the release was meant to overlap), the release records
+  // one event per registered stream of the device and the NEXT owner waits for those -- by then they have normally
+  // completed long ago.
+  std::unordered_map<void*, std::vector<cudaEvent_t>> pending;   // idle block -> events to wait for before reuse
+  std::multimap<int, cudaStream_t> streams;                      // device -> streams of the live contexts
+  std::vector<cudaEvent_t> ev_pool;
   size_t idle_bytes = 0;
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return e;
+  }
+  void drop_pending(void* ptr, bool wait) {
+    auto it = pending.find(ptr);
+    if (it == pending.end()) return;
+    for (cudaEvent_t e : it->second) {
+      if (wait) cudaEventSynchronize(e);
+      ev_pool.push_back(e);
+    }
+    pending.erase(it);
+  }
   size_t cap() {
     static size_t c = [] {
       const char* e = getenv("FABLE_B200_CACHE_GB");
@@ -40,6 +62,7 @@ struct MemCache {
     for (auto it = idle.begin(); it != idle.end();) {
       if (device < 0 || it->first.first == device) {
         cudaSetDevice(it->first.first);
+        drop_pending(it->second, false);       // cudaFree waits for the device itself
         cudaFree(it->second);
         idle_bytes -= it->first.second;
         it = idle.erase(it);
@@ -66,6 +89,7 @@ cudaError_t fb_mem_acquire(void** ptr, size_t bytes) {
     *ptr = it->second;
     m.idle.erase(it);
     m.idle_bytes -= rb;
+    m.drop_pending(*ptr, true);                // whatever the previous owner had queued on the block has finished
   } else {
     e = cudaMalloc(ptr, rb);
     if (e == cudaErrorMemoryAllocation) {      // the cache may be what is holding the memory: flush and retry once
@@ -87,17 +111,27 @@ void fb_mem_release(void* ptr) {
   if (it == m.live.end()) { cudaFree(ptr); return; }
   const MemCache::Block b = it->second;
   m.live.erase(it);
-  // like cudaFree, a release waits for the device: the next owner may use the block on another stream
   int cur = 0;
   cudaGetDevice(&cur);
   if (cur != b.device) cudaSetDevice(b.device);
-  cudaDeviceSynchronize();
   if (b.bytes > m.cap()) {
-    cudaFree(ptr);
+    cudaFree(ptr);                             // (waits for the device)
   } else {
+    // the next owner may use the block on another stream: it waits for these events, not the releaser for the device
+    std::vector<cudaEvent_t> evs;
+    bool ok = true;
+    auto range = m.streams.equal_range(b.device);
+    for (auto st = range.first; st != range.second && ok; ++st) {
+      cudaEvent_t e = m.get_event();
+      if (!e || cudaEventRecord(e, st->second) != cudaSuccess) { (void)cudaGetLastError(); if (e) m.ev_pool.push_back(e); ok = false; break; }
+      evs.push_back(e);
+    }
+    if (!ok) { for (cudaEvent_t e : evs) m.ev_pool.push_back(e); evs.clear(); cudaDeviceSynchronize(); }
+    if (!evs.empty()) m.pending[ptr] = std::move(evs);
     while (m.idle_bytes + b.bytes > m.cap() && !m.idle.empty()) {      // make room: drop the largest idle blocks first
       auto big = std::prev(m.idle.end());
       cudaSetDevice(big->first.first);
+      m.drop_pending(big->second, false);
       cudaFree(big->second);
       m.idle_bytes -= big->first.second;
       m.idle.erase(big);
@@ -113,6 +147,15 @@ void fb_mem_trim(int device) {
   MemCache& m = mem_cache();
   std::lock_guard<std::mutex> lk(m.mu);
   m.trim_locked(device);
+}
+
+void fb_mem_register_stream(int device, cudaStream_t s, bool add) {
+  MemCache& m = mem_cache();
+  std::lock_guard<std::mutex> lk(m.mu);
+  if (add) { m.streams.insert({device, s}); return; }
+  auto range = m.streams.equal_range(device);
+  for (auto it = range.first; it != range.second; ++it)
+    if (it->second == s) { m.streams.erase(it); break; }
 }
 
 namespace {
@@ -135,6 +178,23 @@ inline int64_t glob_p(const fable_ctx* ctx, int64_t p_local) { return shard_on(c
 int shard_sum(fable_ctx* ctx, double* vals, int64_t count) {
   if (!shard_on(ctx)) return FABLE_OK;
   if (ctx->shard_fn(ctx->shard_user, vals, count) != 0) return ctx->fail(FABLE_ERR_INVALID, "column shard: the all-reduce callback failed");
+  return FABLE_OK;
+}
+// sum of `count` DEVICE doubles over the ranks, in place: through the device-pointer callback when the caller gave one
+// (NCCL on the context's stream: the n x n Gram never leaves HBM), else bounced through the host callback
+int shard_sum_dev(fable_ctx* ctx, double* dptr, int64_t count) {
+  if (!shard_on(ctx)) return FABLE_OK;
+  if (ctx->shard_dev_fn) {
+    if (ctx->shard_dev_fn(ctx->shard_dev_user, dptr, count, static_cast<void*>(ctx->stream)) != 0)
+      return ctx->fail(FABLE_ERR_INVALID, "column shard: the device all-reduce callback failed");
+    return FABLE_OK;
+  }
+  std::vector<double> h(static_cast<size_t>(count));
+  FB_CUDA(ctx, cudaMemcpyAsync(h.data(), dptr, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FB_TRY(shard_sum(ctx, h.data(), count));
+  FB_CUDA(ctx, cudaMemcpyAsync(dptr, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // h goes out of scope
   return FABLE_OK;
 }
 #define FB_NO_SHARD(ctx, what)                                                                                          \
@@ -435,6 +495,7 @@ struct fable_posterior {
   int Bcap = 0;
   DevBuf acc_sum, acc_sq;       // compact upper tiles of the slice [tile_begin, tile_end) (tiles.cuh): acc_tiles x 4096 doubles
   int64_t acc_tiles = 0;
+  DevBuf hyp_G0;                // unshrunk G0 of FABLEHyperParameters (cpp:390), kept by fable_wrapper_sampler_begin
   DevBuf cc_gdiag;              // entry-wise coverage correction (f3): diag(G0 G0'); NULL = off
   bool cc = false;
   int64_t tile_begin = 0, tile_end = 0;   // tile_end == 0: every tile
@@ -479,11 +540,7 @@ static int svd_sharded(fable_ctx* ctx, const double* dY, int64_t n, int64_t p_lo
   FB_CUDA(ctx, W.alloc(static_cast<size_t>(n) * sizeof(double)));
   FB_CUDA(ctx, tmp.alloc(static_cast<size_t>(3) * r * sizeof(double)));
   FB_TRY(fb_syrk(ctx, 0, n, p_loc, 1.0, dY, n, G.d(), n));                          // local Y Y'
-  std::vector<double> h(static_cast<size_t>(n) * n);
-  FB_CUDA(ctx, cudaMemcpyAsync(h.data(), G.d(), h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  FB_TRY(shard_sum(ctx, h.data(), static_cast<int64_t>(h.size())));
-  FB_CUDA(ctx, cudaMemcpyAsync(G.d(), h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  FB_TRY(shard_sum_dev(ctx, G.d(), n * n));                                          // the only O(n^2) exchange
   int sweeps = 0;
   int64_t defl = 0;      // triplets deflated at the eigensolver's noise floor (rank-deficient Y): d = 0, U completed, V zero
   FB_TRY(fb_syevj(ctx, G.d(), n, W.d(), dU, &sweeps, &defl));                       // replicated, identical bits
@@ -557,6 +614,8 @@ int fable_ctx_create(int device, uint64_t seed, fable_ctx** out) {
     delete ctx;
     return FABLE_ERR_CUDA;
   }
+  fb_mem_register_stream(device, ctx->stream, true);
+  fb_mem_register_stream(device, ctx->copy_stream, true);
   *out = ctx;
   return FABLE_OK;
 }
@@ -564,6 +623,9 @@ int fable_ctx_create(int device, uint64_t seed, fable_ctx** out) {
 void fable_ctx_destroy(fable_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();              // blocks released from now on carry no events of these streams
+  fb_mem_register_stream(ctx->device, ctx->stream, false);
+  fb_mem_register_stream(ctx->device, ctx->copy_stream, false);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ring) cudaFree(ctx->ring);
   for (int s = 0; s < 2; ++s) {
@@ -597,6 +659,7 @@ int fable_ctx_set_column_shard(fable_ctx* ctx, int64_t p_total, int64_t col_offs
   if (!ctx) return FABLE_ERR_INVALID;
   if (p_total == 0) {          // off
     ctx->shard_p = 0; ctx->shard_off = 0; ctx->shard_rank = 0; ctx->shard_world = 1; ctx->shard_fn = nullptr; ctx->shard_user = nullptr;
+    ctx->shard_dev_fn = nullptr; ctx->shard_dev_user = nullptr;
     return FABLE_OK;
   }
   FB_REQUIRE(ctx, fn, "column shard: NULL all-reduce callback");
@@ -604,6 +667,13 @@ int fable_ctx_set_column_shard(fable_ctx* ctx, int64_t p_total, int64_t col_offs
   FB_REQUIRE(ctx, p_total >= 1 && col_offset >= 0 && col_offset <= p_total, "column shard: need 0 <= col_offset <= p_total");
   ctx->shard_p = p_total; ctx->shard_off = col_offset; ctx->shard_rank = rank; ctx->shard_world = world;
   ctx->shard_fn = fn; ctx->shard_user = user;
+  return FABLE_OK;
+}
+
+int fable_ctx_set_column_shard_dev(fable_ctx* ctx, fable_allreduce_sum_dev_fn fn, void* user) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, shard_on(ctx) || !fn, "column shard: set the shard (fable_ctx_set_column_shard) before its device all-reduce");
+  ctx->shard_dev_fn = fn; ctx->shard_dev_user = user;
   return FABLE_OK;
 }
 
@@ -681,6 +751,32 @@ int fable_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, 
   FB_TRY(download(ctx, U, dU.d(), static_cast<size_t>(n) * r));
   FB_TRY(download(ctx, d, dd.d(), static_cast<size_t>(r)));
   FB_TRY(download(ctx, V, dV.d(), static_cast<size_t>(p) * r));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+// CPPsvd with flag 1 / 2 (cpp:52-58: arma::svd, the FULL decomposition): U n x n, d r, V p x p.  The thin factors come from
+// fable_svd's path; the remaining columns of the longer side complete an orthonormal basis (any such completion is a
+// valid full SVD: those columns meet zero singular values only).
+int fable_svd_full(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, double* d, double* V) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_NO_SHARD(ctx, "the full SVD");
+  FB_REQUIRE(ctx, Y && U && d && V, "svd: NULL pointer");
+  FB_REQUIRE(ctx, n >= 1 && p >= 1, "svd: Y must have at least one row and one column");
+  const int64_t r = n < p ? n : p, big = n < p ? p : n;
+  FB_REQUIRE(ctx, big - r <= 8192, "full SVD: more than 8192 basis vectors to complete; use the economy form (flag 3 / 4)");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf dY, dU, dd, dV;
+  FB_TRY(upload(ctx, dY, Y, static_cast<size_t>(n) * p));
+  FB_CUDA(ctx, dU.alloc(static_cast<size_t>(n) * n * sizeof(double)));
+  FB_CUDA(ctx, dV.alloc(static_cast<size_t>(p) * p * sizeof(double)));
+  FB_CUDA(ctx, dd.alloc(static_cast<size_t>(r) * sizeof(double)));
+  FB_TRY(fb_svd(ctx, dY.d(), n, p, dU.d(), dd.d(), dV.d()));              // first r columns of each (dense leading dimensions)
+  FB_TRY(fb_complete_orthonormal(ctx, dU.d(), n, n, r, n));
+  FB_TRY(fb_complete_orthonormal(ctx, dV.d(), p, p, r, p));
+  FB_TRY(download(ctx, U, dU.d(), static_cast<size_t>(n) * n));
+  FB_TRY(download(ctx, d, dd.d(), static_cast<size_t>(r)));
+  FB_TRY(download(ctx, V, dV.d(), static_cast<size_t>(p) * p));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FABLE_OK;
 }
@@ -1275,14 +1371,25 @@ static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_
                            double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
                            double* tausq, double* G, double* psi_sum, double* psi_sumsq) {
   fable_ctx* ctx = post->ctx;
+  FB_TRY(fable_posterior_fixed_outputs(post, SigmaPostMean, SigmaPlugIn, tausq, nullptr));
+  if (psi_sum) FB_TRY(fable_posterior_accum_reset(post));
+  FB_TRY(sample_range(post, MC, m0, MC, gam_inj, z_inj, LambdaSamples, SigmaSqSamples, psi_sum != nullptr));
+  if (psi_sum) FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
+  if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), post->p, nullptr, post->p, post->k, G));   // cpp:627
+  return FABLE_OK;
+}
+
+// the elements of CPPFABLESampler's list that do not depend on the draws (cpp:622-627)
+extern "C" int fable_posterior_fixed_outputs(fable_posterior* post, double* SigmaPostMean, double* SigmaPlugIn, double* tausq,
+                                             double* G) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
   const int64_t p = post->p;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
   FB_TRY(download(ctx, SigmaPostMean, post->rp.sigmahat.d(), p));              // cpp:622
   FB_TRY(download(ctx, SigmaPlugIn, post->rp.sig.d(), p));                     // cpp:623
   if (tausq) *tausq = post->rp.tausq;                                          // cpp:626
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (psi_sum) FB_TRY(fable_posterior_accum_reset(post));
-  FB_TRY(sample_range(post, MC, m0, MC, gam_inj, z_inj, LambdaSamples, SigmaSqSamples, psi_sum != nullptr));
-  if (psi_sum) FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
   if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), p, nullptr, p, post->k, G));   // cpp:627
   return FABLE_OK;
 }
@@ -1367,8 +1474,8 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
   FB_TRY(rank_dev(ctx, pl.in, pl.kMax, &k));                                     // wrapper:29-33
   if (kEstOut) *kEstOut = k;
   double vi = 0.0;
+  RowPosterior hyp;                                                              // wrapper:35-39 (unshrunk G0, cpp:390)
   {
-    RowPosterior hyp;                                                            // wrapper:35-39 (unshrunk G0, cpp:390)
     FB_TRY(row_posterior(ctx, pl.in, k, 1.0, 1.0, /*shrunk=*/0, hyp));
     FB_TRY(download(ctx, hypSigma, hyp.sig.d(), p));
     FB_TRY(download(ctx, hypG0, hyp.G0.d(), static_cast<size_t>(p) * k));
@@ -1380,7 +1487,20 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   if (varInflationOut) *varInflationOut = vi;
-  return posterior_from_inputs(ctx, pl.in, gamma0, delta0sq, k, vi, out);        // wrapper:46-54, cpp:553-597
+  FB_TRY(posterior_from_inputs(ctx, pl.in, gamma0, delta0sq, k, vi, out));       // wrapper:46-54, cpp:553-597
+  (*out)->hyp_G0 = std::move(hyp.G0);      // R sizes FABLEHyperParameters$G0 (p x kEst) once it knows kEst: fetched later
+  return FABLE_OK;
+}
+
+int fable_posterior_hyper_G0(fable_posterior* post, double* hypG0) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, hypG0, "hyper_G0: NULL output");
+  FB_REQUIRE(ctx, post->hyp_G0.ptr, "hyper_G0: this posterior was not created by fable_wrapper_sampler_begin");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_TRY(download(ctx, hypG0, post->hyp_G0.d(), static_cast<size_t>(post->p) * post->k));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
 }
 
 int fable_posterior_sampler_outputs(fable_posterior* post, int64_t MC, int64_t m0, const double* gam_inj,

@@ -36,6 +36,8 @@ struct fable_ctx {
   int shard_rank = 0, shard_world = 1;
   int (*shard_fn)(void*, double*, int64_t) = nullptr;
   void* shard_user = nullptr;
+  int (*shard_dev_fn)(void*, double*, int64_t, void*) = nullptr;    // optional: sums of DEVICE doubles (the n x n Gram)
+  void* shard_dev_user = nullptr;
 
   int fail(int code, const std::string& msg) {
     err = msg;
@@ -80,6 +82,7 @@ struct fable_ctx {
 cudaError_t fb_mem_acquire(void** ptr, size_t bytes);
 void fb_mem_release(void* ptr);
 void fb_mem_trim(int device);      // device < 0: every device
+void fb_mem_register_stream(int device, cudaStream_t s, bool add);   // streams a release records its events on
 
 // RAII device buffer of doubles (or bytes via raw()).
 struct DevBuf {

@@ -43,13 +43,13 @@
 namespace {
 
 constexpr int TILE = fbt::TILE;
-constexpr int KC = 16;             // rank chunk per pipeline step (multiple of 4)
+constexpr int KC_DEFAULT = 16;     // rank chunk per pipeline step (multiple of 4); 24 for 16 < k <= 24 (one chunk, no mid-draw barrier)
 constexpr int OSTR = TILE + 4;     // operand row stride: 68 = 4 mod 16 -> conflict-free DMMA fragment loads
 constexpr int BOXW = 16;           // TMA box row: 16 doubles = 128 bytes = one swizzle row
 constexpr int BOX_DOUBLES = BOXW * TILE;   // 16 x 64 sub-box, 8 KB; 4 sub-boxes per orientation
 // A CTA owns TILE rows (u) x TV columns (v) of one 64 x 64 tile slot: TV = 64 (one CTA per slot, two CTAs per
 // SM) or TV = 32 (two CTAs per slot, three per SM -- more independent store streams per SM, see fb_psi).
-template <int TV> struct Geo {
+template <int TV, int KC = KC_DEFAULT> struct Geo {
   static constexpr int VSTR = TV + 4;                                  // v-operand row stride (4 mod 16, as OSTR)
   static constexpr int BUF_DOUBLES = KC * (OSTR + VSTR);               // one operand buffer: [u rows][v rows] x KC
   static constexpr size_t OP_BYTES = 2 * BUF_DOUBLES * sizeof(double); // double-buffered: 34 KB / 26 KB
@@ -162,11 +162,11 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 //   Psi_m = G + B o (Lambda_m Lambda_m' - G) + diag(sigma2_m),  B = cov_correct_matrix(sig_hat, G)  (R:251, 282-290).
 // Slot 0 of Lw then holds G0 as a pseudo-draw (b = -1): its tile product is G, from which B is formed once
 // per CTA (R:196-202) and both stay in registers (64 more: one CTA per SM).
-template <bool MAT, bool ACC, bool CC, int TV>
+template <bool MAT, bool ACC, bool CC, int TV, int KC = KC_DEFAULT>
 __global__ void __launch_bounds__(256, CC ? 1 : Geo<TV>::CTAS)
 k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_m,
       const __grid_constant__ CUtensorMap tmap_sum, const __grid_constant__ CUtensorMap tmap_sq) {
-  using G_ = Geo<TV>;
+  using G_ = Geo<TV, KC>;
   constexpr int NI = G_::NI, WR = G_::WR, VSTR = G_::VSTR, BUFD = G_::BUF_DOUBLES, HALVES = TILE / TV;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms: 1 KB aligned
@@ -219,12 +219,15 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
       const double* base = a.Lw + (static_cast<int64_t>(b) * a.KP + l0) * a.pp;
       double* dst = op + buf * BUFD;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < KC / 8; ++h) {
         const int l = (tid >> 5) + 8 * h;
         if (l < kc) cp_async16(dst + l * OSTR + 2 * (tid & 31), base + static_cast<int64_t>(l) * a.pp + u0 + 2 * (tid & 31), pol_keep);
       }
-      const int l = tid >> 4;
-      if (l < kc) cp_async16(dst + KC * OSTR + l * VSTR + 2 * (tid & 15), base + static_cast<int64_t>(l) * a.pp + v0 + 2 * (tid & 15), pol_keep);
+#pragma unroll
+      for (int h = 0; h < (KC + 15) / 16; ++h) {
+        const int l = (tid >> 4) + 16 * h;
+        if (l < kc) cp_async16(dst + KC * OSTR + l * VSTR + 2 * (tid & 15), base + static_cast<int64_t>(l) * a.pp + v0 + 2 * (tid & 15), pol_keep);
+      }
     }
     cp_async_commit();
   };
@@ -549,16 +552,16 @@ int make_output_map(fable_ctx* ctx, double* base, int64_t rows, int64_t cols, in
 
 struct PsiMaps { CUtensorMap out, out_m, sum, sq; };
 
-template <bool MAT, bool ACC, bool CC = false, int TV = TILE>
+template <bool MAT, bool ACC, bool CC = false, int TV = TILE, int KC = KC_DEFAULT>
 int launch_psi(fable_ctx* ctx, const PsiArgs& a, unsigned slots, int64_t t0, const PsiMaps& m) {
-  constexpr size_t smem = Geo<TV>::SMEM_BYTES;
+  constexpr size_t smem = Geo<TV, KC>::SMEM_BYTES;
   static bool attr_dev[64] = {};
   bool& attr = attr_dev[ctx->device & 63];
   if (!attr) {
-    FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC, CC, TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_psi<MAT, ACC, CC, TV, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = true;
   }
-  k_psi<MAT, ACC, CC, TV><<<slots * (TILE / TV), 256, smem, ctx->stream>>>(a, t0, m.out, m.out_m, m.sum, m.sq);
+  k_psi<MAT, ACC, CC, TV, KC><<<slots * (TILE / TV), 256, smem, ctx->stream>>>(a, t0, m.out, m.out_m, m.sum, m.sq);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
 }
@@ -633,10 +636,15 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
     FB_TRY(make_output_map(ctx, a.acc_sum, TILE, ntile * TILE, 1, &m.sum, tv, TILE / BOXW));
     FB_TRY(make_output_map(ctx, a.acc_sq, TILE, ntile * TILE, 1, &m.sq, tv, TILE / BOXW));
   }
+  static const bool kc24_ok = !(getenv("FABLE_B200_PSI_KC24") && atoi(getenv("FABLE_B200_PSI_KC24")) == 0);
+  const bool k24 = kc24_ok && a.KP > 16 && a.KP <= 24;
   for (int64_t t0 = t_lo; t0 < t_hi; t0 += chunk) {
     const unsigned g = static_cast<unsigned>(t_hi - t0 < chunk ? t_hi - t0 : chunk);
     if (a.cc_gdiag && mat && acc) FB_TRY((launch_psi<true, true, true>(ctx, a, g, t0, m)));
     else if (a.cc_gdiag && mat) FB_TRY((launch_psi<true, false, true>(ctx, a, g, t0, m)));
+    // 16 < k <= 24 (BASELINE configs[3]: k = 20): one 24-row rank chunk instead of 16 + 8 with a barrier in mid-draw
+    else if (mat && acc && tv == 32 && k24) FB_TRY((launch_psi<true, true, false, 32, 24>(ctx, a, g, t0, m)));
+    else if (mat && tv == 32 && k24) FB_TRY((launch_psi<true, false, false, 32, 24>(ctx, a, g, t0, m)));
     else if (mat && acc && tv == 32) FB_TRY((launch_psi<true, true, false, 32>(ctx, a, g, t0, m)));
     else if (mat && tv == 32) FB_TRY((launch_psi<true, false, false, 32>(ctx, a, g, t0, m)));
     else if (mat && acc) FB_TRY((launch_psi<true, true>(ctx, a, g, t0, m)));

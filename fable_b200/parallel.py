@@ -188,6 +188,19 @@ def host_allreduce(device=None, group=None):
     return fn
 
 
+def device_allreduce(device, group=None):
+    """In-place NCCL sum of `count` float64 at a device address, ordered on the library's stream: the device-pointer
+    callback of `Context.set_column_shard` (the n x n Gram of the sharded SVD stays in HBM).  NCCL groups only."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(ptr, count, stream):
+        t = as_torch(ptr, count, device)
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=device)):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return fn
+
+
 def gather_rows(local, p_total, col_offset, allreduce):
     """Every rank's rows of a per-variable array (p_local, ...) -> the full (p_total, ...) array on every rank:
     each rank writes its block into zeros and the blocks are summed (disjoint, so the sum is exact)."""
@@ -200,14 +213,14 @@ def gather_rows(local, p_total, col_offset, allreduce):
 
 
 def sharded_estimation(Y_local, p_total, col_offset, rank, world, ctx, allreduce, gamma0=1.0, delta0sq=1.0, maxProp=0.95,
-                       variant="wrapper"):
+                       variant="wrapper", allreduce_dev=None):
     """The estimation half of FABLEPosteriorSampler (R/FABLE_wrapper.R:20-44) on column shards: every rank passes
     its own columns of Y.  Returns, identical on every rank: svd d / u (and the local rows of v), kMax, kEst, the
     gathered row posterior (G0, gnd, sig, sigmahat, tausq: what `Posterior.from_rows` takes), the plug-in
     hyper-parameters' sigma^2 and unshrunk G0, and varInflation."""
     from . import api
     n = Y_local.shape[0]
-    ctx.set_column_shard(p_total, col_offset, rank, world, allreduce)
+    ctx.set_column_shard(p_total, col_offset, rank, world, allreduce, allreduce_dev=allreduce_dev)
     try:
         s = api.svd(Y_local, ctx=ctx)                                              # wrapper:23-26
         kMax = api.kmax_rule(s["d"], maxProp)                                      # wrapper:27

@@ -76,6 +76,12 @@ int fable_ctx_trim_cache(fable_ctx* ctx);
 typedef int (*fable_allreduce_sum_fn)(void* user, double* vals, int64_t count);
 int fable_ctx_set_column_shard(fable_ctx* ctx, int64_t p_total, int64_t col_offset, int rank, int world,
                                fable_allreduce_sum_fn fn, void* user);
+/* Optional, after fable_ctx_set_column_shard: sums of DEVICE-resident doubles -- the n x n Gram of the sharded SVD, the
+ * one O(n^2) exchange of the path (200 MB at n = 5000) -- go through `fn` instead of being bounced through the host
+ * callback: fn must sum `count` doubles at the device pointer over all ranks in place, ordered after the work already
+ * queued on `cuda_stream` (the context's stream, a cudaStream_t) -- e.g. ncclAllReduce on that stream.  NULL: off. */
+typedef int (*fable_allreduce_sum_dev_fn)(void* user, double* dev_vals, int64_t count, void* cuda_stream);
+int fable_ctx_set_column_shard_dev(fable_ctx* ctx, fable_allreduce_sum_dev_fn fn, void* user);
 int fable_ctx_synchronize(fable_ctx* ctx);
 /* the context's main stream as a cudaStream_t cast to void* (for CUDA-event timing). */
 void* fable_ctx_stream(fable_ctx* ctx);
@@ -100,6 +106,9 @@ int fable_ctx_psi_ring(fable_ctx* ctx, double** dev_ring, int* slots);
  * Y n x p.  r = min(n,p).  U n x r, d r (descending), V p x r.  Gram (DMMA) + Jacobi eigensolve
  * + back-multiplication.  Signs: each V column has its largest-|entry| positive. */
 int fable_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, double* d, double* V);
+/* CPPsvd(X, flag) with flag 1 / 2 (:52-58, arma::svd = the FULL decomposition): U n x n, d r, V p x p; flags 3 / 4 (svd_econ,
+ * :60-66) are fable_svd.  `flag` also chose the LAPACK driver there ("std" / "dc"); there is one algorithm here. */
+int fable_svd_full(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double* U, double* d, double* V);
 /* min{ i : cumsum(d)_i / sum(d) >= maxProp }, 1-based (R/FABLE_wrapper.R:27, 94). Host-only. */
 int fable_kmax(const double* d, int64_t r, double maxProp, int* kMax);
 
@@ -165,8 +174,8 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
  * once and every intermediate resident in HBM; the Rcpp layer unpacks the outputs into the wrappers'
  * unchanged return lists.  U n x r, d r, V p x r (r = min(n,p)) are the `svdY` element; any output pointer
  * may be NULL to skip it (kEst is required).  varInflation follows the wrapper's formula (:41-44).
- * hyp* = FABLEHyperParameters' list (unshrunk G0; hypG0 must hold p x min(n,p) doubles, the first
- * kEst columns are written). */
+ * hyp* = FABLEHyperParameters' list (unshrunk G0; hypG0, if not NULL, must hold p x min(n,p) doubles, the first
+ * kEst columns are written -- or pass NULL and call fable_posterior_hyper_G0 once kEst is known). */
 int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
                                  double delta0sq, double maxProp, double* Cov, int* kEst, int* kMax,
                                  double* U, double* d, double* V);
@@ -183,6 +192,9 @@ int fable_posterior_sampler_outputs(fable_posterior* post, int64_t MC, int64_t m
                                     double* SigmaPostMean, double* SigmaPlugIn, double* tausq, double* G,
                                     double* psi_sum, double* psi_sumsq);
 int fable_posterior_rank(fable_posterior* post, int* k);
+/* FABLEHyperParameters$G0 (unshrunk, p x kEst) of a posterior made by fable_wrapper_sampler_begin: lets the caller size
+ * the matrix after the rank is known (hypG0 = NULL in sampler_begin) instead of passing a p x min(n,p) scratch. */
+int fable_posterior_hyper_G0(fable_posterior* post, double* hypG0);
 
 /* ---- f1: CPPCCFABLEPostProcessing (:631-713) / CCFABLEPostProcessingSubmatrix(_Optimized) (:716-893) ---
  * Entry-wise posterior mean and (alpha/2, 1-alpha/2) sample quantiles (Armadillo quantile, type 5) of
@@ -276,6 +288,9 @@ int fable_posterior_samples(fable_posterior* post, int64_t m0, int64_t MC, int64
  * accum_reset + this + accum_fetch + G. */
 int fable_posterior_sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t ldm, const double* gam_inj,
                                  const double* z_inj, double* LambdaSamples, double* SigmaSqSamples, int psi_pass);
+/* the elements of CPPFABLESampler's list that do not depend on the draws (:622-627); any pointer may be NULL */
+int fable_posterior_fixed_outputs(fable_posterior* post, double* SigmaPostMean, double* SigmaPlugIn, double* tausq,
+                                  double* G);
 /* accumulators: device pointers to the compact upper tiles of the slice (count doubles each = tiles * 4096; the
  * one NCCL sum of multi-GPU partition A -- draws sharded over ranks -- reduces these buffers as they are), reset,
  * fetch as dense symmetric p x p host matrices (zeros outside the slice), fetch as raw compact tiles. */
@@ -283,6 +298,27 @@ int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** 
 int fable_posterior_accum_reset(fable_posterior* post);
 int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sumsq);            /* host out */
 int fable_posterior_accum_fetch_tiles(fable_posterior* post, double* sum_tiles, double* sumsq_tiles);
+
+/* ---- multi-GPU behind the boundary: one process (the R session), several devices of one box ------------------------
+ * The reference has no multi-device code; its MC loop (:599-618) is embarrassingly parallel over draws.
+ * fable_multi_sampler is CPPFABLESampler (:532-629; same arguments and outputs as fable_sampler) on the draw partition
+ * (SURVEY 8(e) A): device g draws a contiguous share of the MC axis with the stream one device would use (the union
+ * of the rows is bit-identical to fable_sampler), writes its rows straight into the caller's LambdaSamples /
+ * SigmaSqSamples, and the Psi sum / sumsq accumulators are summed by a hand-written kernel over NVLink peer memory
+ * (device g reduces slice g of the compact tiles over all devices into device 0's buffers; no library collective)
+ * before device 0 alone downloads the dense p x p sums.  devices = NULL: ordinals 0 .. ndev-1.  Needs peer access
+ * between the devices (NVLink / NVSwitch); there is no host-staged fallback. */
+typedef struct fable_multi fable_multi;
+int fable_multi_create(int ndev, const int* devices, uint64_t seed, fable_multi** out);
+void fable_multi_destroy(fable_multi* m);
+const char* fable_multi_last_error(const fable_multi* m);   /* m may be NULL: last create() failure */
+int fable_multi_devices(const fable_multi* m);
+fable_ctx* fable_multi_ctx(fable_multi* m, int g);          /* the per-device contexts (owned by m) */
+int fable_multi_sampler(fable_multi* m, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
+                        int64_t MC, const double* U, const double* V, const double* d, int64_t r, int kEst,
+                        double varInflation, const double* gam_inj, const double* z_inj, int64_t m0,
+                        double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
+                        double* tausq, double* G, double* psi_sum, double* psi_sumsq);
 
 /* ---- device-pointer primitives ------------------------------------------------------------------ */
 /* out[u + p*v] = sum_l A[u + lda*l] A[v + lda*l] + (u==v ? s[u] : 0), dense symmetric p x p

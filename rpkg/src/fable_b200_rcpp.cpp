@@ -197,14 +197,32 @@ Rcpp::List CCFABLEPostProcessingSubmatrix_Optimized(Rcpp::List FABLEOutput, doub
   return CCFABLEPostProcessingSubmatrix(FABLEOutput, alpha, SelectedIndices);
 }
 
-// reference cpp:40-74 (exported, unused by the wrappers); `flag` chose a LAPACK driver there
+// reference cpp:40-74 (exported, unused by the wrappers).  flag 1 / 2: arma::svd, the full decomposition (U n x n, V p x p,
+// :52-58); 3 / anything else: svd_econ (:60-66).  The LAPACK driver the flag also selected ("std" / "dc") has no counterpart.
 // [[Rcpp::export]]
 Rcpp::List CPPsvd(Rcpp::NumericMatrix X, int flag) {
   const int64_t n = X.nrow(), p = X.ncol(), r = n < p ? n : p;
-  Rcpp::NumericMatrix U(n, r), V(p, r);
+  const bool full = flag == 1 || flag == 2;
+  Rcpp::NumericMatrix U(n, full ? n : r), V(p, full ? p : r);
   Rcpp::NumericVector d(r);
-  check(fable_svd(ctx(), X.begin(), n, p, U.begin(), d.begin(), V.begin()));
+  check((full ? fable_svd_full : fable_svd)(ctx(), X.begin(), n, p, U.begin(), d.begin(), V.begin()));
   return Rcpp::List::create(Rcpp::Named("U") = U, Rcpp::Named("d") = d, Rcpp::Named("V") = V);
+}
+
+// reference cpp:17-26: n Gamma(shape a, rate b) draws.  Not on the device path (the sampler draws its gammas on the GPU
+// from the Philox stream); kept because exportPattern makes it public.  R's own generator, honouring set.seed().
+// [[Rcpp::export]]
+Rcpp::NumericVector rGamma(int n, double a, double b) { return Rcpp::rgamma(n, a, 1.0 / b); }
+
+// reference cpp:28-37: A + A' with the diagonal halved.  Host loop: O(p^2) copies, no arithmetic worth a kernel.
+// [[Rcpp::export]]
+Rcpp::NumericMatrix SymmetrizeMatrix(Rcpp::NumericMatrix A) {
+  const int n = A.nrow();
+  if (A.ncol() != n) Rcpp::stop("SymmetrizeMatrix: A must be square");
+  Rcpp::NumericMatrix out(n, n);
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) out(i, j) = i == j ? (A(i, i) + A(i, i)) / 2.0 : A(i, j) + A(j, i);
+  return out;
 }
 
 // NEW: FABLEPosteriorSampler / FABLEPosteriorMean as pipelines with Y uploaded once (a11).  The R wrappers
@@ -213,19 +231,23 @@ Rcpp::List CPPsvd(Rcpp::NumericMatrix X, int flag) {
 Rcpp::List FABLEPosteriorSamplerB200(Rcpp::NumericMatrix Y, double gamma0, double delta0sq, double maxProp, int MC) {
   const int64_t n = Y.nrow(), p = Y.ncol(), r = n < p ? n : p;
   reseed();
-  Rcpp::NumericMatrix U(n, r), V(p, r), hG0full(p, r), hG(p, p), G(p, p);
+  Rcpp::NumericMatrix U(n, r), V(p, r), hG(p, p), G(p, p);
   Rcpp::NumericVector d(r), hsig(p), pm(p), plug(p);
   int kMax = 0, k = 0;
   double htau = 0.0, vi = 0.0, tau = 0.0;
-  fable_posterior* post = nullptr;
+  // the resident row posterior is released on every path out of this function -- an R allocation failure or an
+  // interrupt below would otherwise leak its device buffers for the rest of the session
+  struct PostGuard {
+    fable_posterior* p = nullptr;
+    ~PostGuard() { fable_posterior_destroy(p); }
+  } guard;
   check(fable_wrapper_sampler_begin(ctx(), Y.begin(), n, p, gamma0, delta0sq, maxProp, U.begin(), d.begin(), V.begin(), &kMax,
-                                    &k, hsig.begin(), hG0full.begin(), &htau, hG.begin(), &vi, &post));
-  Rcpp::NumericMatrix L(MC, static_cast<int>(k * p)), S(MC, static_cast<int>(p));   // sized now that k is known
-  const int rc = fable_posterior_sampler_outputs(post, MC, 0, nullptr, nullptr, L.begin(), S.begin(), pm.begin(), plug.begin(),
-                                                 &tau, G.begin(), nullptr, nullptr);
-  fable_posterior_destroy(post);
-  check(rc);
-  Rcpp::NumericMatrix hG0 = hG0full(Rcpp::_, Rcpp::Range(0, k - 1));
+                                    &k, hsig.begin(), /*hypG0 (fetched below, once k is known)=*/nullptr, &htau, hG.begin(), &vi, &guard.p));
+  Rcpp::NumericMatrix hG0(static_cast<int>(p), k);                                   // sized now that k is known
+  check(fable_posterior_hyper_G0(guard.p, hG0.begin()));
+  Rcpp::NumericMatrix L(MC, static_cast<int>(k * p)), S(MC, static_cast<int>(p));
+  check(fable_posterior_sampler_outputs(guard.p, MC, 0, nullptr, nullptr, L.begin(), S.begin(), pm.begin(), plug.begin(),
+                                        &tau, G.begin(), nullptr, nullptr));
   Rcpp::List samples = Rcpp::List::create(Rcpp::Named("LambdaSamples") = L, Rcpp::Named("SigmaSqSamples") = S,
                                           Rcpp::Named("SigmaSqEstimatePostMean") = pm, Rcpp::Named("SigmaSqEstimatePlugIn") = plug,
                                           Rcpp::Named("EstimatedRank") = k, Rcpp::Named("VarianceInflation") = vi,

@@ -124,6 +124,61 @@ def test_svd_against_lapack(ctx, n, p, k):
     assert relerr_mat(s["u"][:, :kk], (u * sgn)[:, :kk]) < 1e-8
 
 
+def _rank_deficient(kind, n, p, k, seed):
+    Y = synth.factor_data(n, p, k, rep=seed)
+    if kind == "centred":          # what the reference asks of its caller (cpp:296): one singular value is exactly 0 when n <= p
+        Y = Y - Y.mean(axis=0, keepdims=True)
+    elif kind == "dup_rows":       # exactly repeated observations: three zero singular values (n <= p)
+        Y[-3:] = Y[:3]
+    elif kind == "dup_cols":       # exactly repeated variables (p < n)
+        Y[:, -2:] = Y[:, :2]
+    elif kind == "low_rank":       # rank k plus nothing
+        rng = np.random.default_rng(seed)
+        Y = rng.standard_normal((n, k)) @ rng.standard_normal((k, p))
+    return np.asfortranarray(Y)
+
+
+@pytest.mark.parametrize("kind,n,p,k,nz", [("centred", 40, 120, 3, 1), ("centred", 200, 1000, 5, 1), ("centred", 500, 1000, 10, 1),
+                                           ("centred", 16, 64, 2, 1), ("centred", 300, 130, 4, 0), ("dup_rows", 60, 200, 3, 3),
+                                           ("dup_cols", 300, 50, 3, 2), ("low_rank", 64, 200, 5, 59), ("low_rank", 130, 40, 4, 36)])
+def test_svd_rank_deficient(ctx, kind, n, p, k, nz):
+    """SURVEY H4 / the reference's own precondition (column-centred Y, cpp:296): numerically zero singular values.  The Gram
+    route cannot resolve them; they must come back as d = 0 with singular vectors that complete orthonormal bases on both
+    sides (what LAPACK returns), never as normalised rounding noise -- and the eigensolver must still converge."""
+    Y = _rank_deficient(kind, n, p, k, n + p)
+    s = fb.svd(Y, ctx=ctx)
+    u, d, v = orc.svd_thin(Y)
+    r = min(n, p)
+    good = r - nz
+    assert relerr_vec(s["d"][:good], d[:good]) < TOL
+    assert np.all(s["d"][good:] == 0.0) and np.all(d[good:] < 1e-9 * d[0])                # deflated exactly where LAPACK has noise
+    assert relerr_mat(s["u"].T @ s["u"], np.eye(r)) < 1e-9 and relerr_mat(s["v"].T @ s["v"], np.eye(r)) < 1e-9
+    assert relerr_mat((s["u"] * s["d"]) @ s["v"].T, Y) < TOL
+    assert np.all(np.diff(s["d"]) <= 0)
+    for maxProp in (0.5, 0.95):
+        kMax = orc.kmax_rule(d, maxProp)
+        assert fb.kmax_rule(s["d"], maxProp) == kMax
+        if kind != "low_rank":            # (noise-free low-rank data: log of a zero residual variance, SURVEY A.6 -- no oracle)
+            assert fb.CPPRankEstimator(Y, s["u"], s["v"], s["d"], kMax, ctx=ctx) == orc.rank_estimator(Y, u, v, d, kMax)
+    if kind == "centred" and n <= p:      # the null left vector of column-centred data is the constant vector
+        assert abs(abs(s["u"][:, -1] @ np.ones(n)) / math.sqrt(n) - 1) < 1e-9
+
+
+def test_wrappers_on_centred_data(ctx):
+    """FABLEPosteriorMean / FABLEPosteriorSampler on column-centred Y (n <= p), sign-invariant outputs vs the oracle."""
+    n, p, k = 120, 400, 4
+    Y = _rank_deficient("centred", n, p, k, 9)
+    got = fb.FABLEPosteriorMean(Y, ctx=ctx); ref = orc.FABLEPosteriorMean(Y)
+    assert got["estRank"] == ref["estRank"] and relerr_mat(got["FABLEPostMean"], ref["FABLEPostMean"]) < TOL
+    assert got["svdY"]["d"][-1] == 0.0 and relerr_vec(got["svdY"]["d"][:-1], ref["svdY"]["d"][:-1]) < TOL
+    smp = fb.FABLEPosteriorSampler(Y, MC=3, ctx=ctx)
+    kMax = orc.kmax_rule(ref["svdY"]["d"], 0.95)
+    assert smp["estRank"] == orc.rank_estimator(Y, ref["svdY"]["u"], ref["svdY"]["v"], ref["svdY"]["d"], kMax)
+    hyp = orc.hyper_parameters(Y, ref["svdY"]["u"], ref["svdY"]["v"], ref["svdY"]["d"], smp["estRank"])
+    assert relerr_vec(smp["FABLEHyperParameters"]["SigmaSqEstimate"], hyp["SigmaSqEstimate"]) < TOL
+    assert relerr_mat(smp["FABLEHyperParameters"]["G"], hyp["G"]) < TOL
+
+
 # ---- C1: n=500, p=1000, k=10 (BASELINE.json configs[0]) end to end vs the oracle ------------------
 @pytest.fixture(scope="module")
 def c1():
@@ -614,6 +669,37 @@ def test_jacobi_eigensolver(ctx, m):
     w = dW.cpu().numpy(); Q = dQ.cpu().numpy().T
     assert sweeps <= 30
     assert relerr_vec(w, np.linalg.eigvalsh(G)[::-1]) < 1e-11
+    assert relerr_mat(Q @ np.diag(w) @ Q.T, G) < 1e-11
+    assert relerr_mat(Q.T @ Q, np.eye(m)) < 1e-11
+
+
+@pytest.mark.parametrize("m,spectrum", [(96, "repeated"), (300, "repeated"), (300, "clustered"), (257, "singular"), (64, "singular"),
+                                        (12, "singular"), (500, "rank1")])
+def test_jacobi_eigensolver_hard_spectra(ctx, m, spectrum):
+    """Repeated and clustered eigenvalues (any orthonormal basis of an eigenspace is right: check the decomposition, not
+    the vectors) and exactly singular matrices (zero eigenvalues deflated to 0, vectors completed to an orthonormal
+    basis, convergence in the usual number of sweeps)."""
+    import torch
+    rng = np.random.default_rng(m)
+    Q0 = np.linalg.qr(rng.standard_normal((m, m)))[0]
+    if spectrum == "repeated":
+        w0 = np.repeat(np.array([9.0, 4.0, 4.0, 1.0]), m // 4 + 1)[:m]
+    elif spectrum == "clustered":
+        w0 = 5.0 + 1e-9 * rng.standard_normal(m); w0[:3] = (100.0, 50.0, 50.0 * (1 + 1e-12))
+    elif spectrum == "singular":
+        w0 = rng.uniform(1.0, 10.0, m); w0[-(m // 4):] = 0.0
+    else:
+        w0 = np.zeros(m); w0[0] = 3.0
+    w0 = np.sort(w0)[::-1]
+    G = (Q0 * w0) @ Q0.T
+    G = 0.5 * (G + G.T)
+    dG = torch.from_numpy(G.copy()).cuda()
+    dW = torch.empty(m, dtype=torch.float64, device="cuda"); dQ = torch.empty((m, m), dtype=torch.float64, device="cuda")
+    sweeps = fb.api.dev_syevj(ctx, dG.data_ptr(), m, dW.data_ptr(), dQ.data_ptr())
+    w = dW.cpu().numpy(); Q = dQ.cpu().numpy().T
+    assert sweeps <= 30
+    assert np.max(np.abs(w - w0)) < 1e-12 * w0[0]
+    assert np.all(w[w0 == 0.0] == 0.0)
     assert relerr_mat(Q @ np.diag(w) @ Q.T, G) < 1e-11
     assert relerr_mat(Q.T @ Q, np.eye(m)) < 1e-11
 

@@ -24,10 +24,11 @@ def main():
     j0, j1 = parallel.column_range(p, rank, world)
     ar = parallel.host_allreduce(dev)
     Yl = np.asfortranarray(Y[:, j0:j1])
-    parallel.sharded_estimation(Yl, p, j0, rank, world, ctx, ar)      # warm-up (module load, NCCL channels)
+    ard = parallel.device_allreduce(dev)                               # the n x n Gram is summed in HBM (NCCL on the library's stream)
+    parallel.sharded_estimation(Yl, p, j0, rank, world, ctx, ar, allreduce_dev=ard)      # warm-up (module load, NCCL channels)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = parallel.sharded_estimation(Yl, p, j0, rank, world, ctx, ar)
+    res = parallel.sharded_estimation(Yl, p, j0, rank, world, ctx, ar, allreduce_dev=ard)
     torch.cuda.synchronize(); dist.barrier()
     t_sh = time.perf_counter() - t0
     post = fb.Posterior.from_rows(n, 1.0, 1.0, res["rows"], res["varInflation"], ctx=ctx)
