@@ -168,6 +168,7 @@ struct Inputs {
   DevBuf Y, U, V, d;
   int64_t n = 0, p = 0, r = 0;
   int kcols = 0;   // number of leading singular triplets resident
+  bool own_svd = false;   // (U, V, d) were produced by fb_svd from this Y: V diag(d) = Y'U and U'U = I by construction
 };
 
 // Column shard (fable_ctx_set_column_shard): Y, V and every per-variable vector hold the columns this context
@@ -279,14 +280,86 @@ int criterion_dev(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, doubl
   return FABLE_OK;
 }
 
+// Criterion values for the rank search.  The reference evaluates CPPCriterionFunction from scratch at every visited rank
+// (cpp:233-247, 321-330: ~25 calls, each an n x p x k' product and an n x p residual pass).  Here the search is STEERED by
+// the all-rank form of SURVEY A.3 -- when (U, V, d) is a consistent SVD of Y, every sum_j log sigma_j^2(k') comes out of
+// ONE pass over V -- and DECIDED by the reference's own arithmetic wherever it matters: two criteria closer than 1e-9
+// relative are re-evaluated with the explicit residual before they are compared, so the bisection takes the same
+// branches and the window arg-min picks the same rank.  Consistency is checked, not assumed: inputs at the
+// CPP* boundary are the caller's (Y'U against V diag(d) and U'U against I, one n x p x kMax product); if the check
+// fails, or any shortcut value is not finite, every evaluation is the explicit one.
 struct CritCache {
   fable_ctx* ctx; const Inputs& in; RowScratch sc; std::map<int, double> memo;
+  std::vector<double> fast;      // fast[k-1]: criterion from the all-rank pass (empty: not available)
   CritCache(fable_ctx* c, const Inputs& i) : ctx(c), in(i) {}
-  int eval(int k, double* v) {
+  int eval(int k, double* v) {                    // the reference's arithmetic (explicit residual)
     auto it = memo.find(k);
     if (it != memo.end()) { *v = it->second; return FABLE_OK; }   // same inputs -> same value (cpp:233 re-evaluates)
     FB_TRY(criterion_dev(ctx, in, k, sc, v));
     memo[k] = *v;
+    return FABLE_OK;
+  }
+  int prepare(int kMax) {
+    const bool on = !(getenv("FABLE_B200_RANK_FAST") && atoi(getenv("FABLE_B200_RANK_FAST")) == 0);   // 0: every evaluation explicit (A/B, tests)
+    fast.clear();
+    if (!on || kMax < 3 || kMax > in.kcols) return FABLE_OK;
+    const int64_t n = in.n, p = in.p;
+    int bad = 0;
+    if (!in.own_svd) {
+      DevBuf T, E;
+      FB_CUDA(ctx, T.alloc(static_cast<size_t>(p) * kMax * sizeof(double)));
+      FB_TRY(fb_gemm(ctx, 1, 1, p, kMax, n, 1.0, in.Y.d(), n, in.U.d(), n, T.d(), p));                 // T = Y'U_kMax
+      double md = 0.0, ma = 0.0;
+      FB_TRY(fb_svd_consistency(ctx, T.d(), p, in.V.d(), p, in.d.d(), p, kMax, &md, &ma));
+      FB_CUDA(ctx, E.alloc(static_cast<size_t>(kMax) * kMax * sizeof(double)));
+      FB_TRY(fb_gemm(ctx, 1, 1, kMax, kMax, n, 1.0, in.U.d(), n, in.U.d(), n, E.d(), kMax));           // U'U
+      double me = 0.0;
+      FB_TRY(fb_identity_err(ctx, E.d(), kMax, &me));
+      if (!(md <= 1e-11 * ma) || !(me <= 1e-11)) bad = 1;
+    }
+    std::vector<double> sl(kMax, 0.0);
+    if (!bad) {
+      FB_TRY(sc.ensure(ctx, p, 1));
+      FB_TRY(fb_colsumsq(ctx, in.Y.d(), n, p, n, sc.s.d()));
+      FB_TRY(fb_prefix_sumlog(ctx, in.V.d(), p, in.d.d(), sc.s.d(), p, kMax, n, sl.data()));
+    }
+    if (shard_on(ctx)) {            // sums over ALL variables; a failed check on any rank switches every rank to the explicit path
+      std::vector<double> buf(sl);
+      buf.push_back(static_cast<double>(bad));
+      FB_TRY(shard_sum(ctx, buf.data(), static_cast<int64_t>(buf.size())));
+      bad = buf.back() != 0.0;
+      std::copy(buf.begin(), buf.end() - 1, sl.begin());
+    }
+    if (bad) return FABLE_OK;
+    const double dn = static_cast<double>(n), dp = static_cast<double>(glob_p(ctx, p));
+    const double maxint = dn > dp ? dn : dp, minint = dn < dp ? dn : dp;
+    for (int k = 1; k <= kMax; ++k) {
+      if (!std::isfinite(sl[k - 1])) { fast.clear(); return FABLE_OK; }
+      const double LL = (-dn * dp / 2.0) - (dn * sl[k - 1] / 2.0);                                      // cpp:199
+      fast.push_back((-2.0 * LL) + (static_cast<double>(k) * maxint * std::log(minint)));               // cpp:209
+    }
+    return FABLE_OK;
+  }
+  // sign of crit(a) - crit(b) as the reference's arithmetic gives it: -1, 0, +1
+  int compare(int a, int b, int* sign) {
+    if (a == b) { *sign = 0; return FABLE_OK; }
+    double va, vb;
+    const bool have = !fast.empty() && a >= 1 && b >= 1 && a <= static_cast<int>(fast.size()) && b <= static_cast<int>(fast.size());
+    if (have && !memo.count(a) && !memo.count(b)) {
+      va = fast[a - 1]; vb = fast[b - 1];
+      const double mag = std::fabs(va) > std::fabs(vb) ? std::fabs(va) : std::fabs(vb);
+      if (std::fabs(va - vb) > 1e-9 * mag) { *sign = va < vb ? -1 : 1; return FABLE_OK; }
+    }
+    if (have) {
+      // one of them already explicit, or too close to call: explicit values for both unless the shortcut is decisive
+      va = memo.count(a) ? memo[a] : fast[a - 1];
+      vb = memo.count(b) ? memo[b] : fast[b - 1];
+      const double mag = std::fabs(va) > std::fabs(vb) ? std::fabs(va) : std::fabs(vb);
+      if (std::fabs(va - vb) > 1e-9 * mag) { *sign = va < vb ? -1 : 1; return FABLE_OK; }
+    }
+    FB_TRY(eval(a, &va));
+    FB_TRY(eval(b, &vb));
+    *sign = va < vb ? -1 : (va > vb ? 1 : 0);
     return FABLE_OK;
   }
 };
@@ -295,14 +368,12 @@ struct CritCache {
 int bisection(CritCache& cc, int lower, int upper, int* lo, int* hi) {
   while (upper - lower > 5) {                                    // cpp:223
     const int mid = (lower + upper) / 2;                         // cpp:225
-    double cl, cm;
-    FB_TRY(cc.eval(lower, &cl));                                 // cpp:233
-    FB_TRY(cc.eval(mid, &cm));                                   // cpp:235
-    if (cl < cm) { upper = mid; continue; }                      // cpp:237-239
+    int sg;
+    FB_TRY(cc.compare(lower, mid, &sg));                         // cpp:233-235
+    if (sg < 0) { upper = mid; continue; }                       // cpp:237-239: crit(lower) < crit(mid)
     const int tq = (mid + upper) / 2;                            // cpp:243
-    double ct;
-    FB_TRY(cc.eval(tq, &ct));                                    // cpp:247
-    if (cm <= ct) upper = mid; else lower = mid;                 // cpp:249-255
+    FB_TRY(cc.compare(mid, tq, &sg));                            // cpp:247
+    if (sg <= 0) upper = mid; else lower = mid;                  // cpp:249-255: crit(mid) <= crit(tq)
   }
   *lo = lower; *hi = upper;
   return FABLE_OK;
@@ -312,13 +383,14 @@ int bisection(CritCache& cc, int lower, int upper, int* lo, int* hi) {
 int rank_dev(fable_ctx* ctx, const Inputs& in, int kMax, int* kEst) {
   FB_REQUIRE(ctx, kMax >= 1 && kMax <= in.kcols, "kMax must be in 1..length(svalsY)");
   CritCache cc(ctx, in);
+  FB_TRY(cc.prepare(kMax));
   int lo, hi;
   FB_TRY(bisection(cc, 1, kMax, &lo, &hi));                      // cpp:314
-  int best = lo; double bestv = 0.0;
-  for (int k = lo; k <= hi; ++k) {                               // cpp:321-330
-    double v;
-    FB_TRY(cc.eval(k, &v));
-    if (k == lo || v < bestv) { best = k; bestv = v; }           // index_min = first minimum (cpp:337)
+  int best = lo;
+  for (int k = lo + 1; k <= hi; ++k) {                           // cpp:321-330
+    int sg;
+    FB_TRY(cc.compare(k, best, &sg));
+    if (sg < 0) best = k;                                        // index_min = first minimum (cpp:337)
   }
   *kEst = best;
   return FABLE_OK;
@@ -838,6 +910,7 @@ int fable_bisection(fable_ctx* ctx, int lower, int upper, const double* Y, int64
   Inputs in;
   FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, upper, in));
   CritCache cc(ctx, in);
+  FB_TRY(cc.prepare(upper));
   return bisection(cc, lower, upper, lo, hi);
 }
 
@@ -1426,6 +1499,7 @@ int pipeline_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double m
   FB_CUDA(ctx, in.V.alloc(static_cast<size_t>(p) * r * sizeof(double)));
   FB_CUDA(ctx, in.d.alloc(static_cast<size_t>(r) * sizeof(double)));
   FB_TRY(fb_svd(ctx, in.Y.d(), n, p, in.U.d(), in.d.d(), in.V.d()));
+  in.own_svd = n <= p;        // n <= p: V = Y'U / d column by column and U is the eigensolver's orthogonal factor
   pl.d.resize(r);
   FB_TRY(download(ctx, pl.d.data(), in.d.d(), r));
   FB_TRY(download(ctx, U, in.U.d(), static_cast<size_t>(n) * r));

@@ -124,6 +124,13 @@ int fb_cq(fable_ctx* ctx, const double* dV, int64_t ldv, const double* dd, int64
           double* d_c, int64_t ldc, double* d_q);
 // reduce.cu
 int fb_sum_log_scaled(fable_ctx* ctx, const double* d_x, int64_t p, double scale, double* host_out);
+// all-rank criterion pieces: host_out[k'-1] = sum_j log((s_j - sum_{l <= k'} (d_l V_jl)^2) / n), k' = 1 .. kMax;
+// max |T - V diag(d)| / max |V diag(d)| over p x k; max |A - I| over k x k
+int fb_prefix_sumlog(fable_ctx* ctx, const double* dV, int64_t ldv, const double* dd, const double* ds, int64_t p, int kMax,
+                     int64_t n, double* host_out);
+int fb_svd_consistency(fable_ctx* ctx, const double* dT, int64_t ldt, const double* dV, int64_t ldv, const double* dd, int64_t p,
+                       int k, double* max_diff, double* max_abs);
+int fb_identity_err(fable_ctx* ctx, const double* dA, int64_t k, double* max_diff);
 int fb_loglik_terms(fable_ctx* ctx, const double* d_resid, const double* d_sig, int64_t p, double* sum_log_sd,
                     double* sum_resid_over_sig);
 int fb_q_over_sig_sum(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, double* host_sum);

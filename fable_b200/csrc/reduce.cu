@@ -72,6 +72,104 @@ int reduce_to_host(fable_ctx* ctx, F f, int64_t len, double* host_out) {
   return FABLE_OK;
 }
 
+// ---- all-rank criterion from one pass ----------------------------------------------------------
+// When (U, V, d) is a consistent SVD of Y -- Y'U = V diag(d) and U'U = I -- the residual column sums of squares of the
+// rank-k' fit (cpp:161-166) are s_j - sum_{l <= k'} (d_l V_jl)^2 for EVERY k' at once.  k_prefix_sumlog forms
+// sumlog[k'-1] = sum_j log((s_j - q_j(k')) / n) for k' = 1 .. kMax: one thread per variable walks the ranks with a
+// running q_j; the sums over variables are two-stage (per-CTA partials in shared memory, then a fixed-order sum over
+// the CTAs), so the result is bit-stable.  The host uses these values to steer the bisection (api.cu) and falls back
+// on the explicit residual wherever two criteria are too close to call.
+constexpr int PL_CHUNK = 32;     // ranks per shared-memory round
+__global__ void __launch_bounds__(RB)
+k_prefix_sumlog(const double* __restrict__ V, int64_t ldv, const double* __restrict__ d, const double* __restrict__ s, int64_t p,
+                int kMax, double inv_n, double* __restrict__ part /* [gridDim.x][kMax] */) {
+  __shared__ double sh[RB / 32][PL_CHUNK];
+  const int64_t j = blockIdx.x * static_cast<int64_t>(RB) + threadIdx.x;
+  const bool in = j < p;
+  const double sj = in ? s[j] : 0.0;
+  double q = 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int l0 = 0; l0 < kMax; l0 += PL_CHUNK) {
+    const int nl = kMax - l0 < PL_CHUNK ? kMax - l0 : PL_CHUNK;
+    for (int l = 0; l < nl; ++l) {
+      double v = 0.0;
+      if (in) {
+        const double c = V[j + ldv * (l0 + l)] * d[l0 + l];
+        q = fma(c, c, q);
+        v = log((sj - q) * inv_n);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sh[warp][l] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nl) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < RB / 32; ++w) t += sh[w][threadIdx.x];
+      part[static_cast<int64_t>(blockIdx.x) * kMax + l0 + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+// out[l] = sum over the CTAs of part[cta][l], in CTA order
+__global__ void __launch_bounds__(RB) k_prefix_sum_parts(const double* __restrict__ part, int64_t nparts, int kMax, double* __restrict__ out) {
+  const int l = blockIdx.x * RB + threadIdx.x;
+  if (l >= kMax) return;
+  double t = 0.0;
+  for (int64_t c = 0; c < nparts; ++c) t += part[c * kMax + l];
+  out[l] = t;
+}
+
+// max_jl |T_jl - d_l V_jl| and max_jl |d_l V_jl|: is Y'U = V diag(d)?
+struct AbsDiffTV {
+  const double* T; int64_t ldt; const double* V; int64_t ldv; const double* d; int64_t p;
+  __device__ double2 operator()(int64_t idx) const {
+    const int64_t l = idx / p, j = idx - l * p;
+    const double c = V[j + ldv * l] * d[l];
+    return make_double2(fabs(T[j + ldt * l] - c), fabs(c));
+  }
+};
+// max |A - I| of a k x k matrix
+struct AbsDiffEye {
+  const double* A; int64_t k;
+  __device__ double2 operator()(int64_t idx) const {
+    const int64_t c = idx / k, r = idx - c * k;
+    return make_double2(fabs(A[idx] - (r == c ? 1.0 : 0.0)), 1.0);
+  }
+};
+template <typename F>
+__global__ void __launch_bounds__(RB) k_max2(F f, int64_t len, double* __restrict__ part) {
+  __shared__ double sh[2][RB / 32];
+  double a = 0.0, b = 0.0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(RB) + threadIdx.x; i < len; i += static_cast<int64_t>(gridDim.x) * RB) {
+    const double2 v = f(i);
+    a = fmax(a, v.x); b = fmax(b, v.y);       // (a NaN difference must not vanish: checked below)
+    if (v.x != v.x) a = INFINITY;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < RB / 32; ++w) { a = fmax(a, sh[0][w]); b = fmax(b, sh[1][w]); }
+    part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+  }
+}
+template <typename F>
+int max2_to_host(fable_ctx* ctx, F f, int64_t len, double* m0, double* m1) {
+  DevBuf part;
+  FB_CUDA(ctx, part.alloc(2 * RGRID * sizeof(double)));
+  k_max2<<<RGRID, RB, 0, ctx->stream>>>(f, len, part.d());
+  FB_LAUNCHED(ctx);
+  double h[2 * RGRID];
+  FB_CUDA(ctx, cudaMemcpyAsync(h, part.d(), sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *m0 = 0.0; *m1 = 0.0;
+  for (int i = 0; i < RGRID; ++i) { *m0 = h[2 * i] > *m0 ? h[2 * i] : *m0; *m1 = h[2 * i + 1] > *m1 ? h[2 * i + 1] : *m1; }
+  return FABLE_OK;
+}
+
 // sig = resid/n ; G0 = coef * c ; gnd = g0d0 + s - imp*q ; sigmahat = gnd/(gamma_n-2)
 __global__ void __launch_bounds__(256)
 k_finish(const double* __restrict__ c, int64_t ldc, const double* __restrict__ s, const double* __restrict__ q,
@@ -192,6 +290,31 @@ k_sum_partials(const double* __restrict__ part, int64_t nparts, int64_t len, int
 }
 
 }  // namespace
+
+int fb_prefix_sumlog(fable_ctx* ctx, const double* dV, int64_t ldv, const double* dd, const double* ds, int64_t p, int kMax,
+                     int64_t n, double* host_out) {
+  const int64_t nparts = ceil_div(p, RB);
+  DevBuf part, out;
+  FB_CUDA(ctx, part.alloc(static_cast<size_t>(nparts) * kMax * sizeof(double)));
+  FB_CUDA(ctx, out.alloc(static_cast<size_t>(kMax) * sizeof(double)));
+  k_prefix_sumlog<<<static_cast<unsigned>(nparts), RB, 0, ctx->stream>>>(dV, ldv, dd, ds, p, kMax, 1.0 / static_cast<double>(n), part.d());
+  FB_LAUNCHED(ctx);
+  k_prefix_sum_parts<<<static_cast<unsigned>(ceil_div(kMax, RB)), RB, 0, ctx->stream>>>(part.d(), nparts, kMax, out.d());
+  FB_LAUNCHED(ctx);
+  FB_CUDA(ctx, cudaMemcpyAsync(host_out, out.d(), static_cast<size_t>(kMax) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+int fb_svd_consistency(fable_ctx* ctx, const double* dT, int64_t ldt, const double* dV, int64_t ldv, const double* dd, int64_t p,
+                       int k, double* max_diff, double* max_abs) {
+  return max2_to_host(ctx, AbsDiffTV{dT, ldt, dV, ldv, dd, p}, p * static_cast<int64_t>(k), max_diff, max_abs);
+}
+
+int fb_identity_err(fable_ctx* ctx, const double* dA, int64_t k, double* max_diff) {
+  double dummy;
+  return max2_to_host(ctx, AbsDiffEye{dA, k}, k * k, max_diff, &dummy);
+}
 
 int fb_sum_log_scaled(fable_ctx* ctx, const double* d_x, int64_t p, double scale, double* host_out) {
   return reduce_to_host(ctx, LogScaled{d_x, scale}, p, host_out);

@@ -179,6 +179,42 @@ def test_wrappers_on_centred_data(ctx):
     assert relerr_mat(smp["FABLEHyperParameters"]["G"], hyp["G"]) < TOL
 
 
+@pytest.mark.parametrize("n,p,k,seed", [(60, 200, 3, 1), (120, 90, 4, 2), (200, 1000, 7, 3), (80, 300, 1, 4), (300, 400, 12, 5)])
+def test_rank_search_steering_takes_the_reference_branches(ctx, n, p, k, seed, monkeypatch):
+    """The rank search is steered by the all-rank criterion (one pass over V when (U, V, d) is a consistent SVD of Y) and
+    decided by the explicit residual where two values are close: window and rank must equal the oracle's replay of
+    cpp:215-341 and the all-explicit path (FABLE_B200_RANK_FAST=0), for maxProp 0.5 and 0.95, with the caller's SVD."""
+    Y, u, d, v = _svd_inputs(n, p, k, 100 + seed)
+    for maxProp in (0.5, 0.95):
+        kMax = orc.kmax_rule(d, maxProp)
+        want_k = orc.rank_estimator(Y, u, v, d, kMax)
+        want_w = orc.bisection(1, kMax, lambda kk: orc.criterion(kk, Y, u, v, d))
+        for fast in ("1", "0"):
+            monkeypatch.setenv("FABLE_B200_RANK_FAST", fast)
+            assert fb.CPPRankEstimator(Y, u, v, d, kMax, ctx=ctx) == want_k, (maxProp, fast)
+            w = fb.CPPBisectionRecursion(1, kMax, Y, u, v, d, ctx=ctx)
+            np.testing.assert_array_equal(w, np.asarray(want_w, dtype=float))
+    monkeypatch.delenv("FABLE_B200_RANK_FAST")
+
+
+def test_rank_search_with_inconsistent_svd_inputs(ctx):
+    """At the CPP* boundary U, V, d are the caller's: if they are NOT a singular value decomposition of Y the shortcut does
+    not apply (the library checks Y'U = V diag(d) and U'U = I) and every criterion is the explicit residual of cpp:161-166,
+    as in the reference -- whatever the inputs mean."""
+    n, p, k = 70, 180, 3
+    Y, u, d, v = _svd_inputs(n, p, k, 77)
+    rng = np.random.default_rng(3)
+    cases = {"rotated U": (np.asfortranarray(u @ np.linalg.qr(rng.standard_normal((n, n)))[0]), v, d),
+             "noisy V": (u, np.asfortranarray(v + 0.05 * rng.standard_normal(v.shape)), d),
+             "scaled d": (u, v, d * np.linspace(1.3, 0.7, d.size)),
+             "SVD of another matrix": orc.svd_thin(synth.factor_data(n, p, k, rep=78))[0:1] + (v, d)}
+    for name, (uu, vv, dd) in cases.items():
+        kMax = 40
+        assert fb.CPPRankEstimator(Y, uu, vv, dd, kMax, ctx=ctx) == orc.rank_estimator(Y, uu, vv, dd, kMax), name
+        for kk in (1, 5, 40):
+            assert abs(fb.CPPCriterionFunction(kk, Y, uu, vv, dd, ctx=ctx) / orc.criterion(kk, Y, uu, vv, dd) - 1) < TOL, name
+
+
 # ---- C1: n=500, p=1000, k=10 (BASELINE.json configs[0]) end to end vs the oracle ------------------
 @pytest.fixture(scope="module")
 def c1():
