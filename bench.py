@@ -416,7 +416,15 @@ def run_draws(args, w, wname, job):
         reduce_check = job.max_over_ranks(worst)
 
     # ---- timed region 2: end to end through the C-ABI with host buffers --------------------------------
-    mc = args.e2e_mc or (w["e2e_mc"] if world == 1 else max(256, w["e2e_mc"] // 2))   # per rank; pinned host memory scales with ranks
+    mc = args.e2e_mc or w["e2e_mc"]                   # per rank (weak scaling, like `value`); pinned host memory scales with the ranks
+    try:                                               # ... so it is halved where the host could not hold two copies of the buffers
+        import psutil
+        need = 8.0 * world * (mc * (kEst + 1) * p) + 16.0 * p * p
+        while mc > 512 and 2.5 * need > psutil.virtual_memory().available:
+            mc //= 2; need = 8.0 * world * (mc * (kEst + 1) * p) + 16.0 * p * p
+    except Exception:
+        pass
+    mc = int(job.max_over_ranks(-float(mc)) * -1)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     ctx.set_psi_ring(slots)
     del ring
@@ -582,7 +590,7 @@ def run_tiles(args, w, wname, job):
     entries, nt = _slice_entries(p, lo, hi)
     assert nt == fb.api.tile_count(p, lo, hi)
     slot_doubles = 2 * nt * 4096
-    B = args.batch or max(1, min(32, int(RING_BUDGET_GB * 1e9 // (8 * slot_doubles))))
+    B = args.batch or max(1, min(48, int(RING_BUDGET_GB * 1e9 // (8 * slot_doubles))))
     B = int(job.max_over_ranks(-float(B)) * -1)                     # the same batch everywhere (min over ranks)
     ring = torch.empty(B * slot_doubles, dtype=torch.float64, device=dev)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)

@@ -607,6 +607,19 @@ class Posterior:
         self.ctx.check(_load().fable_posterior_sample_range(self._h, _i64(MC), _i64(m0), _i64(MC), _ptr(g), _ptr(zz),
                                                             _ptr(out_lambda), _ptr(out_sigma), C.c_int(1 if psi_pass else 0)))
 
+    def post_processing(self, MC, alpha, SelectedIndices=None, m0=0, gam=None, z=None):
+        """CPPCCFABLEPostProcessing / CCFABLEPostProcessingSubmatrix (cpp:631-818) on RESIDENT draws m0 .. m0+MC-1: entry-wise
+        mean and (alpha/2, 1-alpha/2) sample quantiles of Psi with the draws generated and consumed on the device."""
+        sel = None if SelectedIndices is None else np.ascontiguousarray(SelectedIndices, dtype=np.int64)
+        n = self.p if sel is None else sel.size
+        g = None if gam is None else np.ascontiguousarray(gam, dtype=np.float64)
+        zz = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        M = np.empty((n, n), order="F"); Lo = np.empty((n, n), order="F"); Up = np.empty((n, n), order="F")
+        self.ctx.check(_load().fable_posterior_post_processing(
+            self._h, _i64(MC), _i64(m0), C.c_double(alpha), None if sel is None else sel.ctypes.data_as(C.POINTER(C.c_int64)),
+            _i64(n), _ptr(g), _ptr(zz), _ptr(M), _ptr(Lo), _ptr(Up)))
+        return {"PostMeanMatrix": M, "LowerQuantileMatrix": Lo, "UpperQuantileMatrix": Up}
+
     def accum_dev(self):
         """(dev_sum, dev_sumsq, count): the compact upper tiles of the slice, `count` doubles each -- what the NCCL sum
         of the draw partition reduces, as it is."""

@@ -16,6 +16,8 @@
 #include "tiles.cuh"
 
 // ---- device block cache (see common.cuh) ----------------------------------------------------------
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <unordered_map>
 namespace {
@@ -214,6 +216,7 @@ int check_dims(fable_ctx* ctx, const void* Y, int64_t n, int64_t p, const void* 
 
 int upload_bytes(fable_ctx* ctx, void* dptr, const void* h, size_t bytes);
 int copy_threads();
+int download_2d(fable_ctx* ctx, double* h, int64_t hld, const double* dptr, int64_t rows, int64_t ncols);
 
 int upload(fable_ctx* ctx, DevBuf& b, const double* h, size_t count) {
   FB_CUDA(ctx, b.alloc(count * sizeof(double)));
@@ -434,17 +437,71 @@ int row_posterior(fable_ctx* ctx, const Inputs& in, int k, double gamma0, double
 constexpr size_t kStageBytes = size_t(64) << 20;
 constexpr size_t kFastCopyMin = size_t(16) << 20;
 
+// Host copy workers: a small persistent pool (spawning threads per copy costs ~50 us each, which matters when a p x p result
+// leaves as hundreds of 8 MB blocks).  run(n, fn) executes fn(0) .. fn(n-1) on the workers and the calling thread.
+class CopyPool {
+ public:
+  static CopyPool& get() { static CopyPool* p = new CopyPool; return *p; }     // leaked on purpose (no static-destruction order)
+  void run(int njobs, const std::function<void(int)>& fn) {
+    if (njobs <= 1) { if (njobs == 1) fn(0); return; }
+    std::unique_lock<std::mutex> call(call_mu_);                 // one parallel section at a time
+    ensure(njobs - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn; njobs_ = njobs; next_ = 0; pending_ = njobs; ++gen_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+ private:
+  void ensure(int n) {
+    while (static_cast<int>(workers_.size()) < n && workers_.size() < 64)
+      workers_.emplace_back([this] {
+        uint64_t seen = 0;
+        for (;;) {
+          {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+          }
+          work();
+        }
+      }), workers_.back().detach();
+  }
+  void work() {
+    for (;;) {
+      int j;
+      const std::function<void(int)>* f;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!fn_ || next_ >= njobs_) return;
+        j = next_++; f = fn_;
+      }
+      (*f)(j);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_cv_.notify_all();
+    }
+  }
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int njobs_ = 0, next_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+};
+
 void parallel_memcpy(char* dst, const char* src, size_t bytes, int nthreads) {
   if (nthreads <= 1 || bytes < (size_t(4) << 20)) { std::memcpy(dst, src, bytes); return; }
-  std::vector<std::thread> th;
   const size_t per = ((bytes + nthreads - 1) / nthreads + 4095) & ~size_t(4095);
-  for (int t = 0; t < nthreads; ++t) {
+  const int njobs = static_cast<int>((bytes + per - 1) / per);
+  CopyPool::get().run(njobs, [=](int t) {
     const size_t off = per * t;
-    if (off >= bytes) break;
     const size_t len = bytes - off < per ? bytes - off : per;
-    th.emplace_back([=] { std::memcpy(dst + off, src + off, len); });
-  }
-  for (auto& x : th) x.join();
+    std::memcpy(dst + off, src + off, len);
+  });
 }
 
 // A freshly allocated result vector is untouched virtual memory: the copy-out pays one page fault (and one kernel page
@@ -503,6 +560,50 @@ int download(fable_ctx* ctx, double* h, const double* dptr, size_t count) {
     FB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[i & 1]));
     const size_t off = i * kStageBytes, len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
     parallel_memcpy(dst + off, static_cast<const char*>(ctx->stage[i & 1]), len, nthreads);
+  }
+  return FABLE_OK;
+}
+
+// Strided device -> host: `ncols` columns of `rows` doubles, contiguous on the device, to host columns `hld` doubles
+// apart (a block of a column-major matrix).  Pinned destinations take one 2-D copy; pageable ones go through the pinned
+// staging and are scattered by the host threads (a 2-D copy into pageable memory is a synchronous staged copy per row).
+int download_2d(fable_ctx* ctx, double* h, int64_t hld, const double* dptr, int64_t rows, int64_t ncols) {
+  if (!h || rows <= 0 || ncols <= 0) return FABLE_OK;
+  if (hld == rows) return download(ctx, h, dptr, static_cast<size_t>(rows) * ncols);
+  const int nthreads = copy_threads();
+  if (!is_pageable(h) || nthreads <= 0) {
+    FB_CUDA(ctx, cudaMemcpy2DAsync(h, static_cast<size_t>(hld) * sizeof(double), dptr, static_cast<size_t>(rows) * sizeof(double),
+                                   static_cast<size_t>(rows) * sizeof(double), static_cast<size_t>(ncols), cudaMemcpyDeviceToHost, ctx->stream));
+    return FABLE_OK;
+  }
+  for (int s = 0; s < 2; ++s)
+    if (!ctx->stage[s]) {
+      FB_CUDA(ctx, cudaHostAlloc(&ctx->stage[s], kStageBytes, cudaHostAllocDefault));
+      FB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[s], cudaEventDisableTiming));
+    }
+  const int64_t cols_per = static_cast<int64_t>(kStageBytes / (static_cast<size_t>(rows) * sizeof(double)));
+  FB_REQUIRE(ctx, cols_per >= 1, "download_2d: a column exceeds the staging buffer");
+  for (int s = 0; s < 2; ++s) FB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[s]));
+  const int64_t nchunks = ceil_div(ncols, cols_per);
+  auto issue = [&](int64_t i) -> cudaError_t {
+    const int64_t c0 = i * cols_per, nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
+    cudaError_t e = cudaMemcpyAsync(ctx->stage[i & 1], dptr + c0 * rows, static_cast<size_t>(nc) * rows * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(ctx->stage_ev[i & 1], ctx->stream);
+  };
+  FB_CUDA(ctx, issue(0));
+  for (int64_t i = 0; i < nchunks; ++i) {
+    if (i + 1 < nchunks) FB_CUDA(ctx, issue(i + 1));
+    FB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[i & 1]));
+    const int64_t c0 = i * cols_per, nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
+    const double* src = static_cast<const double*>(ctx->stage[i & 1]);
+    int nt = static_cast<int>((static_cast<size_t>(nc) * rows * sizeof(double)) >> 20);      // >= 1 MB per worker
+    nt = nt < 1 ? 1 : (nt > nthreads ? nthreads : nt);
+    if (nt > nc) nt = static_cast<int>(nc);
+    CopyPool::get().run(nt, [=](int t) {
+      for (int64_t c = t; c < nc; c += nt) std::memcpy(h + (c0 + c) * hld, src + c * rows, static_cast<size_t>(rows) * sizeof(double));
+    });
   }
   return FABLE_OK;
 }
@@ -568,6 +669,9 @@ struct fable_posterior {
   DevBuf acc_sum, acc_sq;       // compact upper tiles of the slice [tile_begin, tile_end) (tiles.cuh): acc_tiles x 4096 doubles
   int64_t acc_tiles = 0;
   DevBuf hyp_G0;                // unshrunk G0 of FABLEHyperParameters (cpp:390), kept by fable_wrapper_sampler_begin
+  DevBuf sb_stage;              // dense blocks of super-blocks on their way to the host (accum_fetch_superblocks)
+  cudaEvent_t sb_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  ~fable_posterior() { for (cudaEvent_t e : sb_ev) if (e) cudaEventDestroy(e); }
   DevBuf cc_gdiag;              // entry-wise coverage correction (f3): diag(G0 G0'); NULL = off
   bool cc = false;
   int64_t tile_begin = 0, tile_end = 0;   // tile_end == 0: every tile
@@ -680,8 +784,13 @@ int fable_ctx_create(int device, uint64_t seed, fable_ctx** out) {
   fable_ctx* ctx = new (std::nothrow) fable_ctx();
   if (!ctx) { g_create_error = "out of host memory"; return FABLE_ERR_NOMEM; }
   ctx->device = device; ctx->seed = seed; ctx->sms = prop.multiProcessorCount;
+  // the copy stream outranks the main stream: its small kernels (sample layouts, dense blocks on their way to the host) are
+  // dispatched as soon as an SM has room instead of queueing behind the covariance kernel's backlog of CTAs
+  int prio_lo = 0, prio_hi = 0;
+  cudaSetDevice(device);
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      (e = cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
     return FABLE_ERR_CUDA;
@@ -1121,7 +1230,8 @@ static int ensure_accum(fable_posterior* post) {
 }
 
 static int draw_batch_impl(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots, bool compact,
-                           int accumulate, const double* dev_gam, const double* dev_z) {
+                           int accumulate, const double* dev_gam, const double* dev_z, int64_t launch_begin = 0,
+                           int64_t launch_end = 0) {
   if (!post) return FABLE_ERR_INVALID;
   fable_ctx* ctx = post->ctx;
   FB_REQUIRE(ctx, B >= 1 && m0 >= 0, "draw_batch: need B >= 1 and m0 >= 0");
@@ -1149,8 +1259,16 @@ static int draw_batch_impl(fable_posterior* post, int64_t m0, int B, double* dev
   a.Lw = post->cc ? post->Lw.d() : draws; a.s2w = post->s2w.d(); a.pp = post->pp; a.p = post->p; a.k = post->k; a.KP = post->KP;
   a.B = B; a.psi = dev_psi; a.psi_slots = psi_slots; a.slot0 = 0; a.out_compact = compact;
   a.acc_sum = accumulate ? post->acc_sum.d() : nullptr; a.acc_sq = accumulate ? post->acc_sq.d() : nullptr;
-  a.tile_begin = post->tile_begin; a.tile_end = post->tile_end;
+  a.store_begin = post->tile_begin; a.store_end = post->tile_end;
+  a.tile_begin = launch_begin; a.tile_end = launch_end;
   return fb_psi(ctx, a);
+}
+
+int fable_posterior_draw_batch_range(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots, int accumulate,
+                                     const double* dev_gam, const double* dev_z, int64_t t_begin, int64_t t_end) {
+  if (!post) return FABLE_ERR_INVALID;
+  FB_REQUIRE(post->ctx, t_end > t_begin && t_begin >= 0, "draw_batch_range: empty launch range");
+  return draw_batch_impl(post, m0, B, dev_psi, psi_slots, false, accumulate, dev_gam, dev_z, t_begin, t_end);
 }
 
 int fable_posterior_draw_batch(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots,
@@ -1347,6 +1465,56 @@ int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sums
   return FABLE_OK;
 }
 
+// The dense blocks of the super-blocks [sb_begin, sb_end) of the enumeration (16 x 16 tiles = up to 1024 x 1024 entries
+// each, both the block and its mirror image) into the caller's dense p x p host matrices; everything else is left
+// untouched.  A range of super-blocks is a contiguous range of accumulator tiles, so the tail of a sampling run can
+// be processed chunk by chunk and every finished chunk can cross PCIe while the next one still computes (sampler
+// below).  Runs on the context's CURRENT stream; returns when the host matrices hold the blocks.
+int fable_posterior_accum_fetch_superblocks(fable_posterior* post, int64_t sb_begin, int64_t sb_end, double* sum, double* sumsq) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  FB_TRY(ensure_accum(post));
+  const int64_t p = post->p, slots = fbt::n_slots(p), per_sb = fbt::SB * fbt::SB;
+  const int64_t s_lo = post->tile_begin, s_hi = post->tile_end > 0 ? post->tile_end : slots;
+  FB_REQUIRE(ctx, sb_begin >= 0 && sb_begin <= sb_end && sb_end * per_sb <= slots, "fetch_superblocks: range out of bounds");
+  FB_REQUIRE(ctx, sb_begin * per_sb >= s_lo && sb_end * per_sb <= s_hi, "fetch_superblocks: range outside the posterior's tile slice");
+  const int nT = static_cast<int>(fbt::n_tiles(p));
+  const int64_t cbase = fbt::cidx(s_lo, nT);
+  const int64_t span = static_cast<int64_t>(fbt::SB) * fbt::TILE, blk = span * span;
+  // staging: NSET sets of (direct, mirror) blocks per accumulator, reused round-robin behind events; owned by the
+  // posterior (a block taken from the device cache here would first wait for everything queued on the main stream)
+  constexpr int NSET = 4;
+  DevBuf& stage = post->sb_stage;
+  if (!stage.ptr) {
+    FB_CUDA(ctx, stage.alloc(static_cast<size_t>(NSET) * 4 * blk * sizeof(double)));
+    for (auto& e : post->sb_ev) FB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  cudaEvent_t* ev = post->sb_ev;
+  int rc = FABLE_OK;
+  for (int64_t sb = sb_begin; sb < sb_end && rc == FABLE_OK; ++sb) {
+    int sI, sJ;
+    fbt::tri_of(sb, sI, sJ);
+    const int64_t r0 = sI * span, c0 = sJ * span;
+    if (c0 >= p) continue;
+    const int64_t nr = p - r0 < span ? p - r0 : span, nc = p - c0 < span ? p - c0 : span;
+    const int set = static_cast<int>((sb - sb_begin) % NSET);
+    if (sb - sb_begin >= NSET) FB_CUDA(ctx, cudaEventSynchronize(ev[set]));       // its previous copies have left
+    for (int which = 0; which < 2 && rc == FABLE_OK; ++which) {
+      double* h = which ? sumsq : sum;
+      if (!h) continue;
+      double* d_dir = stage.d() + (static_cast<size_t>(set) * 4 + which * 2) * blk;
+      double* d_mir = d_dir + blk;
+      rc = fb_superblock_to_dense(ctx, which ? post->acc_sq.d() : post->acc_sum.d(), cbase, p, sb, d_dir, d_mir);
+      if (rc == FABLE_OK) rc = download_2d(ctx, h + r0 + p * c0, p, d_dir, nr, nc);
+      if (rc == FABLE_OK && sI != sJ) rc = download_2d(ctx, h + c0 + p * r0, p, d_mir, nc, nr);
+    }
+    if (rc == FABLE_OK) FB_CUDA(ctx, cudaEventRecord(ev[set], ctx->stream));
+  }
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return rc;
+}
+
 // the compact tiles as they are (acc_tiles x 4096 doubles each): the raw share of a rank of the tile partition
 int fable_posterior_accum_fetch_tiles(fable_posterior* post, double* sum_tiles, double* sumsq_tiles) {
   if (!post) return FABLE_ERR_INVALID;
@@ -1385,8 +1553,14 @@ int fable_sampler(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double 
 // covariance pass adds the same draws into the posterior's device-resident sum / sumsq accumulators (and materialises
 // them into the context's ring when one is set) -- nothing p x p crosses PCIe here, so the ranks of a draw partition can
 // sum their accumulators on the device before anyone fetches them.
+//
+// fetch_sum / fetch_sq (single-device callers that want the dense sums on the host at the end): the last ~256 draws are
+// then processed CHUNK-major instead of batch-major -- all of their batches for the first group of super-blocks, then for
+// the next ... -- so that the accumulator tiles of a finished group are final while the following groups still compute,
+// and their dense blocks cross PCIe (copy stream) behind that work instead of after it.
 static int sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t ldm, const double* gam_inj, const double* z_inj,
-                        double* LambdaSamples, double* SigmaSqSamples, bool psi_pass) {
+                        double* LambdaSamples, double* SigmaSqSamples, bool psi_pass, double* fetch_sum = nullptr,
+                        double* fetch_sq = nullptr) {
   fable_ctx* ctx = post->ctx;
   const int64_t p = post->p;
   const int kEst = post->k;
@@ -1394,6 +1568,10 @@ static int sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t l
   // then generated and copied out on the copy stream, so their D2H traffic (8 p (k+1) bytes per draw)
   // overlaps the covariance kernels.  Both read the same immutable row posterior.
   DevBuf dgam, dz;
+  struct TailChunk { cudaEvent_t ev; int64_t sb0, sb1; };
+  struct TailEvents : std::vector<TailChunk> {
+    ~TailEvents() { for (auto& t : *this) cudaEventDestroy(t.ev); }
+  } tail_events;
   if (psi_pass) {
     if (gam_inj) {
       FB_TRY(upload(ctx, dgam, gam_inj, static_cast<size_t>(MC) * p));
@@ -1414,15 +1592,40 @@ static int sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t l
       }
     }
     const int B = ctx->ring_slots > 0 ? (ctx->ring_slots < 64 ? ctx->ring_slots : 64) : 32;
-    for (int64_t b0 = 0; b0 < MC; b0 += B) {
+    const int64_t nbatch = ceil_div(MC, B);
+    // tail: the batches of the last ~256 draws, run chunk-major when the caller fetches the sums (FABLE_B200_TAIL_DRAWS=0: off)
+    int64_t tail = 0;
+    if (fetch_sum && post->tile_end == 0) {
+      const char* e = getenv("FABLE_B200_TAIL_DRAWS");
+      const int64_t td = e ? atoll(e) : 256;
+      tail = td <= 0 ? 0 : ceil_div(td, B);
+      if (tail > nbatch) tail = nbatch;
+      // the fetch staging is allocated before anything is queued (the call drains the stream)
+      if (tail > 0 && !post->sb_stage.ptr) FB_TRY(fable_posterior_accum_fetch_superblocks(post, 0, 0, fetch_sum, fetch_sq));
+    }
+    auto batch = [&](int64_t bi, int64_t lb, int64_t le) -> int {
+      const int64_t b0 = bi * B;
       const int nb = static_cast<int>(MC - b0 < B ? MC - b0 : B);
-      FB_TRY(fable_posterior_draw_batch(post, m0 + b0, nb, ctx->ring_slots > 0 ? ctx->ring : nullptr,
-                                        ctx->ring_slots, 1,
-                                        gam_inj ? dgam.d() + b0 * p : nullptr,
-                                        gam_inj ? dz.d() + b0 * p * kEst : nullptr));
+      return draw_batch_impl(post, m0 + b0, nb, ctx->ring_slots > 0 ? ctx->ring : nullptr, ctx->ring_slots, false, 1,
+                             gam_inj ? dgam.d() + b0 * p : nullptr, gam_inj ? dz.d() + b0 * p * kEst : nullptr, lb, le);
+    };
+    for (int64_t bi = 0; bi < nbatch - tail; ++bi) {
+      FB_TRY(batch(bi, 0, 0));
       if (ctx->poll && ctx->poll(ctx->poll_user)) {
         cudaStreamSynchronize(ctx->stream);
         return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");
+      }
+    }
+    if (tail > 0) {
+      const int64_t nsb = fbt::n_slots(p) / (fbt::SB * fbt::SB);
+      const int64_t nchunk = nsb < 12 ? nsb : 12;
+      for (int64_t c = 0; c < nchunk; ++c) {
+        const int64_t sb0 = nsb * c / nchunk, sb1 = nsb * (c + 1) / nchunk;
+        for (int64_t bi = nbatch - tail; bi < nbatch; ++bi) FB_TRY(batch(bi, sb0 * fbt::SB * fbt::SB, sb1 * fbt::SB * fbt::SB));
+        cudaEvent_t ev;
+        FB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        tail_events.push_back({ev, sb0, sb1});
+        FB_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
       }
     }
   }
@@ -1432,10 +1635,17 @@ static int sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t l
       explicit StreamSwap(fable_ctx* cx) : c(cx), main(cx->stream) { c->stream = c->copy_stream; }
       ~StreamSwap() { c->stream = main; }
     } swap(ctx);
-    const int rc = fable_posterior_samples(post, m0, MC, ldm, LambdaSamples, SigmaSqSamples, gam_inj, z_inj);
+    int rc = fable_posterior_samples(post, m0, MC, ldm, LambdaSamples, SigmaSqSamples, gam_inj, z_inj);
+    // finished groups of super-blocks leave on the copy stream while the main stream works on the following ones
+    for (size_t c = 0; c < tail_events.size() && rc == FABLE_OK; ++c) {
+      const cudaError_t e = cudaEventSynchronize(tail_events[c].ev);
+      if (e != cudaSuccess) { rc = ctx->fail(FABLE_ERR_CUDA, std::string("tail event: ") + cudaGetErrorString(e)); break; }
+      rc = fable_posterior_accum_fetch_superblocks(post, tail_events[c].sb0, tail_events[c].sb1, fetch_sum, fetch_sq);
+    }
     if (rc != FABLE_OK) { cudaStreamSynchronize(swap.main); return rc; }
   }
   if (psi_pass) FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // dgam / dz go out of scope
+  if (psi_pass && fetch_sum && tail_events.empty()) FB_TRY(fable_posterior_accum_fetch(post, fetch_sum, fetch_sq));
   return FABLE_OK;
 }
 
@@ -1446,8 +1656,7 @@ static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_
   fable_ctx* ctx = post->ctx;
   FB_TRY(fable_posterior_fixed_outputs(post, SigmaPostMean, SigmaPlugIn, tausq, nullptr));
   if (psi_sum) FB_TRY(fable_posterior_accum_reset(post));
-  FB_TRY(sample_range(post, MC, m0, MC, gam_inj, z_inj, LambdaSamples, SigmaSqSamples, psi_sum != nullptr));
-  if (psi_sum) FB_TRY(fable_posterior_accum_fetch(post, psi_sum, psi_sumsq));
+  FB_TRY(sample_range(post, MC, m0, MC, gam_inj, z_inj, LambdaSamples, SigmaSqSamples, psi_sum != nullptr, psi_sum, psi_sumsq));
   if (G) FB_TRY(rankk_cov_to_host(ctx, post->rp.G0.d(), post->p, nullptr, post->p, post->k, G));   // cpp:627
   return FABLE_OK;
 }
@@ -1627,11 +1836,85 @@ int fable_post_processing(fable_ctx* ctx, const double* LambdaSamples, const dou
     }
   }
   FB_CUDA(ctx, cudaMemcpyAsync(dI.ptr, idx.data(), static_cast<size_t>(S) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-  FB_TRY(fb_post_processing(ctx, dL.d(), dS.d(), static_cast<const int64_t*>(dI.ptr), MC, k, S, alpha, dM.d(), dLo.d(), dUp.d()));
+  // tile-resident selection (post_tiles.cu) wherever its shape limits allow; the per-pair kernels of post.cu otherwise, and
+  // for the (theoretical) entries the selection reports as undecidable
+  const bool tiles_on = !(getenv("FABLE_B200_POST_TILES") && atoi(getenv("FABLE_B200_POST_TILES")) == 0);   // 0: per-pair kernels (A/B, tests)
+  int unresolved = -1;
+  if (tiles_on && fb_post_tiles_supported(MC, k)) {
+    const int64_t pps = round_up(S, 64);
+    const int KP = static_cast<int>(round_up(k, 4));
+    DevBuf Lw, s2w;
+    FB_CUDA(ctx, Lw.alloc(static_cast<size_t>(MC) * KP * pps * sizeof(double)));
+    FB_CUDA(ctx, s2w.alloc(static_cast<size_t>(MC) * pps * sizeof(double)));
+    FB_TRY(fb_ref_to_work(ctx, dL.d(), dS.d(), S, k, MC, pps, KP, Lw.d(), s2w.d()));
+    FB_TRY(fb_post_tiles(ctx, Lw.d(), s2w.d(), static_cast<const int64_t*>(dI.ptr), MC, KP, S, pps, alpha, dM.d(), dLo.d(), dUp.d(),
+                         &unresolved));
+  }
+  if (unresolved != 0)
+    FB_TRY(fb_post_processing(ctx, dL.d(), dS.d(), static_cast<const int64_t*>(dI.ptr), MC, k, S, alpha, dM.d(), dLo.d(), dUp.d()));
   FB_TRY(download(ctx, PostMean, dM.d(), static_cast<size_t>(S) * S));
   FB_TRY(download(ctx, Lower, dLo.d(), static_cast<size_t>(S) * S));
   FB_TRY(download(ctx, Upper, dUp.d(), static_cast<size_t>(S) * S));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+// f1 without the 16 GB round trip: the draws never leave the device.  Draws m0 .. m0 + MC - 1 of the resident posterior are
+// generated in the working layout (native stream, or injected draws), and the tile-resident selection forms every entry of
+// Psi_m on the fly -- the consumer of the block-wise covariance formation that the reference reaches by storing MC x k p
+// samples and looping over the pairs (cpp:631-713).
+int fable_posterior_post_processing(fable_posterior* post, int64_t MC, int64_t m0, double alpha, const int64_t* selected, int64_t S,
+                                    const double* gam_inj, const double* z_inj, double* PostMean, double* Lower, double* Upper) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, PostMean && Lower && Upper, "post_processing: NULL output");
+  FB_REQUIRE(ctx, MC >= 1 && m0 >= 0, "post_processing: need MC >= 1 and m0 >= 0");
+  FB_REQUIRE(ctx, (gam_inj == nullptr) == (z_inj == nullptr), "injected draws need both gam and z");
+  FB_REQUIRE(ctx, fb_post_tiles_supported(MC, post->k), "post_processing on resident draws: needs MC <= 65535 and k <= 32 "
+                                                        "(use fable_post_processing on stored samples beyond that)");
+  const int64_t p = post->p, pp = post->pp;
+  const int k = post->k, KP = post->KP;
+  if (!selected) S = p;
+  FB_REQUIRE(ctx, S >= 1, "post_processing: empty selection");
+  std::vector<int64_t> idx(S);
+  for (int64_t i = 0; i < S; ++i) {
+    idx[i] = selected ? selected[i] - 1 : i;                          // 1-based R indices (cpp:721)
+    FB_REQUIRE(ctx, idx[i] >= 0 && idx[i] < p, "post_processing: SelectedIndices out of range");
+  }
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf dgam, dz, Lw, s2w, Lsel, s2sel, dI, dM, dLo, dUp;
+  if (gam_inj) {
+    FB_TRY(upload(ctx, dgam, gam_inj, static_cast<size_t>(MC) * p));
+    FB_TRY(upload(ctx, dz, z_inj, static_cast<size_t>(MC) * p * k));
+  }
+  FB_CUDA(ctx, Lw.alloc(static_cast<size_t>(MC) * KP * pp * sizeof(double)));
+  FB_CUDA(ctx, s2w.alloc(static_cast<size_t>(MC) * pp * sizeof(double)));
+  const SampleArgs sa = sample_args(post, gam_inj ? dgam.d() : nullptr, gam_inj ? dz.d() : nullptr, m0);
+  for (int64_t b0 = 0; b0 < MC; b0 += 32768) {
+    const int nb = static_cast<int>(MC - b0 < 32768 ? MC - b0 : 32768);
+    FB_TRY(fb_sample_work(ctx, sa, m0 + b0, nb, pp, KP, Lw.d() + b0 * KP * pp, s2w.d() + b0 * pp));
+  }
+  FB_CUDA(ctx, dI.alloc(static_cast<size_t>(S) * sizeof(int64_t)));
+  FB_CUDA(ctx, cudaMemcpyAsync(dI.ptr, idx.data(), static_cast<size_t>(S) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  const double* useL = Lw.d(); const double* useS = s2w.d();
+  int64_t pps = pp;
+  if (selected) {
+    pps = round_up(S, 64);
+    FB_CUDA(ctx, Lsel.alloc(static_cast<size_t>(MC) * KP * pps * sizeof(double)));
+    FB_CUDA(ctx, s2sel.alloc(static_cast<size_t>(MC) * pps * sizeof(double)));
+    FB_TRY(fb_gather_work_rows(ctx, Lw.d(), s2w.d(), pp, static_cast<const int64_t*>(dI.ptr), S, pps, KP, MC, Lsel.d(), s2sel.d()));
+    useL = Lsel.d(); useS = s2sel.d();
+  }
+  for (auto* b : {&dM, &dLo, &dUp}) FB_CUDA(ctx, b->alloc(static_cast<size_t>(S) * S * sizeof(double)));
+  int unresolved = 0;
+  FB_TRY(fb_post_tiles(ctx, useL, useS, static_cast<const int64_t*>(dI.ptr), MC, KP, S, pps, alpha, dM.d(), dLo.d(), dUp.d(), &unresolved));
+  if (unresolved != 0)
+    return ctx->fail(FABLE_ERR_NUMERIC, "post_processing: " + std::to_string(unresolved) + " entries have more than 16 distinct draws "
+                                        "closer than 2^-52 of their range; use fable_post_processing on stored samples");
+  FB_TRY(download(ctx, PostMean, dM.d(), static_cast<size_t>(S) * S));
+  FB_TRY(download(ctx, Lower, dLo.d(), static_cast<size_t>(S) * S));
+  FB_TRY(download(ctx, Upper, dUp.d(), static_cast<size_t>(S) * S));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // idx and the device buffers go out of scope
   return FABLE_OK;
 }
 

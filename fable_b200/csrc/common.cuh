@@ -186,7 +186,8 @@ struct PsiArgs {
   double* acc_sq;
   const double* cc_gdiag = nullptr;   // entry-wise coverage correction (f3): diag(G) and sig_hat (length p);
   const double* cc_sig = nullptr;     // Lw then carries G0 in slot 0 ahead of the B draws
-  int64_t tile_begin = 0, tile_end = 0;   // slice of the tile enumeration (tile_end == 0: all tiles)
+  int64_t store_begin = 0, store_end = 0; // slice of the tile enumeration the compact buffers cover (store_end == 0: all tiles)
+  int64_t tile_begin = 0, tile_end = 0;   // tiles this launch processes, inside the storage slice (tile_end == 0: the whole slice)
   int tma_mode = 0;    // set by fb_psi (materialised output): 1 = 4-D whole-tile TMA boxes, 2 = 3-D sub-boxes, 0 = plain stores
   int nT = 0;          // set by fb_psi: tiles per side
   int64_t cbase = 0;   // set by fb_psi: compact index of the slice's first tile
@@ -197,11 +198,26 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a);
 // holds (direct, mirrored) tile pairs (materialised draws) instead of upper tiles only (accumulators).
 int fb_tiles_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t p, int64_t t_lo, int64_t t_hi, int paired, int64_t col0,
                       int64_t ncols, double* d_out);
+// one super-block (16 x 16 tiles, index sb of the enumeration) of compact UPPER tiles (buffer starts at compact index
+// cbase) -> its dense block(s): d_direct = rows [1024 sI, ..) x columns [1024 sJ, ..) (nr x nc, ld nr) and, for an
+// off-diagonal super-block, d_mirror = the transposed block (nc x nr, ld nc); a diagonal super-block gives the full
+// symmetric block in d_direct alone.
+int fb_superblock_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t cbase, int64_t p, int64_t sb, double* d_direct,
+                           double* d_mirror);
 // dst (k rows of pp, zero-padded) <- src (k rows of lds, p valid)
 int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, int KP, double* dst);
 // post.cu: Lsel [S][k][MC], Ssel [S][MC], idx [S] (0-based selected variables); outputs S x S column-major
 int fb_post_processing(fable_ctx* ctx, const double* dLsel, const double* dSsel, const int64_t* d_idx, int64_t MC, int k,
                        int64_t S, double alpha, double* d_mean, double* d_lower, double* d_upper);
+// post_tiles.cu: tile-resident mean + exact type-5 quantiles from draws in the WORKING layout (d_Lw [MC][KP][pp], d_s2w [MC][pp],
+// rows >= S zero, pp a multiple of 64); d_idx [S] = the variable behind every position (diagonal term where two are equal)
+bool fb_post_tiles_supported(int64_t MC, int k);
+int fb_post_tiles(fable_ctx* ctx, const double* d_Lw, const double* d_s2w, const int64_t* d_idx, int64_t MC, int KP, int64_t S,
+                  int64_t pp, double alpha, double* d_mean, double* d_lower, double* d_upper, int* unresolved);
+int fb_ref_to_work(fable_ctx* ctx, const double* dLsel, const double* dSsel, int64_t S, int k, int64_t MC, int64_t pp, int KP,
+                   double* d_Lw, double* d_s2w);
+int fb_gather_work_rows(fable_ctx* ctx, const double* d_Lw, const double* d_s2w, int64_t pp, const int64_t* d_idx, int64_t S,
+                        int64_t pps, int KP, int64_t MC, double* d_Lsel, double* d_s2sel);
 // sampler.cu
 struct SampleArgs {
   const double* G0;    // p x k shrunk loadings mean, leading dimension ldg

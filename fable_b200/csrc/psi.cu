@@ -502,6 +502,34 @@ __global__ void __launch_bounds__(256) k_tiles_to_dense(const double* __restrict
   }
 }
 
+// One super-block of compact upper tiles -> dense block(s); grid (16, 16) = (i, j) tile of the super-block.
+__global__ void __launch_bounds__(256) k_superblock_to_dense(const double* __restrict__ tiles, int nT, int64_t cbase, int64_t p, int sI,
+                                                             int sJ, int64_t nr, int64_t nc, double* __restrict__ direct,
+                                                             double* __restrict__ mirror) {
+  __shared__ double sm[TILE][TILE + 1];
+  const int i = blockIdx.x, j = blockIdx.y;
+  const int I = sI * SB + i, J = sJ * SB + j;
+  if (I > J || J >= nT) return;
+  const double* src = tiles + (fbt::cidx(fbt::slot_of(I, J), nT) - cbase) * fbt::TILE_DOUBLES;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const bool diag_sb = sI == sJ;
+  for (int cc = ty; cc < TILE; cc += 4) {
+    const double v = src[cc * TILE + tx];                          // tile(u = tx, v = cc)
+    sm[cc][tx] = v;
+    const int64_t r = static_cast<int64_t>(i) * TILE + tx, c = static_cast<int64_t>(j) * TILE + cc;
+    if (r < nr && c < nc) direct[r + nr * c] = v;
+  }
+  if (diag_sb && I == J) return;                                   // (a diagonal tile is its own mirror image)
+  __syncthreads();
+  double* out = diag_sb ? direct : mirror;                         // diagonal super-block: lower part of the same block
+  const int64_t ld = diag_sb ? nr : nc;
+  for (int cc = ty; cc < TILE; cc += 4) {
+    // element (row = 64 j + tx, column = 64 i + cc) of the transposed block = tile(u = cc, v = tx)
+    const int64_t r = static_cast<int64_t>(j) * TILE + tx, c = static_cast<int64_t>(i) * TILE + cc;
+    if (r < (diag_sb ? nr : nc) && c < (diag_sb ? nc : nr)) out[r + ld * c] = sm[tx][cc];
+  }
+}
+
 // dst[(l*pp) + j] = (j < p && l < k) ? src[l*lds + j] : 0, l < KP   (zero-padded operand layout)
 __global__ void __launch_bounds__(256) k_pad_rows(const double* __restrict__ src, int64_t lds, int64_t p, int64_t pp,
                                                   int k, int KP, double* __restrict__ dst) {
@@ -598,16 +626,22 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
   FB_REQUIRE(ctx, a.KP % 4 == 0 && a.KP >= a.k, "psi: operand rank must be zero-padded to a multiple of 4");
   FB_REQUIRE(ctx, !mat || a.psi_slots >= a.slot0 + a.B, "psi: one output slot per draw of the batch");
   const int64_t tiles = fbt::n_slots(a.p);    // super-block order, padding slots exit at once
-  // slice of the tile enumeration (multi-GPU partition B: every rank processes all draws for its own tiles; no
-  // collective); compact buffers start at the first tile of the slice
-  int64_t t_lo = 0, t_hi = tiles;
+  // storage slice of the tile enumeration (multi-GPU partition B: every rank processes all draws for its own tiles; no
+  // collective): the compact buffers start at its first tile.  The launch may cover a part of it only (the tail of
+  // fable_sampler runs chunk by chunk so that finished accumulator tiles can leave while the rest still computes).
+  int64_t s_lo = 0, s_hi = tiles;
+  if (a.store_end > 0) {
+    FB_REQUIRE(ctx, a.store_begin >= 0 && a.store_begin <= a.store_end && a.store_end <= tiles, "psi: tile slice out of bounds");
+    s_lo = a.store_begin; s_hi = a.store_end;
+  }
+  int64_t t_lo = s_lo, t_hi = s_hi;
   if (a.tile_end > 0) {
-    FB_REQUIRE(ctx, a.tile_begin >= 0 && a.tile_begin <= a.tile_end && a.tile_end <= tiles, "psi: tile range out of bounds");
+    FB_REQUIRE(ctx, a.tile_begin >= s_lo && a.tile_begin <= a.tile_end && a.tile_end <= s_hi, "psi: launch range outside the tile slice");
     t_lo = a.tile_begin; t_hi = a.tile_end;
   }
-  a.cbase = fbt::cidx(t_lo, a.nT);
-  const int64_t ntile = fbt::cidx(t_hi, a.nT) - a.cbase;          // valid tiles of the slice
-  if (ntile == 0) return FABLE_OK;
+  a.cbase = fbt::cidx(s_lo, a.nT);
+  const int64_t ntile = fbt::cidx(s_hi, a.nT) - a.cbase;          // valid tiles of the storage slice
+  if (ntile == 0 || fbt::cidx(t_hi, a.nT) == fbt::cidx(t_lo, a.nT)) return FABLE_OK;
   FB_REQUIRE(ctx, ntile < (int64_t(1) << 24), "psi: more than 2^24 tiles in one slice");
   const int64_t chunk = 1 << 29;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -657,6 +691,20 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
 
 int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, int KP, double* dst) {
   k_pad_rows<<<static_cast<unsigned>(ceil_div(pp, 256)), 256, 0, ctx->stream>>>(src, lds, p, pp, k, KP, dst);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
+int fb_superblock_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t cbase, int64_t p, int64_t sb, double* d_direct,
+                           double* d_mirror) {
+  const int nT = static_cast<int>(fbt::n_tiles(p));
+  int sI, sJ;
+  fbt::tri_of(sb, sI, sJ);
+  const int64_t span = static_cast<int64_t>(SB) * TILE;
+  const int64_t r0 = sI * span, c0 = sJ * span;
+  FB_REQUIRE(ctx, c0 < p, "superblock_to_dense: super-block outside the matrix");
+  const int64_t nr = p - r0 < span ? p - r0 : span, nc = p - c0 < span ? p - c0 : span;
+  k_superblock_to_dense<<<dim3(SB, SB), 256, 0, ctx->stream>>>(d_tiles, nT, cbase, p, sI, sJ, nr, nc, d_direct, d_mirror);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
 }

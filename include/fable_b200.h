@@ -204,6 +204,15 @@ int fable_post_processing(fable_ctx* ctx, const double* LambdaSamples, const dou
                           int64_t MC, int64_t p, int k, double alpha, const int64_t* selected, int64_t S,
                           double* PostMean, double* Lower, double* Upper);
 
+/* The same summaries from RESIDENT draws: draws m0 .. m0+MC-1 of a posterior object are generated on the device (native
+ * stream, or injected gam / z in the reference's consumption order) and every entry of Psi_m is formed block-wise on
+ * the fly -- no MC x k p sample matrix crosses PCIe, nothing of size p^2 MC is stored.  MC <= 65535, k <= 32.
+ * Outputs S x S (selected = NULL: all p variables).  Both entry points use the tile-resident selection of
+ * post_tiles.cu (exact order statistics by radix selection over recomputed values) wherever these limits hold. */
+int fable_posterior_post_processing(fable_posterior* post, int64_t MC, int64_t m0, double alpha, const int64_t* selected,
+                                    int64_t S, const double* gam_inj, const double* z_inj, double* PostMean,
+                                    double* Lower, double* Upper);
+
 /* ---- resident-in-HBM posterior object (what fable_sampler is built from) ---------------------- */
 /* Uploads Y, U_k, V_k, d_k, runs the row-posterior kernels, keeps G0 / gnd / a_n on the device. */
 int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,
@@ -291,6 +300,17 @@ int fable_posterior_sample_range(fable_posterior* post, int64_t MC, int64_t m0, 
 /* the elements of CPPFABLESampler's list that do not depend on the draws (:622-627); any pointer may be NULL */
 int fable_posterior_fixed_outputs(fable_posterior* post, double* SigmaPostMean, double* SigmaPlugIn, double* tausq,
                                   double* G);
+/* draw_batch restricted to the tiles [t_begin, t_end) of the posterior's slice (same storage, fewer tiles per launch), and
+ * the dense blocks of whole super-blocks (256 consecutive slots = 16 x 16 tiles; block and mirror image) of the
+ * accumulators into the caller's dense p x p host matrices, everything else left untouched: the pieces
+ * fable_sampler's tail is made of -- the last draws run chunk-major so that finished chunks cross PCIe while the
+ * following ones compute.  fetch_superblocks runs on the stream the context currently uses and returns when the host
+ * matrices hold the blocks. */
+int fable_posterior_draw_batch_range(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots,
+                                     int accumulate, const double* dev_gam, const double* dev_z, int64_t t_begin,
+                                     int64_t t_end);
+int fable_posterior_accum_fetch_superblocks(fable_posterior* post, int64_t sb_begin, int64_t sb_end, double* sum,
+                                            double* sumsq);
 /* accumulators: device pointers to the compact upper tiles of the slice (count doubles each = tiles * 4096; the
  * one NCCL sum of multi-GPU partition A -- draws sharded over ranks -- reduces these buffers as they are), reset,
  * fetch as dense symmetric p x p host matrices (zeros outside the slice), fetch as raw compact tiles. */

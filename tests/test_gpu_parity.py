@@ -385,6 +385,35 @@ def test_posterior_batches_accumulate_like_one_pass(ctx, c1):
     post.close()
 
 
+@pytest.mark.parametrize("ring", [0, 8])
+def test_sampler_tail_runs_chunk_major_with_the_same_bits(ctx, ring, monkeypatch):
+    """fable_sampler processes the batches of its last ~256 draws super-block group by group so that finished accumulator
+    tiles cross PCIe while the rest computes (dense blocks placed by strided copies).  Every entry still sums its draws
+    in the same order: PsiSum / PsiSumSq must be bit-identical with the tail off, partly on and fully on, with and without
+    the materialising ring, into pageable and into pinned outputs -- and equal the oracle."""
+    import torch
+    n, p, k, MC = 50, 2500, 3, 70           # 40 x 40 tiles = 3 super-block columns (the last one narrow), 3 batches of 32
+    Y, u, d, v = _svd_inputs(n, p, k, 17)
+    ctx.set_psi_ring(ring)
+    outs = {}
+    try:
+        for tail in ("0", "32", "256"):
+            monkeypatch.setenv("FABLE_B200_TAIL_DRAWS", tail)
+            outs[tail] = fb.CPPFABLESampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.3, ctx=ctx, m0=3, want_G=False, psi_moments=True)
+        pinned = {"PsiSum": torch.empty((p, p), dtype=torch.float64).pin_memory().numpy().T,
+                  "PsiSumSq": torch.empty((p, p), dtype=torch.float64).pin_memory().numpy().T}
+        outs["pinned"] = fb.CPPFABLESampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.3, ctx=ctx, m0=3, want_G=False, psi_moments=True, out=pinned)
+    finally:
+        ctx.set_psi_ring(0)
+        monkeypatch.delenv("FABLE_B200_TAIL_DRAWS")
+    for key in ("PsiSum", "PsiSumSq", "LambdaSamples", "SigmaSqSamples"):
+        for other in ("32", "256", "pinned"):
+            np.testing.assert_array_equal(outs["0"][key], outs[other][key], err_msg=f"{key} tail={other}")
+    r1, r2 = c_oracle.psi_moments(outs["0"]["LambdaSamples"], outs["0"]["SigmaSqSamples"], k)
+    assert relerr_mat(outs["256"]["PsiSum"], r1) < TOL and relerr_mat(outs["256"]["PsiSumSq"], r2) < TOL
+    assert np.array_equal(outs["256"]["PsiSum"], outs["256"]["PsiSum"].T)
+
+
 @pytest.mark.parametrize("n,p,k,B", [(120, 640, 20, 3), (90, 333, 17, 2), (50, 64, 1, 5), (60, 16, 2, 2), (60, 80, 3, 3),
                                      (60, 96, 5, 2), (70, 144, 12, 2), (70, 1104, 10, 2), (70, 150, 4, 2)])
 def test_c4_like_ranks_above_one_chunk(ctx, n, p, k, B):
@@ -629,6 +658,78 @@ def test_post_processing_upper_level_at_p_max(ctx, MC, alpha):
     v01 = np.einsum("ml,ml->m", L[:, 0, :], L[:, 1, :])
     assert got["UpperQuantileMatrix"][0, 1] == pytest.approx(v01.max(), rel=1e-12)
     assert got["LowerQuantileMatrix"][0, 1] == pytest.approx(v01.min(), rel=1e-12)
+
+
+@pytest.mark.parametrize("MC", [1, 3, 16, 17, 100, 1000, 5000])
+def test_post_processing_both_kernels_agree(ctx, MC, monkeypatch):
+    """The tile-resident selection (post_tiles.cu) and the per-pair sort / selection kernels (post.cu) are two exact
+    algorithms for the same order statistics: identical quantiles, bit for bit (means differ in summation order)."""
+    n, p, k = 30, 70, 5                     # two tile columns, the second one ragged
+    Y, u, d, v = _svd_inputs(n, p, k, 47)
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=MC + 9)
+    o = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.3, gam, z)
+    res = {}
+    for tiles in ("1", "0"):
+        monkeypatch.setenv("FABLE_B200_POST_TILES", tiles)
+        res[tiles] = fb.CPPCCFABLEPostProcessing(o, 0.1, ctx=ctx)
+    monkeypatch.delenv("FABLE_B200_POST_TILES")
+    for key in ("LowerQuantileMatrix", "UpperQuantileMatrix"):
+        np.testing.assert_array_equal(res["1"][key], res["0"][key], err_msg=key)
+    assert relerr_mat(res["1"]["PostMeanMatrix"], res["0"]["PostMeanMatrix"]) < 1e-13
+    if MC <= 1000:
+        ref = orc.post_processing(o, 0.1)
+        for key in ref:
+            assert relerr_mat(res["1"][key], ref[key]) < TOL, key
+
+
+@pytest.mark.parametrize("n,p,k,MC,alpha", [(40, 150, 3, 400, 0.05), (30, 64, 12, 33, 0.2), (50, 200, 20, 300, 0.05), (40, 96, 1, 1000, 0.01)])
+def test_post_processing_on_resident_draws(ctx, n, p, k, MC, alpha):
+    """fable_posterior_post_processing: the draws are generated and consumed on the device (no MC x k p matrix crosses PCIe).
+    Injected draws: against the oracle's sampler + post-processing.  Native stream: against the stored-sample entry point fed
+    with the same draws (bit for bit), on the full matrix and on a selection with a repeated variable."""
+    Y, u, d, v = _svd_inputs(n, p, k, 53)
+    post = fb.Posterior(Y, 1.0, 1.0, u, v, d, k, 1.2, ctx=ctx)
+    gam, z = synth.injected_draws(MC, p, k, 0.5 * (1.0 + n), seed=MC + p)
+    got = post.post_processing(MC, alpha, gam=gam, z=z)
+    o = orc.sampler(Y, 1.0, 1.0, MC, u, v, d, k, 1.2, gam, z)
+    ref = orc.post_processing(o, alpha)
+    for key in ref:
+        assert relerr_mat(got[key], ref[key]) < TOL, key
+        assert np.array_equal(got[key], got[key].T)
+    L, S = post.samples(7, MC)
+    stored = {"LambdaSamples": L, "SigmaSqSamples": S, "EstimatedRank": k}
+    a = post.post_processing(MC, alpha, m0=7)
+    b = fb.CPPCCFABLEPostProcessing(stored, alpha, ctx=ctx)
+    sel = [5, 1, p, 5, 17]
+    a2 = post.post_processing(MC, alpha, SelectedIndices=sel, m0=7)
+    b2 = fb.CCFABLEPostProcessingSubmatrix(stored, alpha, sel, ctx=ctx)
+    for key in a:
+        np.testing.assert_array_equal(a[key], b[key], err_msg=key)
+        np.testing.assert_array_equal(a2[key], b2[key], err_msg=key)
+    assert a2["PostMeanMatrix"][0, 3] == a2["PostMeanMatrix"][0, 0]          # positions 0 and 3 are the same variable (cpp:770)
+    with pytest.raises(fb.FableError):
+        post.post_processing(MC, alpha, SelectedIndices=[0, 3])
+    post.close()
+
+
+def test_post_processing_c2_shape_sampled_entries(ctx):
+    """A quarter-size BASELINE configs[1] (p = 2500, MC = 2000, k = 10) through the resident path: sampled entries against
+    numpy's order statistics (Hyndman-Fan type 5 = numpy 'hazen') on values rebuilt from the returned samples."""
+    n, p, k, MC, alpha = 300, 2500, 10, 2000, 0.05
+    Y, u, d, v = _svd_inputs(n, p, k, 59)
+    post = fb.Posterior(Y, 1.0, 1.0, u, v, d, k, 1.26, ctx=ctx)
+    got = post.post_processing(MC, alpha)
+    L, S = post.samples(0, MC)
+    Lr = L.reshape(MC, p, k)
+    rng = np.random.default_rng(1)
+    pairs = [(0, 0), (0, 1), (63, 64), (p - 1, p - 1), (17, p - 1), (1024, 1023)] + [tuple(rng.integers(0, p, 2)) for _ in range(200)]
+    for a_, b_ in pairs:
+        vals = np.einsum("ml,ml->m", Lr[:, a_, :], Lr[:, b_, :]) + (S[:, a_] if a_ == b_ else 0.0)
+        assert abs(got["PostMeanMatrix"][a_, b_] - vals.mean()) <= 1e-12 * np.abs(vals).max()
+        for key, pr in (("LowerQuantileMatrix", alpha / 2), ("UpperQuantileMatrix", 1 - alpha / 2)):
+            want = orc.arma_quantile(vals, pr)
+            assert abs(got[key][a_, b_] - want) <= 1e-11 * max(abs(want), np.abs(vals).max() * 1e-3), (key, a_, b_)
+    post.close()
 
 
 @pytest.mark.parametrize("MC", [1000, 17000, 26000])
