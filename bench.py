@@ -315,6 +315,30 @@ def _estimation_rooflines(job, ctx, Y, U, V, d, kEst, stream):
     return gram, rows
 
 
+def _column_shard_check(job, ctx):
+    """Partition C (column-sharded Gram/SVD, rank search, row posterior) over NCCL on the job's ranks, on a
+    small problem, against the one-device path on rank 0: worst relative error of the sign-invariant outputs, or -1 if
+    kEst / kMax differ.  Untimed; part of the multi-rank line so that the driver's scaling run exercises it."""
+    import fable_b200 as fb
+    from fable_b200 import synth, parallel
+    n, p, k = 300, 4000, 5
+    Y = synth.factor_data(n, p, k, rep=7)
+    j0, j1 = parallel.column_range(p, job.rank, job.world)
+    res = parallel.sharded_estimation(np.asfortranarray(Y[:, j0:j1]), p, j0, job.rank, job.world, ctx,
+                                      parallel.host_allreduce(job.dev), allreduce_dev=parallel.device_allreduce(job.dev))
+    worst = 0.0
+    if job.rank == 0:
+        one = fb.FABLEPosteriorSampler(Y, MC=1, ctx=ctx, want_G=False)
+        rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(b)))
+        if res["estRank"] != one["estRank"]:
+            worst = -1.0
+        else:
+            worst = max(rel(res["svd"]["d"], one["svdY"]["d"]), abs(res["varInflation"] / one["varInflation"] - 1),
+                        rel(res["SigmaSqEstimate"], one["FABLEHyperParameters"]["SigmaSqEstimate"]),
+                        abs(res["tauSqEstimate"] / one["FABLEHyperParameters"]["tauSqEstimate"] - 1))
+    return job.max_over_ranks(abs(worst)) * (-1.0 if job.sum_over_ranks(1.0 if worst < 0 else 0.0) > 0 else 1.0)
+
+
 def run_draws(args, w, wname, job):
     import fable_b200 as fb
     from fable_b200 import synth, parallel
@@ -414,6 +438,8 @@ def run_draws(args, w, wname, job):
                 worst = max(worst, float(((a - b).abs().max() / b.abs().max()).item()))
             chk.close()
         reduce_check = job.max_over_ranks(worst)
+
+    shard_check = _column_shard_check(job, ctx) if world > 1 else None
 
     # ---- timed region 2: end to end through the C-ABI with host buffers --------------------------------
     mc = args.e2e_mc or w["e2e_mc"]                   # per rank (weak scaling, like `value`); pinned host memory scales with the ranks
@@ -518,6 +544,7 @@ def run_draws(args, w, wname, job):
                   "nccl_reduce_ms_in_timed_region": round(allreduce_ms, 3)}
         if reduce_check is not None:
             config["reduce_check_relerr"] = reduce_check
+            config["column_shard_check_relerr"] = shard_check      # partition C over NCCL vs one device (-x: kEst differs)
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "draws_per_step_per_gpu": mc, "steps": e2e_steps,
                "call": "fable_sampler (CPPFABLESampler) with pinned host buffers" if world == 1 else

@@ -581,8 +581,12 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
       FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eig_smem)));
       attr = true;
     }
-    for (; sweeps < max_sweeps; ++sweeps) {
-      FB_CUDA(ctx, cudaMemsetAsync(cnt.ptr, 0, sizeof(int), ctx->stream));
+    // One sweep = NB - 1 rounds x (panel Gram, inner solve, panel update): up to ~470 small launches at m = 5000, identical
+    // from sweep to sweep.  The sweep is captured once into a CUDA graph and replayed, which removes the per-launch host
+    // cost and the gaps between the dependent kernels (FABLE_B200_BJ_GRAPH=0: plain launches).
+    auto enqueue_sweep = [&]() -> cudaError_t {
+      cudaError_t e = cudaMemsetAsync(cnt.ptr, 0, sizeof(int), ctx->stream);
+      if (e != cudaSuccess) return e;
       for (int r = 0; r < NB - 1; ++r) {
         k_bj_gram<<<dim3(npairs, static_cast<unsigned>(nsplit)), 128, 0, ctx->stream>>>(Wbuf.d(), ld, rows_per_split, ld, r, NB,
                                                                                          Hpart.d());
@@ -590,9 +594,30 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
                                                          static_cast<int*>(cnt.ptr));
         k_bj_apply<<<dim3(npairs, static_cast<unsigned>(ceil_div(ld, 128))), 256, apply_smem, ctx->stream>>>(Wbuf.d(), ld, r, NB,
                                                                                                              Rall.d());
-        ctx->launches += 3;
       }
-      FB_CUDA(ctx, cudaGetLastError());
+      return cudaGetLastError();
+    };
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    const bool want_graph = !(getenv("FABLE_B200_BJ_GRAPH") && atoi(getenv("FABLE_B200_BJ_GRAPH")) == 0);
+    if (want_graph && cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const cudaError_t e1 = enqueue_sweep();
+      const cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
+      if (e1 != cudaSuccess || e2 != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+      }
+    } else {
+      (void)cudaGetLastError();
+    }
+    struct GraphGuard {
+      cudaGraph_t g; cudaGraphExec_t x;
+      ~GraphGuard() { if (x) cudaGraphExecDestroy(x); if (g) cudaGraphDestroy(g); }
+    } graph_guard{graph, gexec};
+    for (; sweeps < max_sweeps; ++sweeps) {
+      if (gexec) FB_CUDA(ctx, cudaGraphLaunch(gexec, ctx->stream));
+      else FB_CUDA(ctx, enqueue_sweep());
+      ctx->launches += 3 * (NB - 1);
       int nrot = 0;
       FB_CUDA(ctx, cudaMemcpyAsync(&nrot, cnt.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
