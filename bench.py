@@ -695,6 +695,12 @@ def run_tiles(args, w, wname, job):
     alg_bytes = 8.0 * entries * B + 8.0 * p * (kEst + 1) * B        # this GPU's share of 8 p^2 per draw + the operands
     achieved = alg_bytes / ((kern_ms / max(kern_launches, 1)) * 1e-3) / 1e9
     frac_min = -job.max_over_ranks(-achieved)                       # the slowest GPU's figure goes on the line
+    per_rank = [achieved]
+    if world > 1:
+        t = torch.tensor([achieved], dtype=torch.float64, device=dev)
+        g = [torch.zeros_like(t) for _ in range(world)]
+        job.dist.all_gather(g, t)
+        per_rank = [float(x.item()) for x in g]
     post.close()
 
     # ---- timed region 2: end to end through the C-ABI with host buffers: inputs up, all draws over the slice,
@@ -750,6 +756,7 @@ def run_tiles(args, w, wname, job):
             "roofline": {"bound": "hbm", "kernel": "k_psi<MAT,ACC> (compact per-rank output)", "achieved": frac_min, "peak": peak,
                          "unit": "GB/s", "frac": frac_min / peak, "traffic": None, "peak_source": peak_src,
                          "per_gpu": "slowest rank's figure: its share of 8 p^2 bytes per draw / its kernel time",
+                         "per_rank_frac": [round(x / peak, 4) for x in per_rank],
                          "algorithmic_gb_per_launch": alg_bytes / 1e9, "avg_launch_ms": kern_ms / max(kern_launches, 1),
                          "launches_timed": int(kern_launches), "kernel_share_of_step": kern_ms / max(dev_ms, 1e-9)},
         }

@@ -668,6 +668,11 @@ struct fable_posterior {
   int Bcap = 0;
   DevBuf acc_sum, acc_sq;       // compact upper tiles of the slice [tile_begin, tile_end) (tiles.cuh): acc_tiles x 4096 doubles
   int64_t acc_tiles = 0;
+  // Partial sums of the materialising batches (see ensure_partials): slot s holds (sum, sumsq) of one batch, folded into
+  // the accumulators every part_slots batches and before anyone looks at them.
+  DevBuf part;
+  int part_slots = -1;          // -1: not decided yet; 0: off (classic read-modify-write inside the covariance kernel)
+  int part_pending = 0;
   DevBuf hyp_G0;                // unshrunk G0 of FABLEHyperParameters (cpp:390), kept by fable_wrapper_sampler_begin
   DevBuf sb_stage;              // dense blocks of super-blocks on their way to the host (accum_fetch_superblocks)
   cudaEvent_t sb_ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -808,6 +813,7 @@ void fable_ctx_destroy(fable_ctx* ctx) {
   fb_mem_register_stream(ctx->device, ctx->stream, false);
   fb_mem_register_stream(ctx->device, ctx->copy_stream, false);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_extra) cudaEventDestroy(e);
   if (ctx->ring) cudaFree(ctx->ring);
   for (int s = 0; s < 2; ++s) {
     if (ctx->stage[s]) cudaFreeHost(ctx->stage[s]);
@@ -870,6 +876,8 @@ int fable_ctx_kernel_timing(fable_ctx* ctx, int enable) {
   if (!ctx) return FABLE_ERR_INVALID;
   ctx->timing = enable != 0;
   ctx->ev_used = 0;
+  for (cudaEvent_t e : ctx->ev_extra) cudaEventDestroy(e);
+  ctx->ev_extra.clear();
   return FABLE_OK;
 }
 
@@ -881,6 +889,11 @@ int fable_ctx_kernel_time(fable_ctx* ctx, double* total_ms, int64_t* launches) {
   for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
     float ms = 0.f;
     FB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+    tot += ms;
+  }
+  for (size_t i = 0; i + 1 < ctx->ev_extra.size(); i += 2) {
+    float ms = 0.f;
+    FB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_extra[i], ctx->ev_extra[i + 1]));
     tot += ms;
   }
   if (total_ms) *total_ms = tot;
@@ -1229,9 +1242,13 @@ static int ensure_accum(fable_posterior* post) {
   return FABLE_OK;
 }
 
+static int ensure_partials(fable_posterior* post);
+static int fold_range(fable_posterior* post, int64_t c_lo, int64_t c_hi, bool consume);
+static int fold_partials(fable_posterior* post) { return fold_range(post, 0, -1, true); }
+
 static int draw_batch_impl(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots, bool compact,
                            int accumulate, const double* dev_gam, const double* dev_z, int64_t launch_begin = 0,
-                           int64_t launch_end = 0) {
+                           int64_t launch_end = 0, int partial_slot = -1) {
   if (!post) return FABLE_ERR_INVALID;
   fable_ctx* ctx = post->ctx;
   FB_REQUIRE(ctx, B >= 1 && m0 >= 0, "draw_batch: need B >= 1 and m0 >= 0");
@@ -1261,7 +1278,72 @@ static int draw_batch_impl(fable_posterior* post, int64_t m0, int B, double* dev
   a.acc_sum = accumulate ? post->acc_sum.d() : nullptr; a.acc_sq = accumulate ? post->acc_sq.d() : nullptr;
   a.store_begin = post->tile_begin; a.store_end = post->tile_end;
   a.tile_begin = launch_begin; a.tile_end = launch_end;
-  return fb_psi(ctx, a);
+  // materialising + accumulating batch over the whole slice: its sums go to the next partial buffer (ensure_partials);
+  // partial_slot >= 0: the caller (chunk-major tail) names the slot and folds itself
+  bool to_partial = false;
+  if (accumulate && dev_psi && !post->cc) {
+    FB_TRY(ensure_partials(post));
+    if (post->part_slots > 0 && (partial_slot >= 0 || launch_end == 0)) {
+      const int slot = partial_slot >= 0 ? partial_slot : post->part_pending;
+      const int64_t cnt = post->acc_tiles * fbt::TILE_DOUBLES;
+      a.acc_sum = post->part.d() + static_cast<int64_t>(slot) * 2 * cnt;
+      a.acc_sq = a.acc_sum + cnt;
+      a.acc_fresh = true;
+      to_partial = partial_slot < 0;
+    } else if (post->part_pending > 0) {
+      FB_TRY(fold_partials(post));                 // a classic launch adds onto the accumulators: they must be current
+    }
+  } else if (accumulate && post->part_pending > 0 && post->cc) {
+    FB_TRY(fold_partials(post));
+  }
+  FB_TRY(fb_psi(ctx, a));
+  if (to_partial && ++post->part_pending == post->part_slots) FB_TRY(fold_partials(post));
+  return FABLE_OK;
+}
+
+// The covariance kernel can add a batch into the HBM accumulators itself (load the running tiles, store old + batch), but
+// DRAM reads mixed into its saturated write stream cost ~10 x their streaming price (profiles/r01_psi_lab.md: 3.2 GB of
+// accumulator reads = 2.0 ms of a 23 ms launch at C3).  Instead every materialising batch STORES its own sums into the
+// next of a few partial buffers (pure writes, at streaming cost) and a small read-mostly kernel folds them into the
+// accumulators every part_slots batches -- and before anything reads, resets or re-slices them.  Sums are folded in batch
+// order: deterministic; they differ from the classic path in the last bits only (association).  Off (classic) when the
+// buffers would not fit: FABLE_B200_ACC_PARTIALS = slots (default 6, 0 = off), at most ~1/8 of the device memory.
+static int ensure_partials(fable_posterior* post) {
+  if (post->part_slots >= 0) return FABLE_OK;
+  post->part_slots = 0;
+  const char* e = getenv("FABLE_B200_ACC_PARTIALS");
+  int want = e ? atoi(e) : 6;
+  if (want < 2) return FABLE_OK;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return FABLE_OK; }
+  const size_t per = static_cast<size_t>(2) * post->acc_tiles * fbt::TILE_DOUBLES * sizeof(double);
+  if (per == 0) return FABLE_OK;
+  while (want >= 2 && static_cast<size_t>(want) * per > total_b / 8) --want;
+  if (want < 2 || static_cast<size_t>(want) * per + (size_t(4) << 30) > free_b) return FABLE_OK;
+  if (post->part.alloc(static_cast<size_t>(want) * per) != cudaSuccess) { (void)cudaGetLastError(); return FABLE_OK; }
+  post->part_slots = want;
+  return FABLE_OK;
+}
+
+// fold the pending partial sums of tiles [c_lo, c_hi) (compact indices inside the slice; default: all) into the accumulators
+static int fold_range(fable_posterior* post, int64_t c_lo, int64_t c_hi, bool consume) {
+  if (post->part_pending <= 0) return FABLE_OK;
+  fable_ctx* ctx = post->ctx;
+  const int64_t cnt = post->acc_tiles * fbt::TILE_DOUBLES;
+  if (c_hi < 0) c_hi = post->acc_tiles;
+  const int64_t b = c_lo * fbt::TILE_DOUBLES, e = c_hi * fbt::TILE_DOUBLES;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  if (ctx->timing) {            // the fold is part of the covariance pass: its time goes on the same bill (fable_ctx_kernel_time)
+    FB_CUDA(ctx, cudaEventCreate(&t0));
+    FB_CUDA(ctx, cudaEventCreate(&t1));
+    ctx->ev_extra.push_back(t0); ctx->ev_extra.push_back(t1);
+    FB_CUDA(ctx, cudaEventRecord(t0, ctx->stream));
+  }
+  FB_TRY(fb_fold_partials(ctx, post->acc_sum.d(), post->part.d(), post->part_pending, 2 * cnt, b, e));
+  FB_TRY(fb_fold_partials(ctx, post->acc_sq.d(), post->part.d() + cnt, post->part_pending, 2 * cnt, b, e));
+  if (t1) FB_CUDA(ctx, cudaEventRecord(t1, ctx->stream));
+  if (consume) post->part_pending = 0;
+  return FABLE_OK;
 }
 
 int fable_posterior_draw_batch_range(fable_posterior* post, int64_t m0, int B, double* dev_psi, int psi_slots, int accumulate,
@@ -1354,6 +1436,7 @@ int fable_posterior_set_tile_range(fable_posterior* post, int64_t t_begin, int64
     FB_CUDA(ctx, cudaSetDevice(ctx->device));
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     post->acc_sum.release(); post->acc_sq.release(); post->acc_tiles = 0;
+    post->part.release(); post->part_slots = -1; post->part_pending = 0;
   }
   post->tile_begin = t_begin; post->tile_end = t_end;
   return FABLE_OK;
@@ -1416,6 +1499,7 @@ int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** 
   if (!post) return FABLE_ERR_INVALID;
   FB_CUDA(post->ctx, cudaSetDevice(post->ctx->device));
   FB_TRY(ensure_accum(post));
+  FB_TRY(fold_partials(post));
   if (dev_sum) *dev_sum = post->acc_sum.d();
   if (dev_sumsq) *dev_sumsq = post->acc_sq.d();
   if (count) *count = post->acc_tiles * fbt::TILE_DOUBLES;
@@ -1426,6 +1510,7 @@ int fable_posterior_accum_reset(fable_posterior* post) {
   if (!post) return FABLE_ERR_INVALID;
   fable_ctx* ctx = post->ctx;
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  post->part_pending = 0;               // partial sums not folded yet belong to what is being discarded
   if (!post->acc_sum.ptr) return ensure_accum(post);
   const size_t bytes = static_cast<size_t>(post->acc_tiles) * fbt::TILE_DOUBLES * sizeof(double);
   FB_CUDA(ctx, cudaMemsetAsync(post->acc_sum.ptr, 0, bytes, ctx->stream));
@@ -1442,6 +1527,7 @@ int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sums
   fable_ctx* ctx = post->ctx;
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   FB_TRY(ensure_accum(post));
+  FB_TRY(fold_partials(post));
   const int64_t p = post->p;
   int64_t W = (int64_t(256) << 20) / (8 * p) / fbt::TILE * fbt::TILE;      // ~256 MB panels
   if (W < fbt::TILE) W = fbt::TILE;
@@ -1476,6 +1562,8 @@ int fable_posterior_accum_fetch_superblocks(fable_posterior* post, int64_t sb_be
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   FB_TRY(ensure_accum(post));
   const int64_t p = post->p, slots = fbt::n_slots(p), per_sb = fbt::SB * fbt::SB;
+  // (pending partial sums are the caller's business here: the sampler's tail folds chunk by chunk on the main stream and
+  // calls this on the copy stream)
   const int64_t s_lo = post->tile_begin, s_hi = post->tile_end > 0 ? post->tile_end : slots;
   FB_REQUIRE(ctx, sb_begin >= 0 && sb_begin <= sb_end && sb_end * per_sb <= slots, "fetch_superblocks: range out of bounds");
   FB_REQUIRE(ctx, sb_begin * per_sb >= s_lo && sb_end * per_sb <= s_hi, "fetch_superblocks: range outside the posterior's tile slice");
@@ -1521,6 +1609,7 @@ int fable_posterior_accum_fetch_tiles(fable_posterior* post, double* sum_tiles, 
   fable_ctx* ctx = post->ctx;
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   FB_TRY(ensure_accum(post));
+  FB_TRY(fold_partials(post));
   const size_t cnt = static_cast<size_t>(post->acc_tiles) * fbt::TILE_DOUBLES;
   FB_TRY(download(ctx, sum_tiles, post->acc_sum.d(), cnt));
   FB_TRY(download(ctx, sumsq_tiles, post->acc_sq.d(), cnt));
@@ -1601,29 +1690,44 @@ static int sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t l
       const char* e = getenv("FABLE_B200_TAIL_DRAWS");
       const int64_t td = e ? atoll(e) : 256;
       tail = td <= 0 ? 0 : ceil_div(td, B);
+      if (ctx->ring_slots > 0) {                       // materialising run: the tail's partial sums need one slot per batch
+        FB_TRY(ensure_partials(post));
+        if (post->part_slots > 0 && tail > post->part_slots) tail = post->part_slots;
+      }
       if (tail > nbatch) tail = nbatch;
       // the fetch staging is allocated before anything is queued (the call drains the stream)
       if (tail > 0 && !post->sb_stage.ptr) FB_TRY(fable_posterior_accum_fetch_superblocks(post, 0, 0, fetch_sum, fetch_sq));
     }
-    auto batch = [&](int64_t bi, int64_t lb, int64_t le) -> int {
+    auto batch = [&](int64_t bi, int64_t lb, int64_t le, int partial_slot) -> int {
       const int64_t b0 = bi * B;
       const int nb = static_cast<int>(MC - b0 < B ? MC - b0 : B);
       return draw_batch_impl(post, m0 + b0, nb, ctx->ring_slots > 0 ? ctx->ring : nullptr, ctx->ring_slots, false, 1,
-                             gam_inj ? dgam.d() + b0 * p : nullptr, gam_inj ? dz.d() + b0 * p * kEst : nullptr, lb, le);
+                             gam_inj ? dgam.d() + b0 * p : nullptr, gam_inj ? dz.d() + b0 * p * kEst : nullptr, lb, le, partial_slot);
     };
     for (int64_t bi = 0; bi < nbatch - tail; ++bi) {
-      FB_TRY(batch(bi, 0, 0));
+      FB_TRY(batch(bi, 0, 0, -1));
       if (ctx->poll && ctx->poll(ctx->poll_user)) {
         cudaStreamSynchronize(ctx->stream);
         return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");
       }
     }
     if (tail > 0) {
+      // the tail batches of a chunk store their sums into partial slots 0 .. tail-1 (when the posterior uses partial
+      // sums: the same association as the batch-major path, so the results do not depend on the tail) and are folded
+      // into the chunk's accumulator tiles before the chunk's event
+      FB_TRY(fold_partials(post));
+      const bool parts = post->part_slots >= tail && ctx->ring_slots > 0;
+      const int nT = static_cast<int>(fbt::n_tiles(p));
       const int64_t nsb = fbt::n_slots(p) / (fbt::SB * fbt::SB);
       const int64_t nchunk = nsb < 12 ? nsb : 12;
       for (int64_t c = 0; c < nchunk; ++c) {
         const int64_t sb0 = nsb * c / nchunk, sb1 = nsb * (c + 1) / nchunk;
-        for (int64_t bi = nbatch - tail; bi < nbatch; ++bi) FB_TRY(batch(bi, sb0 * fbt::SB * fbt::SB, sb1 * fbt::SB * fbt::SB));
+        const int64_t t0 = sb0 * fbt::SB * fbt::SB, t1 = sb1 * fbt::SB * fbt::SB;
+        for (int64_t bi = nbatch - tail; bi < nbatch; ++bi) FB_TRY(batch(bi, t0, t1, parts ? static_cast<int>(bi - (nbatch - tail)) : -1));
+        if (parts) {
+          post->part_pending = static_cast<int>(tail);
+          FB_TRY(fold_range(post, fbt::cidx(t0, nT), fbt::cidx(t1, nT), true));
+        }
         cudaEvent_t ev;
         FB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         tail_events.push_back({ev, sb0, sb1});

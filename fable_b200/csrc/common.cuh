@@ -22,6 +22,7 @@ struct fable_ctx {
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;     // pairs: [2i] before, [2i+1] after the launch
   size_t ev_used = 0;
+  std::vector<cudaEvent_t> ev_extra;    // pairs around work done on behalf of those launches (folding their partial sums): counted in the total time, not as launches
   // optional device ring of materialised Psi draws kept by fable_sampler (fable_ctx_set_psi_ring)
   double* gemm_ws = nullptr;    // grow-only split-K workspace of the DMMA GEMM
   size_t gemm_ws_bytes = 0;
@@ -184,6 +185,8 @@ struct PsiArgs {
   bool out_compact = false;   // psi holds, per slot, the slice's tiles compactly: direct tile c at 2c, mirrored at 2c + 1
   double* acc_sum;     // accumulators (NULL: none): COMPACT upper tiles of the slice (tiles.cuh), 4096 doubles per tile
   double* acc_sq;
+  bool acc_fresh = false;     // materialising kernels: do not load the running tiles -- store this batch's own sums (the
+                              // pointers then name a PARTIAL buffer that fb_fold_partials adds into the accumulators later)
   const double* cc_gdiag = nullptr;   // entry-wise coverage correction (f3): diag(G) and sig_hat (length p);
   const double* cc_sig = nullptr;     // Lw then carries G0 in slot 0 ahead of the B draws
   int64_t store_begin = 0, store_end = 0; // slice of the tile enumeration the compact buffers cover (store_end == 0: all tiles)
@@ -193,6 +196,8 @@ struct PsiArgs {
   int64_t cbase = 0;   // set by fb_psi: compact index of the slice's first tile
 };
 int fb_psi(fable_ctx* ctx, const PsiArgs& a);
+// acc[i] += sum_{s < np} part[s * stride + i], i in [begin, end): the batches' partial sums folded into an accumulator
+int fb_fold_partials(fable_ctx* ctx, double* d_acc, const double* d_part, int np, int64_t stride, int64_t begin, int64_t end);
 // compact tiles of the slice [t_lo, t_hi) (t_hi == 0: all) -> columns [col0, col0 + ncols) of the dense symmetric p x p
 // matrix (d_out: p x ncols, ld p; col0 a multiple of 64); blocks outside the slice become zeros.  paired: the buffer
 // holds (direct, mirrored) tile pairs (materialised draws) instead of upper tiles only (accumulators).

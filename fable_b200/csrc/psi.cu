@@ -235,7 +235,7 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
   // Materialising kernels with whole-box tensor maps: the running accumulator tiles are fetched by two TMA tensor
   // loads into the (still unused) staging buffers and folded into the registers when draw 0 is accumulated.
   __shared__ uint64_t acc_bar;
-  const bool acc_tma = MAT && ACC && !(PSI_LAB & 16);
+  const bool acc_tma = MAT && ACC && !a.acc_fresh && !(PSI_LAB & 16);
   if (acc_tma) {
     if (tid == 0) mbar_init(&acc_bar, 1);
     __syncthreads();
@@ -686,6 +686,28 @@ int fb_psi(fable_ctx* ctx, const PsiArgs& a_in) {
     else FB_TRY((launch_psi<false, true>(ctx, a, g, t0, m)));
   }
   if (ev1) FB_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+  return FABLE_OK;
+}
+
+// acc[i] += sum_s part[s][i]: a read stream of np + 1 buffers and one write stream, each element touched by one thread
+__global__ void __launch_bounds__(256) k_fold_partials(double* __restrict__ acc, const double* __restrict__ part, int np, int64_t stride,
+                                                       int64_t begin, int64_t end) {
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x * 2;
+  for (int64_t i = begin + (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < end; i += step) {
+    double2 a = *reinterpret_cast<const double2*>(acc + i);
+    for (int s2 = 0; s2 < np; ++s2) {
+      const double2 x = __ldcs(reinterpret_cast<const double2*>(part + s2 * stride + i));
+      a.x += x.x; a.y += x.y;
+    }
+    *reinterpret_cast<double2*>(acc + i) = a;
+  }
+}
+
+int fb_fold_partials(fable_ctx* ctx, double* d_acc, const double* d_part, int np, int64_t stride, int64_t begin, int64_t end) {
+  if (np <= 0 || end <= begin) return FABLE_OK;
+  FB_REQUIRE(ctx, begin % 2 == 0 && end % 2 == 0 && stride % 2 == 0, "fold_partials: ranges must be even");
+  k_fold_partials<<<ctx->sms * 8, 256, 0, ctx->stream>>>(d_acc, d_part, np, stride, begin, end);
+  FB_LAUNCHED(ctx);
   return FABLE_OK;
 }
 

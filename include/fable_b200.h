@@ -87,7 +87,8 @@ int fable_ctx_synchronize(fable_ctx* ctx);
 void* fable_ctx_stream(fable_ctx* ctx);
 /* Per-launch CUDA-event timing of the covariance kernel on the context's stream.  enable != 0
  * starts (and clears) the record; fable_ctx_kernel_time synchronises and returns the summed device
- * time in milliseconds and the number of launches recorded since it was enabled. */
+ * time in milliseconds and the number of launches recorded since it was enabled.  The time includes the kernels
+ * that fold the launches' partial sums into the accumulators (they are part of the same pass), the count does not. */
 int fable_ctx_kernel_timing(fable_ctx* ctx, int enable);
 int fable_ctx_kernel_time(fable_ctx* ctx, double* total_ms, int64_t* launches);
 /* Diagnostics: register-resident issue rate of the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA.8x8x4) on this

@@ -76,3 +76,32 @@ def test_argument_validation_in_the_mirror():
         api._inputs(Y, U, np.zeros((3, 4)), d)
     with pytest.raises(fb.FableError):
         api._F(np.zeros((2, 2, 2)))
+
+
+def test_r_package_native_layer_type_checks():
+    """rpkg/src/*.cpp (the Rcpp layer a maintainer ships) cannot be built here -- no R, no Rcpp -- but it is pure marshalling
+    into the C-ABI: parse and type-check it against include/fable_b200.h with a declaration-only Rcpp stand-in (argument
+    counts and types of every fable_* call, list elements, the registration table)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    for src in ("fable_b200_rcpp.cpp", "RcppExports.cpp"):
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tests", "rcpp_stub"),
+                            "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "rpkg", "src", src)],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-3000:]
+    # the registration table carries the reference's fourteen routines at their arities (src/RcppExports.cpp:212-228)
+    text = open(os.path.join(ROOT, "rpkg", "src", "RcppExports.cpp")).read()
+    want = {"rGamma": 3, "SymmetrizeMatrix": 1, "CPPsvd": 2, "CPPLogLikelihoodEval": 4, "CPPCriterionFunction": 5,
+            "CPPBisectionRecursion": 6, "CPPRankEstimator": 5, "FABLEHyperParameters": 5, "CPPcov_correct_matrix": 2,
+            "CPPFABLEPostMean": 7, "CPPFABLESampler": 9, "CPPCCFABLEPostProcessing": 2, "CCFABLEPostProcessingSubmatrix": 3,
+            "CCFABLEPostProcessingSubmatrix_Optimized": 3}
+    for name, arity in want.items():
+        assert re.search(r"FB_REG\(%s, %d\)" % (name, arity), text), name
+        m = re.search(r"SEXP _FABLE_%s\(([^)]*)\)" % name, text)
+        assert m and len([a for a in m.group(1).split(",") if a.strip()]) == arity, name
+    rtext = open(os.path.join(ROOT, "rpkg", "R", "RcppExports.R")).read()
+    for name, arity in want.items():
+        m = re.search(r"^\s*%s\s*=\s*c\(([^)]*)\)" % name, rtext, flags=re.M)
+        assert m and len(m.group(1).split(",")) == arity, name
