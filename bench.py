@@ -387,9 +387,9 @@ def run_draws(args, w, wname, job):
     e0.record(stream)
     for _ in range(args.steps):
         post.draw_batch(m0, B, dev_psi=ring.data_ptr(), psi_slots=slots, accumulate=True); m0 += B
+    a_sum, a_sq, a_cnt = post.accum_dev()            # folds the batches' partial sums that are still pending: inside the timed region
     e1.record(stream)
     ctx.synchronize()
-    a_sum, a_sq, a_cnt = post.accum_dev()
     local_checksum = float(parallel.as_torch(a_sum, a_cnt, dev).sum().item()) if world > 1 else 0.0   # untimed (between the events)
     if world > 1:       # the one exchange step of the path: sum the accumulators over ranks (NCCL)
         ea = torch.cuda.Event(enable_timing=True); eb = torch.cuda.Event(enable_timing=True)
@@ -682,6 +682,7 @@ def run_tiles(args, w, wname, job):
     e0.record(stream)
     for _ in range(args.steps):
         post.draw_batch_tiles(m0, B, dev_psi_tiles=ring.data_ptr(), psi_slots=B, accumulate=True); m0 += B
+    post.accum_dev()                                  # pending partial sums are folded inside the timed region
     e1.record(stream)
     ctx.synchronize()
     job.barrier()

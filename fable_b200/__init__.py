@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     CPPFABLEPostMean, CPPFABLESampler, CPPsvd, svd, kmax_rule,
     CPPCCFABLEPostProcessing, CCFABLEPostProcessingSubmatrix, CCFABLEPostProcessingSubmatrix_Optimized,
     default_context, library_path, row_posterior,
+    RankEstimator, RankEstimatorCriterion, CCFABLE_DirectSampler,
 )
 from . import synth  # noqa: F401
 
@@ -23,4 +24,5 @@ __all__ = [
     "CPPcov_correct_matrix", "cov_correct_matrix", "var_inflation", "CPPFABLEPostMean",
     "CPPFABLESampler", "CPPsvd", "svd", "kmax_rule", "CPPCCFABLEPostProcessing",
     "CCFABLEPostProcessingSubmatrix", "CCFABLEPostProcessingSubmatrix_Optimized", "default_context", "library_path", "row_posterior", "synth",
+    "RankEstimator", "RankEstimatorCriterion", "CCFABLE_DirectSampler",
 ]

@@ -335,6 +335,54 @@ def CPPRankEstimator(Y, U_Y, V_Y, svalsY, kMax, ctx=None):
     return k.value
 
 
+def RankEstimator(Ymat, svdmod, kMax, ctx=None):
+    """The pure-R prototype RankEstimator(Ymat, svdmod, kMax) (R/FABLE_code.R:32-186): svdmod = list(d, u, v)."""
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Ymat, svdmod["u"], svdmod["v"], svdmod["d"])
+    k = C.c_int()
+    ctx.check(_load().fable_rank_estimator_proto(ctx._h, _ptr(Y), _i64(n), _i64(p), _ptr(U), _ptr(V), _ptr(d), _i64(r),
+                                                 C.c_int(int(kMax)), C.byref(k)))
+    return k.value
+
+
+def RankEstimatorCriterion(kInd, Ymat, svdmod, ctx=None):
+    """CriterionFunction(kInd) inside the prototype's RankEstimator (R/FABLE_code.R:57-116)."""
+    ctx = _ctx(ctx)
+    Y, U, V, d, n, p, r = _inputs(Ymat, svdmod["u"], svdmod["v"], svdmod["d"])
+    out = C.c_double()
+    ctx.check(_load().fable_criterion_proto(ctx._h, C.c_int(int(kInd)), _ptr(Y), _i64(n), _i64(p), _ptr(U), _ptr(V), _ptr(d),
+                                            _i64(r), C.byref(out)))
+    return out.value
+
+
+def CCFABLE_DirectSampler(Y, gamma0=1.0, delta0sq=1.0, MC=1000, ctx=None, gam=None, z=None, m0=0, info=None):
+    """R/FABLE_code.R:212-298: the (MC, p, p) array of entry-wise coverage-corrected draws of Psi.  gam / z: injected draws
+    (z may be a callable (MC, k, p) -> array: the rank is only known after the prototype's RankEstimator has run).
+    `info`, if a dict, receives kMax and k."""
+    ctx = _ctx(ctx)
+    Y = _F(Y, "Y")
+    n, p = Y.shape
+    MC = int(MC)
+    kM = C.c_int(); k = C.c_int(); ph = C.c_void_p()
+    ctx.check(_load().fable_direct_sampler_begin(ctx._h, _ptr(Y), _i64(n), _i64(p), C.c_double(gamma0), C.c_double(delta0sq),
+                                                 C.byref(kM), C.byref(k), C.byref(ph)))
+    try:
+        if info is not None:
+            info.update(kMax=kM.value, k=k.value)
+        g = zz = None
+        if gam is not None or z is not None:
+            if gam is None or z is None:
+                raise FableError(1, "injected draws need both gam and z")
+            zz = z(MC, k.value, p) if callable(z) else z
+            g = np.ascontiguousarray(gam, dtype=np.float64).reshape(MC, p)
+            zz = np.ascontiguousarray(zz, dtype=np.float64).reshape(MC, k.value, p)
+        out = np.empty((MC, p, p), order="F")                         # R array: first index fastest
+        ctx.check(_load().fable_direct_sampler_draws(ph, _i64(MC), _i64(m0), _ptr(g), _ptr(zz), out.ctypes.data_as(_dp)))
+    finally:
+        _load().fable_posterior_destroy(ph)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # a6 / a7
 # ------------------------------------------------------------------------------------------------

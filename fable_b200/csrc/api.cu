@@ -268,12 +268,34 @@ int row_pass(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, bool want_
   return FABLE_OK;
 }
 
-// CPPCriterionFunction (cpp:127-213) on resident inputs.
-int criterion_dev(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, double* out) {
+// The criterion of the pure-R prototype RankEstimator (R/FABLE_code.R:57-116) from the residual column sums of squares r_j
+// and their logs: sigma_j^2 = r_j / (n - k) (:87), LogLik = (-n sum_j log sd_j - 0.5 sum_ij (resid_ij / sd_j)^2) / (n p)
+// (LogLikelihoodEvaluator :12-27), criterion = -2 LogLik + k max(n,p) log(min(n,p)) / (n p) (:113-114).
+// sumlog = sum_j log(r_j / (n - k)), ros = sum_j r_j / sigma_j^2.
+double proto_criterion(double dn, double dp, int k, double sumlog, double ros) {
+  const double term1 = -dn * (0.5 * sumlog), term2 = -0.5 * ros;
+  const double ll = (term1 + term2) / (dn * dp);
+  const double maxint = dn > dp ? dn : dp, minint = dn < dp ? dn : dp;
+  return (-2.0 * ll) + (static_cast<double>(k) * maxint * std::log(minint) / (dn * dp));
+}
+
+// CPPCriterionFunction (cpp:127-213) on resident inputs; variant 1: the R prototype's criterion (above).
+int criterion_dev(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, double* out, int variant = 0) {
   FB_REQUIRE(ctx, k >= 1 && k <= in.kcols, "criterion: kInd out of range");   // arma: cols(0,k-1) throws
   FB_TRY(row_pass(ctx, in, k, sc, false));
   double sumlog = 0.0;
   const double dn = static_cast<double>(in.n), dp = static_cast<double>(glob_p(ctx, in.p));
+  if (variant == 1) {
+    FB_REQUIRE(ctx, in.n > k, "prototype criterion: needs k < n (sigma^2 = resid / (n - k))");
+    const double inv = 1.0 / (dn - static_cast<double>(k));
+    double both[2] = {0.0, 0.0};
+    FB_TRY(fb_sum_log_scaled(ctx, sc.resid.d(), in.p, inv, &both[0]));
+    FB_TRY(fb_resid_over_scaled_self_sum(ctx, sc.resid.d(), in.p, inv, &both[1]));
+    FB_TRY(shard_sum(ctx, both, 2));
+    if (!std::isfinite(both[0]) || !std::isfinite(both[1])) return ctx->fail(FABLE_ERR_NUMERIC, "criterion: non-positive residual variance");
+    *out = proto_criterion(dn, dp, k, both[0], both[1]);
+    return FABLE_OK;
+  }
   FB_TRY(fb_sum_log_scaled(ctx, sc.resid.d(), in.p, 1.0 / dn, &sumlog));
   FB_TRY(shard_sum(ctx, &sumlog, 1));                                            // sum over ALL variables (cpp:199)
   if (!std::isfinite(sumlog)) return ctx->fail(FABLE_ERR_NUMERIC, "criterion: non-positive residual variance");
@@ -294,11 +316,12 @@ int criterion_dev(fable_ctx* ctx, const Inputs& in, int k, RowScratch& sc, doubl
 struct CritCache {
   fable_ctx* ctx; const Inputs& in; RowScratch sc; std::map<int, double> memo;
   std::vector<double> fast;      // fast[k-1]: criterion from the all-rank pass (empty: not available)
-  CritCache(fable_ctx* c, const Inputs& i) : ctx(c), in(i) {}
+  int variant = 0;               // 0: CPPCriterionFunction (cpp:127-213); 1: the R prototype's criterion (R/FABLE_code.R:57-116)
+  CritCache(fable_ctx* c, const Inputs& i, int v = 0) : ctx(c), in(i), variant(v) {}
   int eval(int k, double* v) {                    // the reference's arithmetic (explicit residual)
     auto it = memo.find(k);
     if (it != memo.end()) { *v = it->second; return FABLE_OK; }   // same inputs -> same value (cpp:233 re-evaluates)
-    FB_TRY(criterion_dev(ctx, in, k, sc, v));
+    FB_TRY(criterion_dev(ctx, in, k, sc, v, variant));
     memo[k] = *v;
     return FABLE_OK;
   }
@@ -337,7 +360,12 @@ struct CritCache {
     const double dn = static_cast<double>(n), dp = static_cast<double>(glob_p(ctx, p));
     const double maxint = dn > dp ? dn : dp, minint = dn < dp ? dn : dp;
     for (int k = 1; k <= kMax; ++k) {
-      if (!std::isfinite(sl[k - 1])) { fast.clear(); return FABLE_OK; }
+      if (!std::isfinite(sl[k - 1]) || (variant == 1 && k >= n)) { fast.clear(); return FABLE_OK; }
+      if (variant == 1) {      // sum_j log(r_j / (n-k)) = sum_j log(r_j / n) + p log(n / (n-k));  sum_j r_j / sigma_j^2 = p (n-k)
+        const double dk = static_cast<double>(k);
+        fast.push_back(proto_criterion(dn, dp, k, sl[k - 1] + dp * std::log(dn / (dn - dk)), dp * (dn - dk)));
+        continue;
+      }
       const double LL = (-dn * dp / 2.0) - (dn * sl[k - 1] / 2.0);                                      // cpp:199
       fast.push_back((-2.0 * LL) + (static_cast<double>(k) * maxint * std::log(minint)));               // cpp:209
     }
@@ -382,10 +410,11 @@ int bisection(CritCache& cc, int lower, int upper, int* lo, int* hi) {
   return FABLE_OK;
 }
 
-// CPPRankEstimator (cpp:281-341)
-int rank_dev(fable_ctx* ctx, const Inputs& in, int kMax, int* kEst) {
+// CPPRankEstimator (cpp:281-341); variant 1: the R prototype RankEstimator (R/FABLE_code.R:32-186: the same bisection and
+// window, :118-184, over its own criterion)
+int rank_dev(fable_ctx* ctx, const Inputs& in, int kMax, int* kEst, int variant = 0) {
   FB_REQUIRE(ctx, kMax >= 1 && kMax <= in.kcols, "kMax must be in 1..length(svalsY)");
-  CritCache cc(ctx, in);
+  CritCache cc(ctx, in, variant);
   FB_TRY(cc.prepare(kMax));
   int lo, hi;
   FB_TRY(bisection(cc, 1, kMax, &lo, &hi));                      // cpp:314
@@ -1044,6 +1073,28 @@ int fable_rank_estimator(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, 
   Inputs in;
   FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kMax, in));
   return rank_dev(ctx, in, kMax, kEst);
+}
+
+// the criterion / rank rule of the pure-R prototype (R/FABLE_code.R:32-186), used by CCFABLE_DirectSampler (:221)
+int fable_criterion_proto(fable_ctx* ctx, int kInd, const double* Y, int64_t n, int64_t p, const double* U, const double* V,
+                          const double* d, int64_t r, double* out) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, out, "criterion: NULL output");
+  FB_REQUIRE(ctx, kInd >= 1 && kInd <= r, "criterion: kInd must be in 1..length(svalsY)");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kInd, in));
+  RowScratch sc;
+  return criterion_dev(ctx, in, kInd, sc, out, /*variant=*/1);
+}
+
+int fable_rank_estimator_proto(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* U, const double* V,
+                               const double* d, int64_t r, int kMax, int* kEst) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_REQUIRE(ctx, kEst, "rank estimator: NULL output");
+  FB_REQUIRE(ctx, kMax >= 1 && kMax <= r, "kMax must be in 1..length(svalsY)");
+  Inputs in;
+  FB_TRY(upload_inputs(ctx, Y, n, p, U, V, d, r, kMax, in));
+  return rank_dev(ctx, in, kMax, kEst, /*variant=*/1);
 }
 
 // ---- a6 ------------------------------------------------------------------------------------------
@@ -1888,6 +1939,65 @@ int fable_posterior_hyper_G0(fable_posterior* post, double* hypG0) {
   FB_REQUIRE(ctx, post->hyp_G0.ptr, "hyper_G0: this posterior was not created by fable_wrapper_sampler_begin");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   FB_TRY(download(ctx, hypG0, post->hyp_G0.d(), static_cast<size_t>(post->p) * post->k));
+  FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FABLE_OK;
+}
+
+// ---- f3: CCFABLE_DirectSampler(Y, gamma0, delta0sq, MC) (R/FABLE_code.R:212-298) as a callable -----------------------
+// begin = R:214-263: svd(Y), kMax at 0.95 (:219), the prototype's own RankEstimator (:221), the row posterior (shrunk G0,
+// :236-257 = cpp:564-592) with a_n = 1 / sqrt(n + 1/tau^2) (:263: no variance inflation) and the entry-wise correction
+// B = cov_correct_matrix(sigma^2, G) (:251) switched on.  draws = the MC loop (:267-294) into the (MC, p, p) array.
+int fable_direct_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq, int* kMaxOut,
+                               int* kEstOut, fable_posterior** out) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  FB_NO_SHARD(ctx, "CCFABLE_DirectSampler");
+  FB_REQUIRE(ctx, out, "direct_sampler_begin: NULL out");
+  *out = nullptr;
+  Pipeline pl;
+  FB_TRY(pipeline_svd(ctx, Y, n, p, /*maxProp=*/0.95, pl, nullptr, nullptr, nullptr));          // R:216-219
+  if (kMaxOut) *kMaxOut = pl.kMax;
+  int k = 1;
+  FB_TRY(rank_dev(ctx, pl.in, pl.kMax, &k, /*variant=*/1));                                       // R:221
+  if (kEstOut) *kEstOut = k;
+  FB_TRY(posterior_from_inputs(ctx, pl.in, gamma0, delta0sq, k, /*varInflation=*/1.0, out));     // R:236-263
+  const int rc = fable_posterior_set_entrywise_correction(*out, 1);                              // R:251, 285
+  if (rc != FABLE_OK) { fable_posterior_destroy(*out); *out = nullptr; }
+  return rc;
+}
+
+int fable_direct_sampler_draws(fable_posterior* post, int64_t MC, int64_t m0, const double* gam_inj, const double* z_inj,
+                               double* CovSampleStor) {
+  if (!post) return FABLE_ERR_INVALID;
+  fable_ctx* ctx = post->ctx;
+  FB_REQUIRE(ctx, MC >= 1 && m0 >= 0 && CovSampleStor, "direct_sampler_draws: need MC >= 1, m0 >= 0 and an output array");
+  FB_REQUIRE(ctx, (gam_inj == nullptr) == (z_inj == nullptr), "injected draws need both gam and z");
+  const int64_t p = post->p, p2 = p * p;
+  const int k = post->k;
+  FB_REQUIRE(ctx, static_cast<double>(MC) * static_cast<double>(p2) * 8.0 <= 32e9,
+             "CCFABLE_DirectSampler stores MC x p x p doubles (R/FABLE_code.R:262): above 32 GB use FABLEPosteriorSampler + "
+             "post-processing instead, as the reference's own comments advise (:209-211)");
+  FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf dgam, dz, ring, outb;
+  if (gam_inj) {
+    FB_TRY(upload(ctx, dgam, gam_inj, static_cast<size_t>(MC) * p));
+    FB_TRY(upload(ctx, dz, z_inj, static_cast<size_t>(MC) * p * k));
+  }
+  int64_t B = (int64_t(2) << 30) / (8 * p2);                     // ~2 GB of dense draws per batch
+  B = B < 1 ? 1 : (B > 64 ? 64 : B);
+  if (B > MC) B = MC;
+  FB_CUDA(ctx, ring.alloc(static_cast<size_t>(B) * p2 * sizeof(double)));
+  FB_CUDA(ctx, outb.alloc(static_cast<size_t>(MC) * p2 * sizeof(double)));
+  for (int64_t b0 = 0; b0 < MC; b0 += B) {
+    const int nb = static_cast<int>(MC - b0 < B ? MC - b0 : B);
+    FB_TRY(fable_posterior_draw_batch(post, m0 + b0, nb, ring.d(), static_cast<int>(B), 0, gam_inj ? dgam.d() + b0 * p : nullptr,
+                                      gam_inj ? dz.d() + b0 * p * k : nullptr));
+    FB_TRY(fb_slots_to_marray(ctx, ring.d(), nb, p2, MC, b0, outb.d()));                      // CovSampleStor[m, , ] = PsiSample (R:290)
+    if (ctx->poll && ctx->poll(ctx->poll_user)) {
+      cudaStreamSynchronize(ctx->stream);
+      return ctx->fail(FABLE_ERR_INTERRUPT, "interrupted");
+    }
+  }
+  FB_TRY(download(ctx, CovSampleStor, outb.d(), static_cast<size_t>(MC) * p2));
   FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FABLE_OK;
 }

@@ -132,6 +132,7 @@ int fb_prefix_sumlog(fable_ctx* ctx, const double* dV, int64_t ldv, const double
 int fb_svd_consistency(fable_ctx* ctx, const double* dT, int64_t ldt, const double* dV, int64_t ldv, const double* dd, int64_t p,
                        int k, double* max_diff, double* max_abs);
 int fb_identity_err(fable_ctx* ctx, const double* dA, int64_t k, double* max_diff);
+int fb_resid_over_scaled_self_sum(fable_ctx* ctx, const double* d_resid, int64_t p, double inv, double* host_sum);   // sum_j r_j / (r_j * inv)
 int fb_loglik_terms(fable_ctx* ctx, const double* d_resid, const double* d_sig, int64_t p, double* sum_log_sd,
                     double* sum_resid_over_sig);
 int fb_q_over_sig_sum(fable_ctx* ctx, const double* d_q, const double* d_resid, int64_t n, int64_t p, double* host_sum);
@@ -209,6 +210,8 @@ int fb_tiles_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t p, int64_t 
 // symmetric block in d_direct alone.
 int fb_superblock_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t cbase, int64_t p, int64_t sb, double* d_direct,
                            double* d_mirror);
+// a batch of B materialised draws (slot stride p2) -> rows m_off .. m_off + B - 1 of an (ldm, p, p) array, first index fastest
+int fb_slots_to_marray(fable_ctx* ctx, const double* d_slots, int B, int64_t p2, int64_t ldm, int64_t m_off, double* d_out);
 // dst (k rows of pp, zero-padded) <- src (k rows of lds, p valid)
 int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64_t pp, int k, int KP, double* dst);
 // post.cu: Lsel [S][k][MC], Ssel [S][MC], idx [S] (0-based selected variables); outputs S x S column-major

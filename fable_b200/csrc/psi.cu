@@ -323,7 +323,9 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
               double bb = 0.0;
               if (u < p && v < p) {
                 const double gu = a.cc_gdiag[u], gv = a.cc_gdiag[v], su = a.cc_sig[u], sv = a.cc_sig[v];
-                bb = (gu * gv + c[i][j][e] * c[i][j][e]) / (gu * sv + su * gv);
+                // products rounded before they are added (no FMA contraction): B_uv == B_vu bit for bit, as in R's
+                // element-wise matrix arithmetic, so diagonal tiles stay exactly symmetric
+                bb = __ddiv_rn(__dadd_rn(__dmul_rn(gu, gv), __dmul_rn(c[i][j][e], c[i][j][e])), __dadd_rn(__dmul_rn(gu, sv), __dmul_rn(su, gv)));
                 if (u == v) bb = bb / 2.0;
                 bb = sqrt(1.0 + bb);
               }
@@ -707,6 +709,33 @@ int fb_fold_partials(fable_ctx* ctx, double* d_acc, const double* d_part, int np
   if (np <= 0 || end <= begin) return FABLE_OK;
   FB_REQUIRE(ctx, begin % 2 == 0 && end % 2 == 0 && stride % 2 == 0, "fold_partials: ranges must be even");
   k_fold_partials<<<ctx->sms * 8, 256, 0, ctx->stream>>>(d_acc, d_part, np, stride, begin, end);
+  FB_LAUNCHED(ctx);
+  return FABLE_OK;
+}
+
+// out[e * ldm + m_off + b] = slots[b * p2 + e], b < B: a batch of materialised draws into an (MC, p, p) R array (first index
+// fastest: CovSampleStor[m, , ] of R/FABLE_code.R:262, 290).  32 entries x 32 draws per block through shared memory.
+__global__ void __launch_bounds__(256) k_slots_to_marray(const double* __restrict__ slots, int B, int64_t p2, int64_t ldm, int64_t m_off,
+                                                         double* __restrict__ out) {
+  __shared__ double t[32][33];
+  const int64_t e0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int b0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int b = b0 + r;
+    t[r][tx] = (b < B && e0 + tx < p2) ? slots[static_cast<int64_t>(b) * p2 + e0 + tx] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t e = e0 + r;
+    const int b = b0 + tx;
+    if (e < p2 && b < B) out[e * ldm + m_off + b] = t[tx][r];
+  }
+}
+
+int fb_slots_to_marray(fable_ctx* ctx, const double* d_slots, int B, int64_t p2, int64_t ldm, int64_t m_off, double* d_out) {
+  dim3 grid(static_cast<unsigned>(ceil_div(p2, 32)), static_cast<unsigned>(ceil_div(B, 32)));
+  k_slots_to_marray<<<grid, 256, 0, ctx->stream>>>(d_slots, B, p2, ldm, m_off, d_out);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
 }

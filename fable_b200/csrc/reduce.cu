@@ -36,6 +36,11 @@ struct ResidOverSig {
   const double* resid; const double* sig;
   __device__ double operator()(int64_t j) const { return resid[j] / sig[j]; }
 };
+// R prototype criterion (R/FABLE_code.R:20-22 with sigma^2 = resid / (n - k)): (resid_j / sd_j)^2 summed over a column
+struct ResidOverScaledSelf {
+  const double* resid; double inv;
+  __device__ double operator()(int64_t j) const { return resid[j] / (resid[j] * inv); }
+};
 struct QOverSig {
   const double* q; const double* resid; double inv_n;
   __device__ double operator()(int64_t j) const { return q[j] / (resid[j] * inv_n); }
@@ -318,6 +323,10 @@ int fb_identity_err(fable_ctx* ctx, const double* dA, int64_t k, double* max_dif
 
 int fb_sum_log_scaled(fable_ctx* ctx, const double* d_x, int64_t p, double scale, double* host_out) {
   return reduce_to_host(ctx, LogScaled{d_x, scale}, p, host_out);
+}
+
+int fb_resid_over_scaled_self_sum(fable_ctx* ctx, const double* d_resid, int64_t p, double inv, double* host_sum) {
+  return reduce_to_host(ctx, ResidOverScaledSelf{d_resid, inv}, p, host_sum);
 }
 
 int fb_loglik_terms(fable_ctx* ctx, const double* d_resid, const double* d_sig, int64_t p, double* sum_log_sd,

@@ -214,6 +214,24 @@ int fable_posterior_post_processing(fable_posterior* post, int64_t MC, int64_t m
                                     int64_t S, const double* gam_inj, const double* z_inj, double* PostMean,
                                     double* Lower, double* Upper);
 
+/* ---- f3: the pure-R prototype path CCFABLE_DirectSampler (R/FABLE_code.R:212-298) ------------------------------
+ * The prototype picks the rank with its own RankEstimator (R:32-186): the same bisection and window as the C++ one over
+ * a different criterion -- sigma_j^2 = resid_j / (n - k) (:87), log-likelihood and penalty scaled by 1 / (n p) (:106-114).
+ * fable_criterion_proto / fable_rank_estimator_proto are that criterion and rule at the CPP* boundary (U, V, d given).
+ * fable_direct_sampler_begin = R:214-263 (svd, kMax at 0.95, that rank rule, the shrunk row posterior, a_n without
+ * variance inflation, the entry-wise correction B = cov_correct_matrix(sigma^2, G) on); fable_direct_sampler_draws = the
+ * MC loop (:267-294): CovSampleStor, an (MC, p, p) array with the FIRST index fastest (element (m, u, v) at
+ * m + MC (u + p v)), draws m0 .. m0+MC-1 of the native stream or injected gam / z.  MC p^2 doubles must stay below
+ * 32 GB (the prototype's own comments send larger problems to the sampler + post-processing route, :209-211). */
+int fable_criterion_proto(fable_ctx* ctx, int kInd, const double* Y, int64_t n, int64_t p, const double* U,
+                          const double* V, const double* d, int64_t r, double* out);
+int fable_rank_estimator_proto(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, const double* U, const double* V,
+                               const double* d, int64_t r, int kMax, int* kEst);
+int fable_direct_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0, double delta0sq,
+                               int* kMax, int* kEst, fable_posterior** post);
+int fable_direct_sampler_draws(fable_posterior* post, int64_t MC, int64_t m0, const double* gam_inj, const double* z_inj,
+                               double* CovSampleStor);
+
 /* ---- resident-in-HBM posterior object (what fable_sampler is built from) ---------------------- */
 /* Uploads Y, U_k, V_k, d_k, runs the row-posterior kernels, keeps G0 / gnd / a_n on the device. */
 int fable_posterior_create(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double gamma0,

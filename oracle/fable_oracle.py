@@ -37,6 +37,7 @@ __all__ = [
     "svd_thin", "kmax_rule", "criterion", "bisection", "rank_estimator", "row_stats",
     "hyper_parameters", "cov_correct_matrix_R", "cpp_cov_correct_matrix", "var_inflation_wrapper",
     "var_inflation_script", "post_mean", "sampler", "psi_draw", "psi_moments", "arma_quantile",
+    "criterion_R", "rank_estimator_R", "ccfable_direct_sampler",
     "post_processing", "post_processing_submatrix", "symmetrize", "FABLEPosteriorMean",
     "FABLEPosteriorSampler", "log_likelihood_eval", "direct_sampler_psi",
 ]
@@ -342,6 +343,48 @@ def direct_sampler_psi(Y, gamma0, delta0sq, U, V, d, k, gam, z):
         part2 = a_n * (SZG + SZG.T) + a_n ** 2 * ((Z @ Z.T) * np.outer(np.sqrt(s2), np.sqrt(s2)))   # R:283-284
         out[m] = G + CC * part2 + np.diag(s2)                 # R:286-290
     return out
+
+
+def log_likelihood_evaluator_R(Y, M, Lambda, SigmaSq):
+    """LogLikelihoodEvaluator (R/FABLE_code.R:12-28): the Gaussian log-likelihood scaled by 1 / (n p)."""
+    n, p = Y.shape
+    sd = np.sqrt(SigmaSq)                                     # R:17
+    D = (Y - M @ Lambda.T) / sd[None, :]                      # R:19-20
+    return float((-n * np.sum(np.log(sd))) + (-0.5 * np.sum(D * D))) / (n * p)    # R:21-26
+
+
+def criterion_R(kInd, Y, U, V, d):
+    """CriterionFunction inside the pure-R prototype RankEstimator (R/FABLE_code.R:57-116): sigma^2 = resid / (n - k) (:87),
+    Lambda = YtU / sqrt(n) (:96), M = sqrt(n) U_k (:102), -2 LogLik + k max(n,p) log(min(n,p)) / (n p) (:113-114)."""
+    n, p = Y.shape
+    Uk, Vk, dk = U[:, :kInd], V[:, :kInd], d[:kInd]
+    UDVt = (Uk * dk) @ Vk.T                                   # R:86
+    sig = np.sum((Y - UDVt) ** 2, axis=0) / (n - kInd)        # R:87
+    YtU = Vk * dk                                             # R:94
+    ll = log_likelihood_evaluator_R(Y, math.sqrt(n) * Uk, YtU / math.sqrt(n), sig)     # R:96-106
+    return (-2.0 * ll) + (kInd * max(n, p) * math.log(min(n, p)) / (n * p))             # R:113-114
+
+
+def rank_estimator_R(Y, U, V, d, kMax):
+    """RankEstimator (R/FABLE_code.R:32-186): BisectionRecursion (:118-164, as.integer midpoints) from [1, kMax], then the
+    criterion on the whole final window and which.min = the first minimum (:166-184)."""
+    fn = lambda k: criterion_R(k, Y, U, V, d)
+    lo, hi = bisection(1, int(kMax), fn)
+    ks = list(range(lo, hi + 1))
+    return ks[int(np.argmin([fn(k) for k in ks]))]
+
+
+def ccfable_direct_sampler(Y, gamma0, delta0sq, MC, gam, z, svd=None):
+    """CCFABLE_DirectSampler(Y, gamma0, delta0sq, MC) (R/FABLE_code.R:212-298) with injected draws: svd, kMax at 0.95
+    (:219), the prototype's RankEstimator (:221), then the draws of direct_sampler_psi.  z: array (MC, k, p) or a callable
+    (MC, k, p) -> array.  Returns (k, array (MC, p, p)).  `svd` = (u, d, v) replaces svd(Y): for FIXED injected normals the
+    draws depend on the signs of the singular vectors, so a comparison needs both sides on the same signs."""
+    Y = np.asarray(Y, dtype=np.float64)
+    u, d, v = svd if svd is not None else svd_thin(Y)         # R:216
+    kMax = kmax_rule(d, 0.95)                                 # R:219
+    k = rank_estimator_R(Y, u, v, d, kMax)                    # R:221
+    zz = z(MC, k, Y.shape[1]) if callable(z) else z
+    return k, direct_sampler_psi(Y, gamma0, delta0sq, u, v, d, k, gam, zz)
 
 
 def log_likelihood_eval(Y, M, Lambda, SigmaSq):

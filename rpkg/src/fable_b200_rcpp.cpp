@@ -280,3 +280,30 @@ Rcpp::List FABLEsvd(Rcpp::NumericMatrix Y) {
   check(fable_svd(ctx(), Y.begin(), n, p, U.begin(), d.begin(), V.begin()));
   return Rcpp::List::create(Rcpp::Named("d") = d, Rcpp::Named("u") = U, Rcpp::Named("v") = V);
 }
+
+// f3 -- the pure-R prototype path (R/FABLE_code.R).  The R-level functions RankEstimator(Ymat, svdmod, kMax) (:32-186) and
+// CCFABLE_DirectSampler(Y, gamma0, delta0sq, MC) (:212-298) keep their signatures in rpkg/R/FABLE_code.R and call these.
+// [[Rcpp::export]]
+int RankEstimatorB200(Rcpp::NumericMatrix Ymat, Rcpp::NumericMatrix U_Y, Rcpp::NumericMatrix V_Y, Rcpp::NumericVector svalsY, int kMax) {
+  Svd s(Ymat, U_Y, V_Y, svalsY);
+  int k = 0;
+  check(fable_rank_estimator_proto(ctx(), s.Y, s.n, s.p, s.U, s.V, s.d, s.r, kMax, &k));
+  return k;
+}
+
+// returns the (MC, p, p) array CovSampleStor as a numeric vector with a dim attribute set on the R side
+// [[Rcpp::export]]
+Rcpp::NumericVector CCFABLEDirectSamplerB200(Rcpp::NumericMatrix Y, double gamma0, double delta0sq, int MC) {
+  const int64_t n = Y.nrow(), p = Y.ncol();
+  if (MC < 1) Rcpp::stop("MC must be >= 1");
+  reseed();
+  struct PostGuard {
+    fable_posterior* p = nullptr;
+    ~PostGuard() { fable_posterior_destroy(p); }
+  } guard;
+  int kMax = 0, k = 0;
+  check(fable_direct_sampler_begin(ctx(), Y.begin(), n, p, gamma0, delta0sq, &kMax, &k, &guard.p));
+  Rcpp::NumericVector out(static_cast<R_xlen_t>(MC) * p * p);
+  check(fable_direct_sampler_draws(guard.p, MC, 0, nullptr, nullptr, out.begin()));
+  return out;
+}

@@ -434,6 +434,39 @@ def test_c4_like_ranks_above_one_chunk(ctx, n, p, k, B):
     post.close()
 
 
+@pytest.mark.parametrize("n,p,k,seed", [(60, 150, 3, 5), (80, 64, 2, 6), (120, 400, 6, 7), (50, 257, 1, 8)])
+def test_prototype_rank_rule_and_direct_sampler_f3(ctx, n, p, k, seed, monkeypatch):
+    """The pure-R prototype path as a callable (R/FABLE_code.R:32-186, 212-298): its own criterion (sigma^2 = resid / (n - k),
+    everything scaled by 1 / (n p)) and rank rule at the boundary, and CCFABLE_DirectSampler(Y, ...) end to end -- svd, kMax at
+    0.95, that rank rule, entry-wise corrected draws in the (MC, p, p) array -- against the numpy restatement, with
+    injected draws.  (The restatement follows the cited R lines; R itself cannot run here: parity unpinned for this row.)"""
+    Y, u, d, v = _svd_inputs(n, p, k, seed)
+    svdmod = {"u": u, "d": d, "v": v}
+    kMax = orc.kmax_rule(d, 0.95)
+    for kk in (1, 2, 5, kMax):
+        assert abs(fb.RankEstimatorCriterion(kk, Y, svdmod, ctx=ctx) / orc.criterion_R(kk, Y, u, v, d) - 1) < TOL
+    want_k = orc.rank_estimator_R(Y, u, v, d, kMax)
+    for fast in ("1", "0"):
+        monkeypatch.setenv("FABLE_B200_RANK_FAST", fast)
+        assert fb.RankEstimator(Y, svdmod, kMax, ctx=ctx) == want_k
+    monkeypatch.delenv("FABLE_B200_RANK_FAST")
+    MC = 5
+    gam = np.random.default_rng(seed).gamma(0.5 * (1.0 + n), 1.0, size=(MC, p))
+    zfn = lambda MC_, k_, p_: np.random.default_rng(seed + 1).standard_normal((MC_, k_, p_))
+    # for fixed injected normals the draws depend on the signs of the singular vectors (SURVEY A.5): put the oracle's SVD on
+    # the library's sign convention (largest |entry| of every right vector positive)
+    sgn = np.sign(v[np.argmax(np.abs(v), axis=0), np.arange(v.shape[1])])
+    k_ref, want = orc.ccfable_direct_sampler(Y, 1.0, 1.0, MC, gam, zfn, svd=(u * sgn, d, v * sgn))
+    info = {}
+    got = fb.CCFABLE_DirectSampler(Y, 1.0, 1.0, MC, ctx=ctx, gam=gam, z=zfn, info=info)
+    assert info["k"] == k_ref == want_k and info["kMax"] == kMax
+    assert got.shape == (MC, p, p) and got.flags.f_contiguous
+    assert relerr_mat(got, want) < TOL
+    assert np.array_equal(got, got.transpose(0, 2, 1))
+    nat = fb.CCFABLE_DirectSampler(Y, 1.0, 1.0, 3, ctx=ctx)                     # native stream: runs, symmetric, finite
+    assert nat.shape == (3, p, p) and np.all(np.isfinite(nat)) and np.array_equal(nat, nat.transpose(0, 2, 1))
+
+
 @pytest.mark.parametrize("n,p,k", [(60, 160, 3), (40, 77, 2), (50, 130, 17)])
 def test_entrywise_corrected_draws_f3(ctx, n, p, k):
     """CCFABLE_DirectSampler (R/FABLE_code.R:212-298): G + B o (Lambda Lambda' - G) + diag(sigma2), B on the fly."""

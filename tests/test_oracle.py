@@ -215,6 +215,23 @@ def test_arma_quantile_at_p_max_is_the_maximum():
         assert orc.arma_quantile(x, alpha / 2.0) == x.min()
 
 
+def test_prototype_criterion_known_structure():
+    """R prototype criterion (R/FABLE_code.R:57-116): with sigma^2 = resid / (n - k) the quadratic term of the log-likelihood is
+    exactly -p (n - k) / 2, so criterion_R(k) = [n sum_j log sigma_j^2 + p (n - k) + k max(n,p) log min(n,p)] / (n p)."""
+    from fable_b200 import synth
+    n, p = 40, 90
+    Y = synth.factor_data(n, p, 3, rep=2)
+    u, d, v = orc.svd_thin(Y)
+    for k in (1, 3, 7):
+        resid = np.sum((Y - (u[:, :k] * d[:k]) @ v[:, :k].T) ** 2, axis=0)
+        want = (n * np.sum(np.log(resid / (n - k))) + p * (n - k) + k * max(n, p) * math.log(min(n, p))) / (n * p)
+        assert orc.criterion_R(k, Y, u, v, d) == pytest.approx(want, rel=1e-12)
+    kMax = orc.kmax_rule(d, 0.95)
+    k_r = orc.rank_estimator_R(Y, u, v, d, kMax)
+    vals = [orc.criterion_R(k, Y, u, v, d) for k in range(1, kMax + 1)]
+    assert 1 <= k_r <= kMax and vals[k_r - 1] <= min(vals) + 1e-3          # bisection lands in a near-minimal window (Q1)
+
+
 def test_post_processing_mean_matches_moments():
     n, p, k, MC = 25, 6, 2, 11
     Y = synth.factor_data(n, p, k, rep=9)
