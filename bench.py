@@ -44,7 +44,7 @@ WORKLOADS = {
     "c1": dict(n=500, p=1000, k=10, batch=64, e2e_mc=1000, ref_mc=256),
     "c2": dict(n=1000, p=5000, k=10, batch=32, e2e_mc=2000, ref_mc=128),
     "c3": dict(n=1000, p=20000, k=10, batch=40, e2e_mc=8192, ref_mc=16),    # 40 slots x 3.2 GB = 128 GB of the 183 GB
-    "c4": dict(n=500, p=50000, k=20, batch=0, e2e_mc=256, ref_mc=4),     # 20 GB per p x p: tiles over the GPUs
+    "c4": dict(n=500, p=50000, k=20, batch=0, e2e_mc=1024, ref_mc=4),    # 20 GB per p x p: tiles over the GPUs
 }
 RING_BUDGET_GB = 120.0     # tile partition: HBM given to the ring of materialised draws (per GPU)
 

@@ -7,7 +7,7 @@
 // (:692-693).  Storing the values is out of the question at scale (p^2 MC / 2 doubles), so the values are RECOMPUTED from
 // the draws -- they cost 2k flops each on the FP64 tensor cores -- and the order statistics are found by an exact
 // most-significant-digit radix selection over several passes:
-//   * a CTA owns 64 x 32 entries (8 per thread, in the DMMA accumulator layout of the covariance kernel); per pass it
+//   * a CTA of 16 warps owns 64 x 32 entries (4 per thread, in the DMMA accumulator layout of the covariance kernel); per pass it
 //     streams its 96 rows of every draw from HBM/L2 (cp.async, double-buffered), forms the block with DMMA and folds the
 //     values into per-entry state that never leaves the SM;
 //   * pass A: sum (-> mean), minimum and maximum of every entry.  They define a per-entry order-preserving 52-bit key
@@ -30,8 +30,8 @@ namespace {
 
 constexpr int TILE = 64, TV = 32;
 constexpr int OSTR = TILE + 4, VSTR = TV + 4;      // operand row strides (4 mod 16: conflict-free DMMA fragment loads)
-constexpr int PT = 256;
-constexpr int NE = 8;                              // entries per thread: 2 (i) x 2 (j) x 2 (e)
+constexpr int PT = 512;                            // 16 warps: 4 along u (16 rows each) x 4 along v (8 columns each)
+constexpr int NE = 4;                              // entries per thread: 2 (i: 8-row DMMA tiles) x 2 (h: adjacent columns)
 constexpr int NB = 16;                             // bins per digit (4 bits)
 constexpr int NDIG = 13;                           // 13 x 4 = 52 key bits
 constexpr int CAP = 16;                            // candidates kept per (entry, level)
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(PT, 1) k_post_tiles(PostTileArgs a) {
   __shared__ long long s_iu[TILE], s_iv[TV];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int wu = warp & 3, wv = warp >> 2;                          // 4 warps along u (16 rows), 2 along v (16 columns)
+  const int wu = warp & 3, wv = warp >> 2;                          // 4 warps along u (16 rows), 4 along v (8 columns)
   const int nchunks = KP * (TILE / 2) + KP * (TV / 2) + TILE / 2;   // 16-byte pieces per draw
   double* myscratch = a.scratch + (static_cast<int64_t>(blockIdx.x) * PT + tid) * (2 * NE * CAP);
 
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(PT, 1) k_post_tiles(PostTileArgs a) {
     unsigned same = 0, valid = 0;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-      const int ul = wu * 16 + (e >> 2) * 8 + g, vl = wv * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+      const int ul = wu * 16 + (e >> 1) * 8 + g, vl = wv * 8 + 2 * t + (e & 1);
       if (u0 + ul < a.S && v0 + vl < a.S) valid |= 1u << e;
       if (s_iu[ul] == s_iv[vl]) same |= 1u << e;
     }
@@ -137,29 +137,24 @@ __global__ void __launch_bounds__(PT, 1) k_post_tiles(PostTileArgs a) {
         const int buf = static_cast<int>(m & 1);
         if (m + 1 < a.MC) prefetch(m + 1, buf ^ 1);
         const double* As = op + buf * opd + wu * 16 + g + t * OSTR;
-        const double* Bs = op + buf * opd + KP * OSTR + wv * 16 + g + t * VSTR;
+        const double* Bs = op + buf * opd + KP * OSTR + wv * 8 + g + t * VSTR;
         const double* s2 = op + buf * opd + KP * (OSTR + VSTR);
-        double c[2][2][2];
+        double c[2][2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+        for (int i = 0; i < 2; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
         for (int ks = 0; ks < KP / 4; ++ks) {
-          double af[2], bf[2];
+          double af[2];
 #pragma unroll
           for (int i = 0; i < 2; ++i) af[i] = As[ks * 4 * OSTR + i * 8];
+          const double bf = Bs[ks * 4 * VSTR];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) bf[j] = Bs[ks * 4 * VSTR + j * 8];
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) dmma(c[i][j], af[i], bf[j]);
+          for (int i = 0; i < 2; ++i) dmma(c[i], af[i], bf);
         }
         double x[NE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-          x[e] = c[e >> 2][(e >> 1) & 1][e & 1];
-          if (same & (1u << e)) x[e] += s2[wu * 16 + (e >> 2) * 8 + g];          // + sigma2_m[j1] (cpp:676-684)
+          x[e] = c[e >> 1][e & 1];
+          if (same & (1u << e)) x[e] += s2[wu * 16 + (e >> 1) * 8 + g];          // + sigma2_m[j1] (cpp:676-684)
         }
         f(m, x);
         cp_wait_all();
@@ -199,7 +194,7 @@ __global__ void __launch_bounds__(PT, 1) k_post_tiles(PostTileArgs a) {
       }
 
     for (int d = 0; d < NDIG; ++d) {
-      if (__syncthreads_and(done == 0xFFFFu)) break;
+      if (__syncthreads_and(done == ((1u << (2 * NE)) - 1u))) break;
       for (int i = tid; i < 2 * NE * NB * PT; i += PT) hist[i] = 0;          // (a thread clears its own column: i % PT == tid)
       const int sh_pref = 52 - 4 * d, sh_dig = 48 - 4 * d;
       stream([&](int64_t, const double (&x)[NE]) {
@@ -272,7 +267,7 @@ __global__ void __launch_bounds__(PT, 1) k_post_tiles(PostTileArgs a) {
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       if (!(valid & (1u << e))) continue;
-      const int ul = wu * 16 + (e >> 2) * 8 + g, vl = wv * 16 + ((e >> 1) & 1) * 8 + 2 * t + (e & 1);
+      const int ul = wu * 16 + (e >> 1) * 8 + g, vl = wv * 8 + 2 * t + (e & 1);
       const int64_t ra = u0 + ul, rb = v0 + vl;
       double res[2];
 #pragma unroll
