@@ -332,7 +332,9 @@ int fable_posterior_accum_fetch_superblocks(fable_posterior* post, int64_t sb_be
                                             double* sumsq);
 /* accumulators: device pointers to the compact upper tiles of the slice (count doubles each = tiles * 4096; the
  * one NCCL sum of multi-GPU partition A -- draws sharded over ranks -- reduces these buffers as they are), reset,
- * fetch as dense symmetric p x p host matrices (zeros outside the slice), fetch as raw compact tiles. */
+ * fetch as dense symmetric p x p host matrices (zeros outside the slice), fetch as raw compact tiles.
+ * (Materialising batches keep their sums in a few partial buffers first -- no DRAM reads inside the write-bound
+ * covariance kernel -- which every one of these calls folds into the accumulators before it looks at them.) */
 int fable_posterior_accum_dev(fable_posterior* post, double** dev_sum, double** dev_sumsq, int64_t* count);
 int fable_posterior_accum_reset(fable_posterior* post);
 int fable_posterior_accum_fetch(fable_posterior* post, double* sum, double* sumsq);            /* host out */
