@@ -79,7 +79,7 @@ struct fable_ctx {
 // call (accumulators, sample layouts, residuals), and cudaMalloc / cudaFree of such blocks map and unmap device
 // memory synchronously -- tens to hundreds of milliseconds per call, with outliers.  Released blocks are therefore
 // kept per device and handed out again to requests of the same rounded size; the cache is bounded
-// (FABLE_B200_CACHE_GB, default 24), flushed when an allocation fails, and emptied by fb_mem_trim().
+// (FABLE_B200_CACHE_GB, default 40), flushed when an allocation fails, and emptied by fb_mem_trim().
 cudaError_t fb_mem_acquire(void** ptr, size_t bytes);
 void fb_mem_release(void* ptr);
 void fb_mem_trim(int device);      // device < 0: every device
@@ -208,8 +208,9 @@ int fb_tiles_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t p, int64_t 
 // cbase) -> its dense block(s): d_direct = rows [1024 sI, ..) x columns [1024 sJ, ..) (nr x nc, ld nr) and, for an
 // off-diagonal super-block, d_mirror = the transposed block (nc x nr, ld nc); a diagonal super-block gives the full
 // symmetric block in d_direct alone.
+// (ld_direct / ld_mirror > 0: leading dimensions of the two targets, e.g. p when they point into a dense p x p matrix)
 int fb_superblock_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t cbase, int64_t p, int64_t sb, double* d_direct,
-                           double* d_mirror);
+                           double* d_mirror, int64_t ld_direct = 0, int64_t ld_mirror = 0);
 // a batch of B materialised draws (slot stride p2) -> rows m_off .. m_off + B - 1 of an (ldm, p, p) array, first index fastest
 int fb_slots_to_marray(fable_ctx* ctx, const double* d_slots, int B, int64_t p2, int64_t ldm, int64_t m_off, double* d_out);
 // dst (k rows of pp, zero-padded) <- src (k rows of lds, p valid)

@@ -506,8 +506,8 @@ __global__ void __launch_bounds__(256) k_tiles_to_dense(const double* __restrict
 
 // One super-block of compact upper tiles -> dense block(s); grid (16, 16) = (i, j) tile of the super-block.
 __global__ void __launch_bounds__(256) k_superblock_to_dense(const double* __restrict__ tiles, int nT, int64_t cbase, int64_t p, int sI,
-                                                             int sJ, int64_t nr, int64_t nc, double* __restrict__ direct,
-                                                             double* __restrict__ mirror) {
+                                                             int sJ, int64_t nr, int64_t nc, double* __restrict__ direct, int64_t ldd,
+                                                             double* __restrict__ mirror, int64_t ldm) {
   __shared__ double sm[TILE][TILE + 1];
   const int i = blockIdx.x, j = blockIdx.y;
   const int I = sI * SB + i, J = sJ * SB + j;
@@ -519,12 +519,12 @@ __global__ void __launch_bounds__(256) k_superblock_to_dense(const double* __res
     const double v = src[cc * TILE + tx];                          // tile(u = tx, v = cc)
     sm[cc][tx] = v;
     const int64_t r = static_cast<int64_t>(i) * TILE + tx, c = static_cast<int64_t>(j) * TILE + cc;
-    if (r < nr && c < nc) direct[r + nr * c] = v;
+    if (r < nr && c < nc) direct[r + ldd * c] = v;
   }
   if (diag_sb && I == J) return;                                   // (a diagonal tile is its own mirror image)
   __syncthreads();
   double* out = diag_sb ? direct : mirror;                         // diagonal super-block: lower part of the same block
-  const int64_t ld = diag_sb ? nr : nc;
+  const int64_t ld = diag_sb ? ldd : ldm;
   for (int cc = ty; cc < TILE; cc += 4) {
     // element (row = 64 j + tx, column = 64 i + cc) of the transposed block = tile(u = cc, v = tx)
     const int64_t r = static_cast<int64_t>(j) * TILE + tx, c = static_cast<int64_t>(i) * TILE + cc;
@@ -747,7 +747,7 @@ int fb_pad_rows(fable_ctx* ctx, const double* src, int64_t lds, int64_t p, int64
 }
 
 int fb_superblock_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t cbase, int64_t p, int64_t sb, double* d_direct,
-                           double* d_mirror) {
+                           double* d_mirror, int64_t ld_direct, int64_t ld_mirror) {
   const int nT = static_cast<int>(fbt::n_tiles(p));
   int sI, sJ;
   fbt::tri_of(sb, sI, sJ);
@@ -755,7 +755,8 @@ int fb_superblock_to_dense(fable_ctx* ctx, const double* d_tiles, int64_t cbase,
   const int64_t r0 = sI * span, c0 = sJ * span;
   FB_REQUIRE(ctx, c0 < p, "superblock_to_dense: super-block outside the matrix");
   const int64_t nr = p - r0 < span ? p - r0 : span, nc = p - c0 < span ? p - c0 : span;
-  k_superblock_to_dense<<<dim3(SB, SB), 256, 0, ctx->stream>>>(d_tiles, nT, cbase, p, sI, sJ, nr, nc, d_direct, d_mirror);
+  k_superblock_to_dense<<<dim3(SB, SB), 256, 0, ctx->stream>>>(d_tiles, nT, cbase, p, sI, sJ, nr, nc, d_direct, ld_direct > 0 ? ld_direct : nr,
+                                                                d_mirror, ld_mirror > 0 ? ld_mirror : nc);
   FB_LAUNCHED(ctx);
   return FABLE_OK;
 }

@@ -56,7 +56,7 @@ int fable_ctx_set_interrupt(fable_ctx* ctx, int (*poll)(void*), void* user);
 /* number of kernels this context has launched since creation (bench.py "gpu_launches"). */
 int64_t fable_ctx_launch_count(const fable_ctx* ctx);
 /* Work buffers released by the entry points are kept in a per-device block cache (bounded by FABLE_B200_CACHE_GB,
- * default 24, flushed automatically when an allocation fails, emptied when the context is destroyed) so that
+ * default 40, flushed automatically when an allocation fails, emptied when the context is destroyed) so that
  * repeated calls do not pay cudaMalloc / cudaFree of multi-GB blocks.  This returns the idle blocks to the driver
  * now, e.g. before another library needs the memory.  (No reference counterpart: R's gc() plays this role.) */
 int fable_ctx_trim_cache(fable_ctx* ctx);
