@@ -182,10 +182,20 @@ k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int6
 // pairs inside a block need one visit per outer sweep, not one per round: round 0 of every sweep runs the full 63-step
 // ordering, the other rounds the cross pairs, so an outer sweep is an exact cyclic sweep over all element pairs.  Same
 // 14-15 outer sweeps, 40 % less time (measured at n = 500, 1000, 2000).
+// REPLAY (cross_only launches with one inner sweep): the CTA does not carry R at all.  A step is bound by the shared-memory
+// pipe (per warp 21 wavefronts for the H block + 18 for its two R row pairs: 1250 of the ~2000 cycles of a step on the one SM
+// a pair occupies), and R <- R J is row-wise independent work that only needs the rotations: warp 0 writes every rotation
+// it derives to global memory as well (32 steps x 32 pairs x (c, s) = 16 KB per block pair) and k_bj_replay rebuilds R from
+// them on 8 CTAs per pair, one warp per row of R.  mode[pair]: 0 = nothing to rotate (R = I), 1 = rotations recorded,
+// 2 = R written here (full ordering / legacy path).
 constexpr int EIGT = 1024;
+#ifdef BJ_LAB
+__device__ int bj_lab_count = 0;
+#endif
+template <bool REPLAY>
 __global__ void __launch_bounds__(EIGT)
 k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2, int inner, int cross_only, double* __restrict__ Rout,
-         int* __restrict__ nrot) {
+         int* __restrict__ nrot, double2* __restrict__ rots, int* __restrict__ mode, int iso) {
   constexpr int S = PW + 1;
   extern __shared__ double dsm[];
   double* H = dsm;
@@ -221,7 +231,7 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
     for (int e = 0; e < NE; ++e) {
       const int idx = tid + e * EIGT, a = idx & (PW - 1), b = idx >> 6;
       H[a * S + b] = v[e];
-      R[a * S + b] = (a == b) ? 1.0 : 0.0;
+      if (!(REPLAY && cross_only)) R[a * S + b] = (a == b) ? 1.0 : 0.0;
     }
   }
   if (tid == 0) { any_rot = 0; need = 0; }
@@ -235,6 +245,104 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
     }
   }
   __syncthreads();
+  if (tid == 0 && mode) mode[blockIdx.x] = (REPLAY && cross_only) ? (need ? 1 : 0) : 2;
+  double2* rots_pair = REPLAY ? rots + static_cast<int64_t>(blockIdx.x) * (BW * BW) : nullptr;
+  if constexpr (REPLAY) {
+    if (cross_only && !(iso & 2)) {
+      // Symmetric form of the pipelined cross steps below (which it replaces when the rotations are recorded).  Measured
+      // with clock64 in the form below (tools: -DBJ_LAB): a step took 1470 cycles, the deriving warp 0 was busy for 1360 of
+      // them and every applying warp for 920 -- the 31 warps' 650 shared-memory wavefronts per step queue in front of warp
+      // 0's own twelve loads, and their FP64 instructions in front of its dependent chain (alone on its scheduler: 810).
+      // So (i) H is kept as its upper triangle only: entry (r, c) lives at [min][max], a block (row pair a, column pair b)
+      // with a <= b is rotated from both sides by one thread and its mirror image is never formed -- 528 blocks on 17 warps
+      // instead of 1024 on 31, 24 instead of 21 wavefronts per warp; (ii) those 17 warps are the ones that do NOT share a
+      // scheduler with warp 0 (warp ids 1-3, 5-7, .. 21-22), the other warps leave; (iii) the step barrier is a named
+      // barrier of the 18 warps.  A diagonal block needs no special case: its (q, p) address is its (p, q) address.
+      if (!need) return;
+      if (tid == 0) atomicAdd(nrot, 1);
+      const int lane = tid & 31, w = tid >> 5;
+      const bool applies = (w & 3) != 0 && w <= 22;
+      if (w != 0 && !applies) return;
+      const int v = w - 1 - (w >> 2);                    // 0 .. 16 over the applying warps
+      int a, b;
+      if (v < 16) {
+        if (lane >= v) { a = v; b = lane; } else { a = 31 - v; b = 32 - v + lane; }
+      } else {
+        a = b = 16 + (lane & 15);
+      }
+      const bool has_block = applies && (v < 16 || lane < 16);
+      auto rotation = [&](double hpq, double hpp, double hqq, double2& cs_) {
+        cs_ = make_double2(1.0, 0.0);
+        if (hpq != 0.0 && hpq * hpq > tol2 * hpp * hqq && hpp > floor2 && hqq > floor2) {
+          const double d = hqq - hpp, h2 = 2.0 * hpq, r2 = fma(d, d, h2 * h2);
+          const double tt = h2 * (1.0 / (d + copysign(r2 * rsqrt(r2), d)));
+          const double c_ = rsqrt(fma(tt, tt, 1.0));
+          cs_ = make_double2(c_, c_ * tt);
+        }
+      };
+      if (w == 0) {
+        const int q = BW + lane;
+        double2 r0;
+        rotation(H[lane * S + q], H[lane * S + lane], H[q * S + q], r0);
+        rot2[0][lane] = r0;
+        rots_pair[lane] = r0;
+      }
+      asm volatile("bar.sync 1, 576;" ::: "memory");
+      int cur = 0, nxt = 2 * PW * S;
+      int o_a = a, o_b = b, o_l = lane;                  // (index + step) % 32
+#ifdef BJ_LAB
+      long long lab_busy = 0, lab_t0 = clock64();
+#endif
+      for (int step = 0; step < BW; ++step) {
+        const double2* rr = rot2[step & 1];
+        const double* Hc = dsm + cur;
+        double* Hn = dsm + nxt;
+#ifdef BJ_LAB
+        const long long lab_s = clock64();
+#endif
+        if (w == 0) {
+          if (step + 1 < BW) {
+            const int i = lane, i1 = (i + 1) & (BW - 1), qi = BW + o_l, qn = BW + ((o_l + 1) & (BW - 1));
+            const int ilo = i < i1 ? i : i1, ihi = i < i1 ? i1 : i, qlo = qi < qn ? qi : qn, qhi = qi < qn ? qn : qi;
+            const double2 r1 = rr[i], r2 = rr[i1];
+            const double h_ii = Hc[i * S + i], h_iqi = Hc[i * S + qi], h_qiqi = Hc[qi * S + qi];
+            const double h_11 = Hc[i1 * S + i1], h_1qn = Hc[i1 * S + qn], h_qnqn = Hc[qn * S + qn];
+            const double h_i1 = Hc[ilo * S + ihi], h_iqn = Hc[i * S + qn], h_1qi = Hc[i1 * S + qi], h_qiqn = Hc[qlo * S + qhi];
+            const double ap = r1.x * h_ii - r1.y * h_iqi, aq = r1.x * h_iqi - r1.y * h_qiqi;
+            const double hii = r1.x * ap - r1.y * aq;                                             // H'[i][i]
+            const double bp1 = r2.y * h_11 + r2.x * h_1qn, bq1 = r2.y * h_1qn + r2.x * h_qnqn;
+            const double hqq = r2.y * bp1 + r2.x * bq1;                                           // H'[qn][qn]
+            const double bp = r2.y * h_i1 + r2.x * h_iqn, bq = r2.y * h_1qi + r2.x * h_qiqn;
+            const double hpq = r1.x * bp - r1.y * bq;                                             // H'[i][qn]
+            double2 rn;
+            rotation(hpq, hii, hqq, rn);
+            rot2[(step + 1) & 1][i] = rn;
+            rots_pair[(step + 1) * BW + i] = rn;
+          }
+        } else if (has_block) {
+          const double2 r1 = rr[a], r2 = rr[b];
+          const int lo = o_a < o_b ? o_a : o_b, hi = o_a < o_b ? o_b : o_a;
+          const int A_pp = a * S + b, A_pq = a * S + BW + o_b, A_qp = b * S + BW + o_a, A_qq = (BW + lo) * S + BW + hi;
+          const double hpp_ = Hc[A_pp], hpq_ = Hc[A_pq], hqp_ = Hc[A_qp], hqq_ = Hc[A_qq];
+          const double ap = r2.x * hpp_ - r2.y * hpq_, bp = r2.y * hpp_ + r2.x * hpq_;
+          const double aq = r2.x * hqp_ - r2.y * hqq_, bq = r2.y * hqp_ + r2.x * hqq_;
+          Hn[A_pp] = r1.x * ap - r1.y * aq; Hn[A_qp] = r1.y * ap + r1.x * aq;
+          Hn[A_pq] = r1.x * bp - r1.y * bq; Hn[A_qq] = r1.y * bp + r1.x * bq;
+        }
+#ifdef BJ_LAB
+        lab_busy += clock64() - lab_s;
+#endif
+        asm volatile("bar.sync 1, 576;" ::: "memory");
+        const int tswap = cur; cur = nxt; nxt = tswap;
+        o_a = (o_a + 1) & (BW - 1); o_b = (o_b + 1) & (BW - 1); o_l = (o_l + 1) & (BW - 1);
+      }
+#ifdef BJ_LAB
+      if (blockIdx.x == 0 && lane == 0 && (w == 0 || w == 1 || w == 5 || w == 22) && atomicAdd(&bj_lab_count, 1) / 4 == 300)
+        printf("BJ_LAB(sym) warp %2d: busy %lld cycles of %lld for 32 steps\n", w, lab_busy, clock64() - lab_t0);
+#endif
+      return;
+    }
+  }
   if (need && cross_only) {
     // Cross pairs, software-pipelined: step s rotates (i, 32 + (i + s) % 32), i = 0 .. 31.  While warps 1-31 apply step s
     // (H_next = J' H_cur J into the OTHER buffer, R <- R J in place), warp 0 derives the rotations of step s + 1: the three
@@ -269,15 +377,22 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
         double2 r0;
         rotation(Hc[tid * S + q], Hc[tid * S + tid], Hc[q * S + q], r0);
         rot2[0][tid] = r0;
+        if (REPLAY) rots_pair[tid] = r0;
         if (r0.y != 0.0) any_rot = 1;
       }
       __syncthreads();
       // rotating column offsets: o = (index + step) % 32
       int o_lane = lane, o_w = (w - 1) & (BW - 1), o_r0 = (tid - BW) >> 6, o_r1 = ((tid - BW) >> 6) + 16;
+#ifdef BJ_LAB
+      long long lab_busy = 0, lab_t0 = clock64();
+#endif
       for (int step = 0; step < BW; ++step) {
         const double2* rr = rot2[step & 1];
         const double* Hc = dsm + cur;
         double* Hn = dsm + nxt;
+#ifdef BJ_LAB
+        const long long lab_s = clock64();
+#endif
         if (w == 0) {
           if (step + 1 < BW) {
             const int i = lane, i1 = (i + 1) & (BW - 1), qi = BW + o_lane, qn = BW + ((o_lane + 1) & (BW - 1));
@@ -291,15 +406,21 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
             double2 rn;
             rotation(hpq, hii, hqq, rn);
             rot2[(step + 1) & 1][i] = rn;
+            if (REPLAY) rots_pair[(step + 1) * BW + i] = rn;
             if (rn.y != 0.0) any_rot = 1;
           }
+        } else if (iso && (w & 3) == 0) {
+          // iso: warps 4, 8, .. 28 share the scheduler (and its FP64 pipe) of the deriving warp 0 and stay idle; their row
+          // pairs are taken by the next warp
         } else {
           const int q2 = BW + o_lane;
           const double2 r2 = rr[lane];
           block(Hc, Hn, (w - 1) * S, (BW + o_w) * S, lane, q2, rr[w - 1], r2);
+          if (iso && (w & 3) == 1 && w > 1) block(Hc, Hn, (w - 2) * S, (BW + ((o_w - 1) & (BW - 1))) * S, lane, q2, rr[w - 2], r2);
           if (w == BW - 1) block(Hc, Hn, (BW - 1) * S, (BW + ((o_w + 1) & (BW - 1))) * S, lane, q2, rr[BW - 1], r2);
           // R <- R J: thread u = tid - 32 owns row i = u % 64 of the pairs u / 64 and u / 64 + 16 (u < 992: pairs 15 and 31
           // have rows 32 .. 63 left over)
+          if (!REPLAY) {
           const int i = (tid - BW) & (PW - 1);
           {
             const int r = (tid - BW) >> 6;
@@ -330,11 +451,19 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
               R[i2 * S + r] = cs_.x * rp - cs_.y * rq; R[i2 * S + q] = cs_.y * rp + cs_.x * rq;
             }
           }
+          }
         }
+#ifdef BJ_LAB
+        lab_busy += clock64() - lab_s;
+#endif
         __syncthreads();
         const int tswap = cur; cur = nxt; nxt = tswap;
         o_lane = (o_lane + 1) & (BW - 1); o_w = (o_w + 1) & (BW - 1);
       }
+#ifdef BJ_LAB
+      if (blockIdx.x == 0 && lane == 0 && (w == 0 || w == 1 || w == 5 || w == 31) && atomicAdd(&bj_lab_count, 1) / 4 == 300)
+        printf("BJ_LAB warp %2d: busy %lld cycles of %lld for 32 steps (iso %d)\n", w, lab_busy, clock64() - lab_t0, iso);
+#endif
       if (!any_rot) break;
     }
   } else if (need) {
@@ -388,11 +517,46 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
       if (!any_rot) break;
     }
   }
+  if (REPLAY && cross_only) return;                        // k_bj_replay writes R
   double* Rg = Rout + static_cast<int64_t>(blockIdx.x) * (PW * PW);
   for (int idx = tid; idx < PW * PW; idx += EIGT) {
     const int a = idx & (PW - 1), b = idx >> 6;
     Rg[a + PW * b] = R[a * S + b];          // column-major 64 x 64
   }
+}
+
+// R of a block pair from the recorded cross rotations: one warp per row of R, lane i holds the entries of column i (p) and
+// of column 32 + (i + step) % 32 (q) -- the q entries move one lane per step, so step s rotates (i, 32 + (i + s) % 32) as
+// k_bj_eig does.  32 dependent steps of two FMAs and a shuffle: ~1 us, on 8 CTAs per pair instead of inside the one CTA
+// whose shared-memory pipe bounds the round.  grid (pairs, 8), 256 threads.
+__global__ void __launch_bounds__(256)
+k_bj_replay(const double2* __restrict__ rots, const int* __restrict__ mode, double* __restrict__ Rall) {
+  __shared__ double2 rs[BW * BW];                        // the pair's 32 x 32 rotations: one coalesced fetch, then LDS per step
+  const int md = mode[blockIdx.x];                       // (straight from global the 32 loads of a lane were serialised: 8.6 us)
+  if (md == 2) return;
+  const int lane = threadIdx.x & 31, row = blockIdx.y * 8 + (threadIdx.x >> 5);
+  double p = row == lane ? 1.0 : 0.0, q = row == BW + lane ? 1.0 : 0.0;
+  if (md == 1) {
+    const double2* r = rots + static_cast<int64_t>(blockIdx.x) * (BW * BW);
+    double2 v[BW * BW / 256];
+#pragma unroll
+    for (int e = 0; e < BW * BW / 256; ++e) v[e] = r[threadIdx.x + e * 256];
+#pragma unroll
+    for (int e = 0; e < BW * BW / 256; ++e) rs[threadIdx.x + e * 256] = v[e];
+    __syncthreads();
+    double2 cs = rs[lane];
+#pragma unroll
+    for (int s = 0; s < BW; ++s) {
+      const double2 nx = rs[((s + 1) & (BW - 1)) * BW + lane];      // next step's rotation while this one is applied
+      const double np = cs.x * p - cs.y * q, nq = cs.y * p + cs.x * q;
+      p = np;
+      q = __shfl_sync(0xffffffffu, nq, (lane + 1) & 31);
+      cs = nx;
+    }
+  }
+  double* Rg = Rall + static_cast<int64_t>(blockIdx.x) * (PW * PW);
+  Rg[row + PW * lane] = p;
+  Rg[row + PW * (BW + lane)] = q;
 }
 
 // W (rows i0..i0+127 of the pair's 64 columns) <- W R, in place
@@ -565,7 +729,12 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     if (nsplit > ld / 64) nsplit = ld / 64 > 0 ? ld / 64 : 1;
     const int64_t rows_per_split = round_up(ceil_div(ld, nsplit), GKT);
     nsplit = ceil_div(ld, rows_per_split);
-    DevBuf Hpart, Rall;
+    // cross rounds record their rotations and k_bj_replay rebuilds R (FABLE_B200_BJ_REPLAY=0: R carried inside k_bj_eig)
+    const bool replay = cross && inner == 1 && !(getenv("FABLE_B200_BJ_REPLAY") && atoi(getenv("FABLE_B200_BJ_REPLAY")) == 0);
+    const int iso = getenv("FABLE_B200_BJ_ISO") ? atoi(getenv("FABLE_B200_BJ_ISO")) : 0;
+    DevBuf Hpart, Rall, Rots, Mode;
+    FB_CUDA(ctx, Rots.alloc(static_cast<size_t>(npairs) * BW * BW * sizeof(double2)));
+    FB_CUDA(ctx, Mode.alloc(static_cast<size_t>(npairs) * sizeof(int)));
     FB_CUDA(ctx, Wbuf.alloc(static_cast<size_t>(ld) * ncols * sizeof(double)));
     FB_CUDA(ctx, Hpart.alloc(static_cast<size_t>(npairs) * nsplit * PW * PW * sizeof(double)));
     FB_CUDA(ctx, Rall.alloc(static_cast<size_t>(npairs) * PW * PW * sizeof(double)));
@@ -578,7 +747,8 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     bool& attr = attr_dev[ctx->device & 63];
     if (!attr) {
       FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem)));
-      FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eig_smem)));
+      FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_eig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eig_smem)));
+      FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_eig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eig_smem)));
       attr = true;
     }
     // One sweep = NB - 1 rounds x (panel Gram, inner solve, panel update): up to ~470 small launches at m = 5000, identical
@@ -590,8 +760,15 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
       for (int r = 0; r < NB - 1; ++r) {
         k_bj_gram<<<dim3(npairs, static_cast<unsigned>(nsplit)), 128, 0, ctx->stream>>>(Wbuf.d(), ld, rows_per_split, ld, r, NB,
                                                                                          Hpart.d());
-        k_bj_eig<<<npairs, EIGT, eig_smem, ctx->stream>>>(Hpart.d(), static_cast<int>(nsplit), tol, floor2, inner, (cross && r > 0) ? 1 : 0, Rall.d(),
-                                                         static_cast<int*>(cnt.ptr));
+        const int cross_only = (cross && r > 0) ? 1 : 0;
+        if (replay && cross_only) {
+          k_bj_eig<true><<<npairs, EIGT, eig_smem, ctx->stream>>>(Hpart.d(), static_cast<int>(nsplit), tol, floor2, inner, 1, Rall.d(), static_cast<int*>(cnt.ptr),
+                                                                 static_cast<double2*>(Rots.ptr), static_cast<int*>(Mode.ptr), iso);
+          k_bj_replay<<<dim3(npairs, PW / 8), 256, 0, ctx->stream>>>(static_cast<const double2*>(Rots.ptr), static_cast<const int*>(Mode.ptr), Rall.d());
+        } else {
+          k_bj_eig<false><<<npairs, EIGT, eig_smem, ctx->stream>>>(Hpart.d(), static_cast<int>(nsplit), tol, floor2, inner, cross_only, Rall.d(),
+                                                                  static_cast<int*>(cnt.ptr), nullptr, nullptr, iso);
+        }
         k_bj_apply<<<dim3(npairs, static_cast<unsigned>(ceil_div(ld, 128))), 256, apply_smem, ctx->stream>>>(Wbuf.d(), ld, r, NB,
                                                                                                              Rall.d());
       }
@@ -617,7 +794,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     for (; sweeps < max_sweeps; ++sweeps) {
       if (gexec) FB_CUDA(ctx, cudaGraphLaunch(gexec, ctx->stream));
       else FB_CUDA(ctx, enqueue_sweep());
-      ctx->launches += 3 * (NB - 1);
+      ctx->launches += (replay ? 4 : 3) * (NB - 1) - (replay ? 1 : 0);
       int nrot = 0;
       FB_CUDA(ctx, cudaMemcpyAsync(&nrot, cnt.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
