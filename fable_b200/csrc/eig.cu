@@ -12,7 +12,11 @@
 #include <cmath>
 #include <numeric>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -192,12 +196,13 @@ constexpr int EIGT = 1024;
 #ifdef BJ_LAB
 __device__ int bj_lab_count = 0;
 #endif
+// The inner solve proper; called by all EIGT threads of a CTA with H (64 x 64, row stride 65) at dsm and, unless REPLAY &&
+// cross_only, R = I behind it.  Returns (uniformly) the mode: 0 = nothing to rotate (R = I), 1 = cross rotations recorded in
+// rots_pair (global or shared), 2 = R complete in shared memory behind H.
 template <bool REPLAY>
-__global__ void __launch_bounds__(EIGT)
-k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2, int inner, int cross_only, double* __restrict__ Rout,
-         int* __restrict__ nrot, double2* __restrict__ rots, int* __restrict__ mode, int iso) {
+__device__ __forceinline__ int bj_solve(double* dsm, double tol, double floor2, int inner, int cross_only, int* __restrict__ nrot,
+                                        double2* rots_pair, int iso) {
   constexpr int S = PW + 1;
-  extern __shared__ double dsm[];
   double* H = dsm;
   double* R = dsm + PW * S;
   __shared__ double cs[BW], sn[BW];
@@ -207,33 +212,6 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
   const int tid = threadIdx.x;
   const int nsteps = cross_only ? BW : PW - 1;
   const double tol2 = tol * tol;
-  const double* src = Hpart + static_cast<int64_t>(blockIdx.x) * nsplit * (PW * PW);
-  {
-    // partial Grams of the row splits, added in split order; the loads of a thread's four entries go out together,
-    // eight splits at a time (one load per iteration = nsplit x 4 serial L2 round trips, 20 us of a 50 us kernel)
-    constexpr int NE = PW * PW / EIGT;
-    double v[NE];
-#pragma unroll
-    for (int e = 0; e < NE; ++e) v[e] = 0.0;
-    for (int s0 = 0; s0 < nsplit; s0 += 8) {
-      double x[8][NE];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int e = 0; e < NE; ++e)
-          x[u][e] = (s0 + u < nsplit) ? __ldg(src + static_cast<int64_t>(s0 + u) * (PW * PW) + tid + e * EIGT) : 0.0;
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int e = 0; e < NE; ++e) v[e] += x[u][e];
-    }
-#pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      const int idx = tid + e * EIGT, a = idx & (PW - 1), b = idx >> 6;
-      H[a * S + b] = v[e];
-      if (!(REPLAY && cross_only)) R[a * S + b] = (a == b) ? 1.0 : 0.0;
-    }
-  }
   if (tid == 0) { any_rot = 0; need = 0; }
   __syncthreads();
   // does this pair need work at all?  (outer convergence test: |h_ab| > tol sqrt(h_aa h_bb))
@@ -245,8 +223,6 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
     }
   }
   __syncthreads();
-  if (tid == 0 && mode) mode[blockIdx.x] = (REPLAY && cross_only) ? (need ? 1 : 0) : 2;
-  double2* rots_pair = REPLAY ? rots + static_cast<int64_t>(blockIdx.x) * (BW * BW) : nullptr;
   if constexpr (REPLAY) {
     if (cross_only && !(iso & 2)) {
       // Symmetric form of the pipelined cross steps below (which it replaces when the rotations are recorded).  Measured
@@ -258,11 +234,11 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
       // instead of 1024 on 31, 24 instead of 21 wavefronts per warp; (ii) those 17 warps are the ones that do NOT share a
       // scheduler with warp 0 (warp ids 1-3, 5-7, .. 21-22), the other warps leave; (iii) the step barrier is a named
       // barrier of the 18 warps.  A diagonal block needs no special case: its (q, p) address is its (p, q) address.
-      if (!need) return;
+      if (!need) return 0;
       if (tid == 0) atomicAdd(nrot, 1);
       const int lane = tid & 31, w = tid >> 5;
       const bool applies = (w & 3) != 0 && w <= 22;
-      if (w != 0 && !applies) return;
+      if (w == 0 || applies) {
       const int v = w - 1 - (w >> 2);                    // 0 .. 16 over the applying warps
       int a, b;
       if (v < 16) {
@@ -340,7 +316,9 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
       if (blockIdx.x == 0 && lane == 0 && (w == 0 || w == 1 || w == 5 || w == 22) && atomicAdd(&bj_lab_count, 1) / 4 == 300)
         printf("BJ_LAB(sym) warp %2d: busy %lld cycles of %lld for 32 steps\n", w, lab_busy, clock64() - lab_t0);
 #endif
-      return;
+      }
+      __syncthreads();
+      return 1;
     }
   }
   if (need && cross_only) {
@@ -517,7 +495,49 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
       if (!any_rot) break;
     }
   }
-  if (REPLAY && cross_only) return;                        // k_bj_replay writes R
+  return (REPLAY && cross_only) ? (need ? 1 : 0) : 2;
+}
+
+template <bool REPLAY>
+__global__ void __launch_bounds__(EIGT)
+k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2, int inner, int cross_only, double* __restrict__ Rout,
+         int* __restrict__ nrot, double2* __restrict__ rots, int* __restrict__ mode, int iso) {
+  constexpr int S = PW + 1;
+  extern __shared__ double dsm[];
+  double* H = dsm;
+  double* R = dsm + PW * S;
+  const int tid = threadIdx.x;
+  const double* src = Hpart + static_cast<int64_t>(blockIdx.x) * nsplit * (PW * PW);
+  {
+    // partial Grams of the row splits, added in split order; the loads of a thread's four entries go out together,
+    // eight splits at a time (one load per iteration = nsplit x 4 serial L2 round trips, 20 us of a 50 us kernel)
+    constexpr int NE = PW * PW / EIGT;
+    double v[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) v[e] = 0.0;
+    for (int s0 = 0; s0 < nsplit; s0 += 8) {
+      double x[8][NE];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+          x[u][e] = (s0 + u < nsplit) ? __ldg(src + static_cast<int64_t>(s0 + u) * (PW * PW) + tid + e * EIGT) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) v[e] += x[u][e];
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int idx = tid + e * EIGT, a = idx & (PW - 1), b = idx >> 6;
+      H[a * S + b] = v[e];
+      if (!(REPLAY && cross_only)) R[a * S + b] = (a == b) ? 1.0 : 0.0;
+    }
+  }
+  const int md = bj_solve<REPLAY>(dsm, tol, floor2, inner, cross_only, nrot,
+                                  REPLAY ? rots + static_cast<int64_t>(blockIdx.x) * (BW * BW) : nullptr, iso);
+  if (tid == 0 && mode) mode[blockIdx.x] = md;
+  if (md != 2) return;                                     // k_bj_replay writes R
   double* Rg = Rout + static_cast<int64_t>(blockIdx.x) * (PW * PW);
   for (int idx = tid; idx < PW * PW; idx += EIGT) {
     const int a = idx & (PW - 1), b = idx >> 6;
@@ -608,6 +628,188 @@ k_bj_apply(double* __restrict__ A, int64_t ld, int round, int NB, const double* 
         const int64_t row = i0 + wr + i * 8 + g;
         if (row < ld) A[bj_col(wc + j * 8 + 2 * t + e, bi, bj) * ld + row] = c[i][j][e];
       }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_bj_round: one round of the block Jacobi as ONE kernel (m <= 8 * 240 rows) -- a thread-block cluster of CL = 8 CTAs per
+// block pair.  CTA r keeps rows [r rps, (r + 1) rps) of the pair's 64-column panel in shared memory for the whole round:
+//   1. panel slab -> shared memory (cp.async), partial Gram of the slab (DMMA) -> global scratch
+//   2. cluster barrier; every CTA adds one eighth of the 64 x 64 entries over the eight partial Grams, in CTA order
+//   3. cluster barrier; CTA 0 runs the inner solve (bj_solve: rotations recorded, or R for the full ordering of round 0)
+//   4. cluster barrier; every CTA rebuilds R from the 16 KB of recorded rotations (one warp per two rows of R) or fetches
+//      it, and updates its slab in place: W <- W R (DMMA) -- the panel is read once and written once per round.
+// The cluster is used for what it guarantees -- the eight CTAs are co-resident and meet at a hardware barrier with
+// release / acquire semantics; the exchanged data (32 KB partial Grams, rotations) goes through L2, not through
+// distributed shared memory (17-21 B per cycle and CTA, measured in B300_MICROARCH.md: slower than L2 for a one-to-seven
+// broadcast).  Replaces four dependent launches per round (k_bj_gram, k_bj_eig, k_bj_replay, k_bj_apply).
+constexpr int CL = 8;
+__global__ void __launch_bounds__(EIGT, 1)
+k_bj_round(double* __restrict__ A, int64_t ld, int rps, int round, int NB, double tol, double floor2, int inner, int cross_only,
+           double* __restrict__ Hwork, double2* __restrict__ rots, double* __restrict__ Rall, int* __restrict__ mode,
+           int* __restrict__ nrot, int iso) {
+  constexpr int S = PW + 1;
+  extern __shared__ __align__(16) double dsm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int pair = blockIdx.x / CL, r = static_cast<int>(cluster.block_rank());
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  int bi, bj;
+  bj_pair(pair, round, NB, bi, bj);
+#ifdef BJ_LAB
+  const long long lab_t0 = clock64();
+#endif
+  double* T = dsm + 3 * PW * S;                              // slab: 64 columns x rps rows, column stride TS = 4 mod 16
+  const int TS = rps + 4;
+  const int64_t row0 = static_cast<int64_t>(r) * rps;
+  {
+    const int cpc = rps >> 1;                                // 16-byte chunks per column
+    for (int idx = tid; idx < PW * cpc; idx += EIGT) {
+      const int a = idx / cpc, ch = idx - a * cpc;
+      double* dst = T + a * TS + 2 * ch;
+      if (row0 + 2 * ch < ld) cp16(dst, A + bj_col(a, bi, bj) * ld + row0 + 2 * ch);
+      else { dst[0] = 0.0; dst[1] = 0.0; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+#ifdef BJ_LAB
+  const long long lab_t1 = clock64();
+#endif
+  double* Hp = Hwork + static_cast<int64_t>(pair) * (CL + 1) * (PW * PW);
+  {
+    // partial Gram, upper 8 x 8 tiles only (36 of 64; the reduction below mirrors them): tile q -> warp q % 32, so every
+    // scheduler gets nine tiles; four K interleaves per tile keep the FP64 tensor pipe fed from one warp
+    double* P = Hp + static_cast<int64_t>(r) * (PW * PW);
+    for (int q = w; q < 36; q += EIGT / 32) {
+      int ti = 0, rem = q;
+      while (rem >= 8 - ti) { rem -= 8 - ti; ++ti; }
+      const int a0 = ti * 8, b0 = (ti + rem) * 8;
+      double c[4][2] = {};
+      const double* Ta = T + (a0 + g) * TS + t;
+      const double* Tb = T + (b0 + g) * TS + t;
+      for (int k0 = 0; k0 < rps; k0 += 16) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma4(c[u], Ta[k0 + 4 * u], Tb[k0 + 4 * u]);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) P[(a0 + g) + PW * (b0 + 2 * t + e)] = (c[0][e] + c[1][e]) + (c[2][e] + c[3][e]);
+    }
+  }
+#ifdef BJ_LAB
+  const long long lab_t2 = clock64();
+#endif
+  cluster.sync();
+#ifdef BJ_LAB
+  const long long lab_t3 = clock64();
+#endif
+  if (tid < PW * PW / CL) {
+    const int idx = r * (PW * PW / CL) + tid;
+    const int ea = idx & (PW - 1), eb = idx >> 6;            // entry (ea, eb); tiles below the diagonal were not formed
+    const int src = (ea >> 3) > (eb >> 3) ? eb + PW * ea : idx;
+    double x[CL];
+#pragma unroll
+    for (int u = 0; u < CL; ++u) x[u] = __ldcg(Hp + u * (PW * PW) + src);
+    double sum = x[0];
+#pragma unroll
+    for (int u = 1; u < CL; ++u) sum += x[u];
+    Hp[CL * (PW * PW) + idx] = sum;
+  }
+  cluster.sync();
+#ifdef BJ_LAB
+  const long long lab_t4 = clock64();
+#endif
+  if (r == 0) {
+    double* H = dsm;
+    double* R = dsm + PW * S;
+    const double* Hred = Hp + CL * (PW * PW);
+    double v[PW * PW / EIGT];
+#pragma unroll
+    for (int e = 0; e < PW * PW / EIGT; ++e) v[e] = __ldcg(Hred + tid + e * EIGT);
+#pragma unroll
+    for (int e = 0; e < PW * PW / EIGT; ++e) {
+      const int idx = tid + e * EIGT, a = idx & (PW - 1), b = idx >> 6;
+      H[a * S + b] = v[e];
+      if (!cross_only) R[a * S + b] = (a == b) ? 1.0 : 0.0;
+    }
+    const int md = bj_solve<true>(dsm, tol, floor2, inner, cross_only, nrot, rots + static_cast<int64_t>(pair) * (BW * BW), iso);
+    if (md == 2) {
+      double* Rg = Rall + static_cast<int64_t>(pair) * (PW * PW);
+      for (int idx = tid; idx < PW * PW; idx += EIGT) {
+        const int a = idx & (PW - 1), b = idx >> 6;
+        Rg[a + PW * b] = R[a * S + b];
+      }
+    }
+    if (tid == 0) mode[pair] = md;
+  }
+#ifdef BJ_LAB
+  const long long lab_t5 = clock64();
+#endif
+  cluster.sync();
+#ifdef BJ_LAB
+  const long long lab_t6 = clock64();
+#endif
+  const int md = __ldcg(mode + pair);
+  if (md == 0) return;                                       // R = I: the panel stays as it is
+  double* Rt = dsm;                                          // Rt[c * RSTR + a] = R[a][c] (the solve buffers are dead now)
+  if (md == 2) {
+    const double* Rg = Rall + static_cast<int64_t>(pair) * (PW * PW);
+    for (int idx = tid; idx < PW * PW; idx += EIGT) Rt[(idx >> 6) * RSTR + (idx & (PW - 1))] = __ldcg(Rg + idx);
+  } else {
+    // every CTA of the cluster replays eight rows of R (one warp each; lane i holds columns i (p) and 32 + (i + step) % 32
+    // (q), as k_bj_replay), the cluster meets once more and everybody fetches the 64 x 64 result
+    double2* rs = reinterpret_cast<double2*>(dsm + 2 * PW * S);
+    rs[tid] = __ldcg(rots + static_cast<int64_t>(pair) * (BW * BW) + tid);       // BW * BW == EIGT
+    __syncthreads();
+    double* Rg = Rall + static_cast<int64_t>(pair) * (PW * PW);
+    if (w < PW / CL) {
+      const int row = r * (PW / CL) + w;
+      double p_ = row == lane ? 1.0 : 0.0, q_ = row == BW + lane ? 1.0 : 0.0;
+      double2 cs_ = rs[lane];
+#pragma unroll 8
+      for (int s = 0; s < BW; ++s) {
+        const double2 nx = rs[((s + 1) & (BW - 1)) * BW + lane];
+        const double np = cs_.x * p_ - cs_.y * q_, nq = cs_.y * p_ + cs_.x * q_;
+        p_ = np;
+        q_ = __shfl_sync(0xffffffffu, nq, (lane + 1) & 31);
+        cs_ = nx;
+      }
+      Rg[row + PW * lane] = p_;
+      Rg[row + PW * (BW + lane)] = q_;
+    }
+    cluster.sync();
+    for (int idx = tid; idx < PW * PW; idx += EIGT) Rt[(idx >> 6) * RSTR + (idx & (PW - 1))] = __ldcg(Rg + idx);
+  }
+  __syncthreads();
+#ifdef BJ_LAB
+  const long long lab_t7 = clock64();
+#endif
+  {
+    const int wc = (w & 1) * 32;
+    for (int rt = w >> 1; rt < (rps >> 3); rt += EIGT / 64) {
+      double c[4][2] = {};
+      const double* Ta = T + t * TS + rt * 8 + g;
+      const double* Rb = Rt + (wc + g) * RSTR + t;
+#pragma unroll 4
+      for (int ks = 0; ks < PW / 4; ++ks) {
+        const double af = Ta[ks * 4 * TS];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma4(c[j], af, Rb[j * 8 * RSTR + ks * 4]);
+      }
+      const int64_t row = row0 + rt * 8 + g;
+      if (row < ld) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) A[bj_col(wc + j * 8 + 2 * t + e, bi, bj) * ld + row] = c[j][e];
+      }
+    }
+  }
+#ifdef BJ_LAB
+  if (pair == 0 && tid == 0 && (r == 0 || r == 3) && atomicAdd(&bj_lab_count, 1) / 6 == 200)
+    printf("BJ_LAB(round) cta %d: load %lld gram %lld sync1 %lld reduce+sync2 %lld solve %lld sync3 %lld buildR %lld apply %lld total %lld\n", r,
+           lab_t1 - lab_t0, lab_t2 - lab_t1, lab_t3 - lab_t2, lab_t4 - lab_t3, lab_t5 - lab_t4, lab_t6 - lab_t5, lab_t7 - lab_t6,
+           clock64() - lab_t7, clock64() - lab_t0);
+#endif
 }
 
 __global__ void __launch_bounds__(256) k_bj_copy_in(const double* __restrict__ G, int64_t m, double* __restrict__ W, int64_t ld, int64_t ncols) {
@@ -754,9 +956,42 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     // One sweep = NB - 1 rounds x (panel Gram, inner solve, panel update): up to ~470 small launches at m = 5000, identical
     // from sweep to sweep.  The sweep is captured once into a CUDA graph and replayed, which removes the per-launch host
     // cost and the gaps between the dependent kernels (FABLE_B200_BJ_GRAPH=0: plain launches).
+    // Fused round (k_bj_round, a cluster of CL CTAs per pair) when the slabs fit: rps rows per CTA, CL * rps >= ld
+    const int rps = static_cast<int>(round_up(ceil_div(ld, CL), 16));
+    const size_t round_smem = (static_cast<size_t>(3) * PW * (PW + 1) + static_cast<size_t>(PW) * (rps + 4)) * sizeof(double);
+    const int want_fused = getenv("FABLE_B200_BJ_FUSED") ? atoi(getenv("FABLE_B200_BJ_FUSED")) : 1;      // 2: also with a second wave
+    bool fused = replay && rps <= 240 && want_fused != 0;
+    DevBuf Hwork;
+    cudaLaunchConfig_t rcfg = {};
+    cudaLaunchAttribute rattr[1];
+    if (fused) {
+      rcfg.gridDim = dim3(static_cast<unsigned>(npairs) * CL);
+      rcfg.blockDim = dim3(EIGT);
+      rcfg.dynamicSmemBytes = round_smem;
+      rcfg.stream = ctx->stream;
+      rattr[0].id = cudaLaunchAttributeClusterDimension;
+      rattr[0].val.clusterDim.x = CL; rattr[0].val.clusterDim.y = 1; rattr[0].val.clusterDim.z = 1;
+      rcfg.attrs = rattr; rcfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaFuncSetAttribute(k_bj_round, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(round_smem)) != cudaSuccess ||
+          cudaOccupancyMaxActiveClusters(&nclusters, k_bj_round, &rcfg) != cudaSuccess || (nclusters < npairs && want_fused != 2) || nclusters < 1) {
+        // (a second wave of clusters doubles the round: B200 holds 15 clusters of 8 such CTAs, m = 1000 has 16 pairs)
+        (void)cudaGetLastError();
+        fused = false;
+      }
+    }
+    if (fused) FB_CUDA(ctx, Hwork.alloc(static_cast<size_t>(npairs) * (CL + 1) * PW * PW * sizeof(double)));
     auto enqueue_sweep = [&]() -> cudaError_t {
       cudaError_t e = cudaMemsetAsync(cnt.ptr, 0, sizeof(int), ctx->stream);
       if (e != cudaSuccess) return e;
+      if (fused) {
+        for (int r = 0; r < NB - 1; ++r) {
+          e = cudaLaunchKernelEx(&rcfg, k_bj_round, Wbuf.d(), ld, rps, r, NB, tol, floor2, inner, (cross && r > 0) ? 1 : 0, Hwork.d(),
+                                 static_cast<double2*>(Rots.ptr), Rall.d(), static_cast<int*>(Mode.ptr), static_cast<int*>(cnt.ptr), iso);
+          if (e != cudaSuccess) return e;
+        }
+        return cudaGetLastError();
+      }
       for (int r = 0; r < NB - 1; ++r) {
         k_bj_gram<<<dim3(npairs, static_cast<unsigned>(nsplit)), 128, 0, ctx->stream>>>(Wbuf.d(), ld, rows_per_split, ld, r, NB,
                                                                                          Hpart.d());
@@ -794,7 +1029,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     for (; sweeps < max_sweeps; ++sweeps) {
       if (gexec) FB_CUDA(ctx, cudaGraphLaunch(gexec, ctx->stream));
       else FB_CUDA(ctx, enqueue_sweep());
-      ctx->launches += (replay ? 4 : 3) * (NB - 1) - (replay ? 1 : 0);
+      ctx->launches += fused ? (NB - 1) : (replay ? 4 : 3) * (NB - 1) - (replay ? 1 : 0);
       int nrot = 0;
       FB_CUDA(ctx, cudaMemcpyAsync(&nrot, cnt.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
