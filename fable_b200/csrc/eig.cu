@@ -120,7 +120,9 @@ __device__ __forceinline__ void cp16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
 }
 
-// H_part[(pair * nsplit + split)][64 x 64 column-major] = sum over the split's rows of W[i,a] W[i,b]
+// H_part[(pair * nsplit + split)][64 x 64 column-major] = sum over the split's rows of W[i,a] W[i,b] -- the 8 x 8 tiles on
+// and above the diagonal are formed (36 of 64: the FP64 tensor pipe bounds this kernel, 112 us of a 276 us round at m = 5000)
+// and stored twice (mirrored reads in k_bj_eig were uncoalesced: n = 1000 16 -> 21 ms).  Warp q owns tile rows q and 7 - q (8 - q and q + 1 tiles: nine per warp).
 __global__ void __launch_bounds__(128)
 k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int64_t mrows, int round, int NB,
           double* __restrict__ Hpart) {
@@ -128,14 +130,11 @@ k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int6
   int bi, bj;
   bj_pair(blockIdx.x, round, NB, bi, bj);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int wa = (warp & 1) * 32, wb = (warp >> 1) * 32;
   const int64_t r0 = blockIdx.y * rows_per_split;
   const int64_t r1 = r0 + rows_per_split < mrows ? r0 + rows_per_split : mrows;
-  double c[4][4][2];
+  double c[9][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+  for (int i = 0; i < 9; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
   // stage = 16 rows x 64 columns = 512 chunks of 16 bytes (2 rows); 4 per thread
   auto load = [&](int64_t i0, int buf) {
 #pragma unroll
@@ -147,6 +146,7 @@ k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int6
   };
   load(r0, 0);
   int buf = 0;
+  const int rowA = warp, rowB = 7 - warp;                   // tile rows; columns rowA .. 7 and rowB .. 7
   for (int64_t i0 = r0; i0 < r1; i0 += GKT, buf ^= 1) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -154,24 +154,27 @@ k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int6
     const double* Ts = T[buf];
 #pragma unroll
     for (int ks = 0; ks < GKT / 4; ++ks) {
-      double af[4], bf[4];
+      const double afA = Ts[(rowA * 8 + g) * GS + ks * 4 + t], afB = Ts[(rowB * 8 + g) * GS + ks * 4 + t];
+      // slot i of the warp: i < 8 - warp -> tile (rowA, rowA + i), else tile (rowB, rowB + i - (8 - warp))
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = Ts[(wa + i * 8 + g) * GS + ks * 4 + t];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = Ts[(wb + j * 8 + g) * GS + ks * 4 + t];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma4(c[i][j], af[i], bf[j]);
+      for (int i = 0; i < 9; ++i) {
+        const bool first = i < 8 - warp;                    // warp-uniform
+        const int tj = first ? rowA + i : rowB + i - (8 - warp);
+        dmma4(c[i], first ? afA : afB, Ts[(tj * 8 + g) * GS + ks * 4 + t]);
+      }
     }
   }
   double* H = Hpart + (static_cast<int64_t>(blockIdx.x) * gridDim.y + blockIdx.y) * (PW * PW);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 9; ++i) {
+    const bool first = i < 8 - warp;
+    const int ti = first ? rowA : rowB, tj = first ? rowA + i : rowB + i - (8 - warp);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) H[(wa + i * 8 + g) + PW * (wb + j * 8 + 2 * t + e)] = c[i][j][e];
+    for (int e = 0; e < 2; ++e) {
+      H[(ti * 8 + g) + PW * (tj * 8 + 2 * t + e)] = c[i][e];
+      if (ti != tj) H[(tj * 8 + 2 * t + e) + PW * (ti * 8 + g)] = c[i][e];      // mirror image: the reader stays coalesced
+    }
+  }
 }
 
 // two-sided cyclic Jacobi on H (64 x 64, shared memory), rotations accumulated in R; one CTA per pair.
