@@ -843,6 +843,30 @@ def test_jacobi_eigensolver(ctx, m):
     assert relerr_mat(Q.T @ Q, np.eye(m)) < 1e-11
 
 
+@pytest.mark.parametrize("m", [96, 301, 1100])
+@pytest.mark.parametrize("env", [{"FABLE_B200_BJ_FUSED": "0"}, {"FABLE_B200_BJ_FUSED": "2"}, {"FABLE_B200_BJ_REPLAY": "0"},
+                                 {"FABLE_B200_BJ_FUSED": "0", "FABLE_B200_BJ_ISO": "2"}, {"FABLE_B200_BJ_GRAPH": "0"}])
+def test_jacobi_eigensolver_every_round_form(ctx, m, env, monkeypatch):
+    """The round of the block Jacobi exists in several forms (one cluster kernel per round where all pairs' clusters are
+    resident -- also forced into a second wave here --, four kernels with recorded rotations, the legacy in-kernel R, the
+    full-matrix inner steps, plain launches instead of the graph): all of them give the decomposition."""
+    import torch
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    rng = np.random.default_rng(m)
+    X = rng.standard_normal((m, m // 2 + 3))              # rank-deficient: the deflation runs behind every form
+    G = X @ X.T
+    dG = torch.from_numpy(G.copy()).cuda()
+    dW = torch.empty(m, dtype=torch.float64, device="cuda"); dQ = torch.empty((m, m), dtype=torch.float64, device="cuda")
+    sweeps = fb.api.dev_syevj(ctx, dG.data_ptr(), m, dW.data_ptr(), dQ.data_ptr())
+    w = dW.cpu().numpy(); Q = dQ.cpu().numpy().T
+    lam = np.linalg.eigvalsh(G)[::-1]
+    assert sweeps <= 30
+    assert np.max(np.abs(w - lam)) < 1e-11 * lam[0]
+    assert relerr_mat(Q @ np.diag(w) @ Q.T, G) < 1e-11
+    assert relerr_mat(Q.T @ Q, np.eye(m)) < 1e-11
+
+
 @pytest.mark.parametrize("m,spectrum", [(96, "repeated"), (300, "repeated"), (300, "clustered"), (257, "singular"), (64, "singular"),
                                         (12, "singular"), (500, "rank1")])
 def test_jacobi_eigensolver_hard_spectra(ctx, m, spectrum):
