@@ -155,6 +155,9 @@ k_rowstats(const double* __restrict__ Y, int64_t n, int64_t p, int64_t ldy, cons
 // The per-column partial sums of a group's warps meet once per tile in a double-buffered shared array behind a
 // NAMED barrier of that group only -- groups drift freely against each other -- and are added in warp order:
 // bit-stable.
+#ifdef ROWS_LAB_TIMING
+__device__ int rows_lab_count = 0;
+#endif
 constexpr int MW = 16;                 // warps per CTA
 constexpr int ITEM = 32;               // rows per item (4 DMMA column blocks of the transposed product)
 constexpr int MAXS = 8;                // ring stages per warp, at most
@@ -266,14 +269,28 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
 
   int buf = 0, stage = 0;
   const int bar_id = 1 + ts, bar_threads = G * 32;
+#ifdef ROWS_LAB_TIMING
+  long long lab_wait = 0, lab_math = 0, lab_bar = 0, lab_issue = 0;
+  const long long lab_t0 = clock64();
+#endif
   for (int st = blockIdx.x; st < nsuper; st += sstep) {
     double ar0 = 0.0, ar1 = 0.0, as0 = 0.0, as1 = 0.0;
     double a[KS];
 #pragma unroll
     for (int q = 0; q < IPW; ++q) {
       if (q == 0 || wr + q * G < nitems) {               // warp-uniform
+#ifdef ROWS_LAB_TIMING
+        const long long lab_a = clock64();
+#endif
         issue();                                         // item + S - 1 into the stage consumed by the previous step
+#ifdef ROWS_LAB_TIMING
+        const long long lab_b = clock64();
+#endif
         asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+#ifdef ROWS_LAB_TIMING
+        const long long lab_c = clock64();
+        lab_issue += lab_b - lab_a; lab_wait += lab_c - lab_b;
+#endif
         double2 acc[4];
         const uint32_t sb = stage * STB;
 #pragma unroll
@@ -296,6 +313,9 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
 #endif
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) { ar0 = fma(acc[nb].x, acc[nb].x, ar0); ar1 = fma(acc[nb].y, acc[nb].y, ar1); }
+#ifdef ROWS_LAB_TIMING
+        lab_math += clock64() - lab_c;
+#endif
       }
     }
     // the warp's part of this tile is complete
@@ -313,7 +333,13 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
         red[(buf * MW + w) * 16 + g] = r;
         red[(buf * MW + w) * 16 + 8 + g] = s;
       }
+#ifdef ROWS_LAB_TIMING
+      const long long lab_d = clock64();
+#endif
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+#ifdef ROWS_LAB_TIMING
+      lab_bar += clock64() - lab_d;
+#endif
       if (wr == 0 && lane < 16) {
         double sum = 0.0;
         for (int w2 = 0; w2 < G; ++w2) sum += red[(buf * MW + w + w2) * 16 + lane];
@@ -326,6 +352,240 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef ROWS_LAB_TIMING
+  if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (w == 0 || w == 5 || w == 15) && atomicAdd(&rows_lab_count, 1) / 6 == 50)
+    printf("ROWS_LAB cta %3d warp %2d: issue %lld wait %lld math %lld barrier %lld total %lld cycles\n", blockIdx.x, w, lab_issue, lab_wait, lab_math,
+           lab_bar, clock64() - lab_t0);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_rowstats_tma<KS, IPW>: the same fit, the stream of Y moved by the TMA engine instead of by the computing warps.
+// Cycle counters in k_rowstats_mma (-DROWS_LAB_TIMING, C3) show what bounds it: a warp never waits for its data (190 of
+// 64 000 cycles in cp.async.wait_group) -- it spends 10-19 k cycles ISSUING its own copies (four LDGSTS per item behind the
+// memory pipe's back-pressure) and 22-34 k in the math section, one after the other, so neither the memory pipe nor the
+// FP64 pipe (44 % busy) is kept full by four warps per scheduler.  Here the TMA engine owns the stream: a stage is a whole
+// tile group -- 8 (16 / G) columns x n rows, CONTIGUOUS in column-major Y (needs ldy == n) -- and arrives by ONE
+// cp.async.bulk (global -> shared, completion counted in bytes on an mbarrier) issued by one lane of warp 0 two stages ahead
+// (a first version with one copy per column and 512-row chunk spent 850 cycles per stage issuing them: a bulk copy costs
+// its issuing thread ~100 cycles); the 16 warps wait on the stage's "full" barrier, read their fragments with one LDS.128
+// each, release the stage on its "empty" barrier after their last read and otherwise do nothing but math.  Rows past n of
+// a warp's last item belong to the next column and are masked by the reader; columns past p are not copied and their sums
+// are not stored.  c fragments: plain loads, one tile ahead.
+__device__ __forceinline__ uint32_t rows_smem_u32(const void* p_) { return static_cast<uint32_t>(__cvta_generic_to_shared(p_)); }
+__device__ __forceinline__ void rows_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rows_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rows_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rows_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rows_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rows_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void rows_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred P1;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(rows_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void rows_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rows_smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(rows_smem_u32(bar))
+               : "memory");
+}
+constexpr int TMA_HDR = 2 * MW * 16 * 8 + 128;      // red[2][MW][16] + full[8] + empty[8]
+constexpr int TMA_SLACK = 256;                      // masked reads past the last column of the last slot stay inside the allocation
+
+template <int KS, int IPW>
+__global__ void __launch_bounds__(MW * 32, 1)
+k_rowstats_tma(const double* __restrict__ Y, int n, int p, const double* __restrict__ U, int64_t ldu, const double* __restrict__ c,
+               int64_t ldc, int k, int nitems, int G, int nsuper, int S, int stage_bytes, double* __restrict__ s_out,
+               double* __restrict__ resid_out) {
+  extern __shared__ __align__(128) unsigned char rows_smem[];
+  double* red = reinterpret_cast<double*>(rows_smem);                             // [2][MW][16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(rows_smem + 2 * MW * 16 * 8);
+  uint64_t* empty = full + MAXS;
+  unsigned char* stages = rows_smem + TMA_HDR;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int TC = MW / G, stage_cols = 8 * TC;
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { rows_mbar_init(full + i, 1); rows_mbar_init(empty + i, MW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // ---- the stream: stage j (tile group blockIdx.x + j gridDim.x) lives in slot j % S and may be refilled once all 16
+  // warps have released stage j - S; issued S - 1 stages ahead of the fit ----
+  int pj = 0;
+  auto produce = [&]() {
+    const int64_t pst = blockIdx.x + static_cast<int64_t>(pj) * gridDim.x;
+    if (pst >= nsuper) return;
+    const int slot = pj % S;
+    const int64_t col0 = pst * stage_cols;
+    const int ncol = p - col0 < stage_cols ? static_cast<int>(p - col0) : stage_cols;
+    if (lane == 0) {
+      if (pj >= S) rows_mbar_wait(empty + slot, ((pj / S) - 1) & 1);
+      const uint32_t bytes = static_cast<uint32_t>(ncol) * n * 8;
+      rows_mbar_expect_tx(full + slot, bytes);
+      rows_bulk_load(stages + static_cast<size_t>(slot) * stage_bytes, Y + col0 * n, bytes, full + slot);
+    }
+    ++pj;
+  };
+  if (w == 0)
+    for (int i = 0; i < S - 1; ++i) produce();
+  // ---- the fit ---------------------------------------------------------------------------------------
+  const int g = lane >> 2, t = lane & 3;
+  const int ts = w / G, wr = w - ts * G;
+  const bool grouped = ts < TC;                              // 16 % G warps have no group: they only pass the barriers
+  double ub[IPW][KS][4];
+#pragma unroll
+  for (int q = 0; q < IPW; ++q)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        const int row = (wr + q * G) * ITEM + nb * 8 + g, l = ks * 4 + t;
+        ub[q][ks][nb] = (grouped && row < n && l < k) ? __ldg(U + row + ldu * l) : 0.0;
+      }
+#pragma unroll
+  for (int q = 0; q < IPW; ++q)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) ub[q][ks][nb] = -ub[q][ks][nb];
+  auto load_c = [&](int64_t st, double (&a)[KS]) {
+    const int64_t col = (st * TC + ts) * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int l = ks * 4 + t;
+      a[ks] = (grouped && st < nsuper && col < p && l < k) ? __ldg(c + col + ldc * l) : 0.0;
+    }
+  };
+  double a_next[KS];
+  load_c(blockIdx.x, a_next);
+  int buf = 0, use = 0;
+  const int bar_id = 1 + ts, bar_threads = G * 32;
+#ifdef ROWS_LAB_TIMING
+  long long lab_prod = 0, lab_wait = 0, lab_math = 0, lab_bar = 0;
+  const long long lab_t0 = clock64();
+#endif
+  const uint32_t lane_off = static_cast<uint32_t>(((ts * 8 + g) * n + wr * ITEM + 2 * t) * 8);
+  const uint32_t stage0 = rows_smem_u32(stages);
+  for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x, ++use) {
+    double a[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) a[ks] = a_next[ks];
+    load_c(st + gridDim.x, a_next);
+    double ar0 = 0.0, ar1 = 0.0, as0 = 0.0, as1 = 0.0;
+    const int slot = use % S;
+#ifdef ROWS_LAB_TIMING
+    const long long lab_a = clock64();
+#endif
+    if (w == 0) produce();                                   // stage use + S - 1 into the slot released during stage use - 1
+#ifdef ROWS_LAB_TIMING
+    const long long lab_b = clock64();
+#endif
+    rows_mbar_wait(full + slot, (use / S) & 1);
+#ifdef ROWS_LAB_TIMING
+    const long long lab_c = clock64();
+    lab_prod += lab_b - lab_a; lab_wait += lab_c - lab_b;
+#endif
+    const uint32_t src0 = stage0 + slot * stage_bytes + lane_off;
+#pragma unroll
+    for (int q = 0; q < IPW; ++q) {
+      const int it = wr + q * G;
+      double2 acc[4];
+      const bool mine = grouped && it < nitems;              // warp-uniform
+      if (mine) {
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(acc[nb].x), "=d"(acc[nb].y) : "r"(src0 + (q * G * ITEM + nb * 8) * 8) : "memory");
+      }
+      if (q == IPW - 1) {                                    // last read of this stage
+        __syncwarp();
+        if (lane == 0) rows_mbar_arrive(empty + slot);
+      }
+      if (mine) {
+        if (it * ITEM + ITEM > n) {                          // last item of a column: rows past n belong to the next column
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb)
+            if (it * ITEM + nb * 8 + 2 * t >= n) acc[nb] = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) { as0 = fma(acc[nb].x, acc[nb].x, as0); as1 = fma(acc[nb].y, acc[nb].y, as1); }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+          for (int nb = 0; nb < 4; ++nb) dmma_884(acc[nb], a[ks], ub[q][ks][nb]);
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) { ar0 = fma(acc[nb].x, acc[nb].x, ar0); ar1 = fma(acc[nb].y, acc[nb].y, ar1); }
+      }
+    }
+#ifdef ROWS_LAB_TIMING
+    lab_math += clock64() - lab_c;
+#endif
+    if (!grouped) continue;
+    double r = ar0 + ar1, s = as0 + as1;
+    r += __shfl_xor_sync(0xffffffffu, r, 1); s += __shfl_xor_sync(0xffffffffu, s, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2); s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const int64_t col = (st * TC + ts) * 8;
+    if (G == 1) {
+      if (t == 0 && col + g < p) {
+        resid_out[col + g] = r;
+        if (s_out) s_out[col + g] = s;
+      }
+    } else {
+      if (t == 0) {
+        red[(buf * MW + w) * 16 + g] = r;
+        red[(buf * MW + w) * 16 + 8 + g] = s;
+      }
+#ifdef ROWS_LAB_TIMING
+      const long long lab_d = clock64();
+#endif
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+#ifdef ROWS_LAB_TIMING
+      lab_bar += clock64() - lab_d;
+#endif
+      if (wr == 0 && lane < 16) {
+        double sum = 0.0;
+        for (int w2 = 0; w2 < G; ++w2) sum += red[(buf * MW + w + w2) * 16 + lane];
+        if (col + (lane & 7) < p) {
+          if (lane < 8) resid_out[col + lane] = sum;
+          else if (s_out) s_out[col + lane - 8] = sum;
+        }
+      }
+      buf ^= 1;
+    }
+  }
+#ifdef ROWS_LAB_TIMING
+  if ((blockIdx.x == 0 || blockIdx.x == 77) && lane == 0 && (w == 0 || w == 5 || w == 15) && atomicAdd(&rows_lab_count, 1) / 6 == 50)
+    printf("ROWS_LAB(tma) cta %3d warp %2d: produce %lld wait %lld math %lld barrier %lld total %lld cycles\n", blockIdx.x, w, lab_prod, lab_wait,
+           lab_math, lab_bar, clock64() - lab_t0);
+#endif
+}
+
+template <int KS, int IPW>
+int launch_rowstats_tma(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t ldy, const double* dU, int64_t ldu,
+                        const double* d_c, int64_t ldc, int k, int nitems, double* d_s, double* d_resid, bool* launched) {
+  const int G = nitems < MW ? nitems : MW;
+  const int64_t stage_bytes = round_up(static_cast<int64_t>(8) * (MW / G) * n * 8, 128);
+  int64_t S = (227 * 1024 - TMA_HDR - TMA_SLACK) / stage_bytes;
+  if (S > MAXS) S = MAXS;
+  *launched = false;
+  if (S < 3 || ldy != n) return FABLE_OK;                    // (the tile must be contiguous; longer columns: k_rowstats_mma)
+  const size_t smem = TMA_HDR + TMA_SLACK + static_cast<size_t>(S) * stage_bytes;
+  static bool attr_dev[64] = {};
+  bool& attr_set = attr_dev[ctx->device & 63];
+  if (!attr_set) {
+    FB_CUDA(ctx, cudaFuncSetAttribute(k_rowstats_tma<KS, IPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int64_t nsuper = ceil_div(ceil_div(p, 8), MW / G);
+  const unsigned grid = static_cast<unsigned>(nsuper < ctx->sms ? nsuper : ctx->sms);
+  k_rowstats_tma<KS, IPW><<<grid, MW * 32, smem, ctx->stream>>>(dY, static_cast<int>(n), static_cast<int>(p), dU, ldu, d_c, ldc, k, nitems, G,
+                                                                static_cast<int>(nsuper), static_cast<int>(S), static_cast<int>(stage_bytes), d_s, d_resid);
+  FB_LAUNCHED(ctx);
+  *launched = true;
+  return FABLE_OK;
 }
 
 template <int KS, int IPW>
@@ -374,8 +634,20 @@ int fb_rowstats(fable_ctx* ctx, const double* dY, int64_t n, int64_t p, int64_t 
     const int64_t nitems = ceil_div(n, ITEM);
     const int64_t IPW = ceil_div(nitems, MW);
     const int ni = static_cast<int>(nitems);
+    // TMA-streamed form where it measured faster: ranks up to 4 (C3 shape at k = 4: 28.9 vs 30.8 us = 0.85 of HBM); at
+    // k = 10 the two are level (39.7 vs 38.9 us), at n = 500, k = 20 and n = 200 the cp.async ring wins (74 vs 82, 29 vs 33 us).
+    // FABLE_B200_ROWS_TMA=1 / 0 forces / forbids it.
+    const char* env_tma = getenv("FABLE_B200_ROWS_TMA");
+    const bool use_tma = env_tma ? atoi(env_tma) != 0 : k <= 4;
 #define FB_ROWS_MMA(KS_, IPW_) \
-    if (KS == KS_ && IPW == IPW_) return launch_rowstats_mma<KS_, IPW_>(ctx, dY, n, p, ldy, dU, ldu, d_c, ldc, k, ni, d_s, d_resid);
+    if (KS == KS_ && IPW == IPW_) { \
+      if (use_tma) { \
+        bool launched = false; \
+        FB_TRY((launch_rowstats_tma<KS_, IPW_>(ctx, dY, n, p, ldy, dU, ldu, d_c, ldc, k, ni, d_s, d_resid, &launched))); \
+        if (launched) return FABLE_OK; \
+      } \
+      return launch_rowstats_mma<KS_, IPW_>(ctx, dY, n, p, ldy, dU, ldu, d_c, ldc, k, ni, d_s, d_resid); \
+    }
     FB_ROWS_MMA(1, 1) FB_ROWS_MMA(2, 1) FB_ROWS_MMA(3, 1) FB_ROWS_MMA(4, 1) FB_ROWS_MMA(5, 1) FB_ROWS_MMA(6, 1)
     FB_ROWS_MMA(1, 2) FB_ROWS_MMA(2, 2) FB_ROWS_MMA(3, 2)
     FB_ROWS_MMA(1, 3) FB_ROWS_MMA(2, 3)

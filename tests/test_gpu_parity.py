@@ -585,17 +585,18 @@ def test_dev_rowstats_both_kernels(ctx, n, p, k, monkeypatch):
     want_s = np.sum(Y ** 2, axis=0)
     dY = torch.from_numpy(np.ascontiguousarray(Y.T)).cuda(); dU = torch.from_numpy(np.ascontiguousarray(U.T)).cuda()
     dc = torch.from_numpy(np.ascontiguousarray(c.T)).cuda()
-    for mma in ("1", "0"):
+    for mma, tma in (("1", "0"), ("1", "1"), ("0", "0")):      # cp.async ring, TMA-streamed tiles, DFMA kernel
         monkeypatch.setenv("FABLE_B200_ROWS_MMA", mma)
+        monkeypatch.setenv("FABLE_B200_ROWS_TMA", tma)
         ds = torch.full((p,), -1.0, dtype=torch.float64, device="cuda"); dr = torch.full((p,), -1.0, dtype=torch.float64, device="cuda")
         fb.api.dev_rowstats(ctx, dY.data_ptr(), n, p, dU.data_ptr(), dc.data_ptr(), p, k, ds.data_ptr(), dr.data_ptr())
         ctx.synchronize()
-        assert relerr_vec(dr.cpu().numpy(), want_r) < 1e-12, mma
-        assert relerr_vec(ds.cpu().numpy(), want_s) < 1e-12, mma
+        assert relerr_vec(dr.cpu().numpy(), want_r) < 1e-12, (mma, tma)
+        assert relerr_vec(ds.cpu().numpy(), want_s) < 1e-12, (mma, tma)
         dr.fill_(-1.0)
         fb.api.dev_rowstats(ctx, dY.data_ptr(), n, p, dU.data_ptr(), dc.data_ptr(), p, k, 0, dr.data_ptr())   # s not wanted
         ctx.synchronize()
-        assert relerr_vec(dr.cpu().numpy(), want_r) < 1e-12, mma
+        assert relerr_vec(dr.cpu().numpy(), want_r) < 1e-12, (mma, tma)
 
 
 @pytest.mark.parametrize("p,k", [(1, 1), (16, 1), (48, 4), (63, 1), (64, 2), (65, 3), (80, 2), (96, 7), (112, 5), (130, 13),
