@@ -338,6 +338,117 @@ def test_block_jacobi_sweep_visits_every_column_pair(NB):
         assert cnt == 1, (a, b, cnt)                                                # ... exactly once: a cyclic sweep
 
 
+def _sym_blocks(BW=32):
+    """thread -> (row pair a, column pair b) of the symmetric cross steps in bj_solve (eig.cu): 17 virtual warps x 32 lanes"""
+    out = []
+    for v in range(17):
+        for lane in range(32):
+            if v < 16:
+                a, b = (v, lane) if lane >= v else (31 - v, 32 - v + lane)
+            elif lane < 16:
+                a = b = 16 + lane
+            else:
+                continue
+            out.append((a, b))
+    return out
+
+
+def _rotation(hpq, hpp, hqq):
+    if hpq == 0.0:
+        return 1.0, 0.0
+    d, h2 = hqq - hpp, 2.0 * hpq
+    t = h2 / (d + np.copysign(np.sqrt(d * d + h2 * h2), d))
+    c = 1.0 / np.sqrt(1.0 + t * t)
+    return c, c * t
+
+
+def test_inner_solve_upper_triangle_scheme_equals_the_full_update():
+    """bj_solve keeps H as its upper triangle: entry (r, c) lives at [min][max]; a block (row pair a, column pair b) with
+    a <= b is rotated from both sides by one thread (528 blocks), a diagonal block through the same four addresses, and
+    warp 0 derives the next rotations from upper entries only.  Restated here with NaN in the lower triangle: every upper
+    entry is written exactly once per step, nothing below the diagonal is read or written, and the result equals
+    J' H J of the full matrix; the recorded rotations replayed with the lane-shift scheme of k_bj_replay give R."""
+    BW, PW = 32, 64
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((PW, PW + 7))
+    Hf = A @ A.T
+    iu = np.triu_indices(PW)
+    Hc = np.full((PW, PW), np.nan); Hc[iu] = Hf[iu]
+    blocks = _sym_blocks()
+    assert len(blocks) == 528 and len(set(blocks)) == 528 and all(a <= b for a, b in blocks)
+    rot = [_rotation(Hc[i, BW + i], Hc[i, i], Hc[BW + i, BW + i]) for i in range(BW)]
+    recorded, R_full = [], np.eye(PW)
+    for step in range(BW):
+        recorded.append(list(rot))
+        o = [(x + step) % BW for x in range(BW)]
+        J = np.eye(PW)
+        for i in range(BW):
+            c, s = rot[i]; pi, qi = i, BW + o[i]
+            J[pi, pi] = c; J[qi, qi] = c; J[pi, qi] = s; J[qi, pi] = -s
+        Hf_next = J.T @ Hf @ J
+        R_full = R_full @ J
+        nxt = None
+        if step + 1 < BW:                       # the deriving warp: next pivots from upper entries and the current rotations
+            nxt = []
+            for i in range(BW):
+                i1 = (i + 1) % BW; qi = BW + o[i]; qn = BW + (o[i] + 1) % BW
+                r1, r2 = rot[i], rot[i1]
+                ap = r1[0] * Hc[i, i] - r1[1] * Hc[i, qi]; aq = r1[0] * Hc[i, qi] - r1[1] * Hc[qi, qi]
+                hii = r1[0] * ap - r1[1] * aq
+                bp1 = r2[1] * Hc[i1, i1] + r2[0] * Hc[i1, qn]; bq1 = r2[1] * Hc[i1, qn] + r2[0] * Hc[qn, qn]
+                hqq = r2[1] * bp1 + r2[0] * bq1
+                bp = r2[1] * Hc[min(i, i1), max(i, i1)] + r2[0] * Hc[i, qn]
+                bq = r2[1] * Hc[i1, qi] + r2[0] * Hc[min(qi, qn), max(qi, qn)]
+                hpq = r1[0] * bp - r1[1] * bq
+                assert np.isfinite([hii, hqq, hpq]).all()
+                np.testing.assert_allclose([hii, hqq, hpq], [Hf_next[i, i], Hf_next[qn, qn], Hf_next[i, qn]], atol=1e-11)
+                nxt.append(_rotation(hpq, hii, hqq))
+        Hn = np.full((PW, PW), np.nan)
+        for a, b in blocks:
+            r1, r2 = rot[a], rot[b]
+            lo, hi = min(o[a], o[b]), max(o[a], o[b])
+            App, Apq, Aqp, Aqq = (a, b), (a, BW + o[b]), (b, BW + o[a]), (BW + lo, BW + hi)
+            hpp, hpq, hqp, hqq = Hc[App], Hc[Apq], Hc[Aqp], Hc[Aqq]
+            assert np.isfinite([hpp, hpq, hqp, hqq]).all()                         # nothing below the diagonal is read
+            ap = r2[0] * hpp - r2[1] * hpq; bp = r2[1] * hpp + r2[0] * hpq
+            aq = r2[0] * hqp - r2[1] * hqq; bq = r2[1] * hqp + r2[0] * hqq
+            for addr, val in ((App, r1[0] * ap - r1[1] * aq), (Aqp, r1[1] * ap + r1[0] * aq), (Apq, r1[0] * bp - r1[1] * bq),
+                              (Aqq, r1[1] * bp + r1[0] * bq)):
+                assert addr[0] <= addr[1] and (np.isnan(Hn[addr]) or a == b)       # one writer per upper entry
+                Hn[addr] = val
+        assert np.isfinite(Hn[iu]).all() and np.isnan(Hn[np.tril_indices(PW, -1)]).all()
+        np.testing.assert_allclose(Hn[iu], Hf_next[iu], atol=1e-11)
+        Hc, Hf = Hn, Hf_next
+        if nxt is not None:
+            rot = nxt
+    # k_bj_replay: one warp per row of R; lane i holds column i (p) and column 32 + (i + step) % 32 (q); q moves one lane per step
+    R = np.zeros((PW, PW))
+    for row in range(PW):
+        p_ = np.array([1.0 if row == i else 0.0 for i in range(BW)]); q_ = np.array([1.0 if row == BW + i else 0.0 for i in range(BW)])
+        for step in range(BW):
+            c = np.array([r[0] for r in recorded[step]]); s = np.array([r[1] for r in recorded[step]])
+            np_, nq = c * p_ - s * q_, s * p_ + c * q_
+            p_, q_ = np_, np.roll(nq, -1)                                          # lane i takes lane i + 1's value
+        R[row, :BW], R[row, BW:] = p_, q_
+    np.testing.assert_allclose(R, R_full, atol=1e-13)
+
+
+@pytest.mark.parametrize("warp", [0, 1, 2, 3])
+def test_panel_gram_upper_tiles_nine_per_warp(warp):
+    """k_bj_gram: warp q owns tile rows q and 7 - q of the 8 x 8 grid of 8 x 8 tiles, columns from the diagonal on: nine
+    tiles each, together the 36 upper tiles exactly once."""
+    def tiles(w):
+        out = []
+        for i in range(9):
+            first = i < 8 - w
+            out.append((w, w + i) if first else (7 - w, 7 - w + i - (8 - w)))
+        return out
+    mine = tiles(warp)
+    assert len(set(mine)) == 9 and all(0 <= ti <= tj < 8 for ti, tj in mine)
+    allt = [t for w in range(4) for t in tiles(w)]
+    assert sorted(allt) == [(i, j) for i in range(8) for j in range(i, 8)]
+
+
 # ---- work split of the tensor-core row pass (fable_b200/csrc/rows.cu, k_rowstats_mma): restated index maps -------
 @pytest.mark.parametrize("n,p,grid", [(1000, 20000, 148), (500, 1000, 148), (200, 777, 148), (66, 9, 148), (2, 5, 148),
                                       (2000, 300, 148), (3000, 100, 7), (1000, 2003, 3)])
