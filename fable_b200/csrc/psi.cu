@@ -384,14 +384,25 @@ k_psi(PsiArgs a, int64_t tile_begin, const __grid_constant__ CUtensorMap tmap, c
       __syncthreads();
       if (!(PSI_LAB & 4))
 #pragma unroll
-      for (int i = 0; i < NI; ++i)
+      for (int i = 0; i < NI; ++i) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int ul = wu * WR + i * 8 + g, vl = wv * 16 + j * 8 + 2 * t;
           D[d_off<TV>(ul, vl)] = c[i][j][0];
           D[d_off<TV>(ul, vl + 1)] = c[i][j][1];
-          if (!diag) *reinterpret_cast<double2*>(M + m_off(ul, vl)) = make_double2(c[i][j][0], c[i][j][1]);
         }
+        if (!diag) {
+          // mirrored 16-byte stores: a quarter-warp is rows u = g, g + 1 with the four column pairs t; stored tile by tile
+          // both rows hit the same 64-byte half of their 128-byte swizzle row (the XOR with u & 7 = g flips only bit 0
+          // between them): 2-way conflicts on every STS.128, 498 M excess wavefronts per launch in ncu.  Odd rows therefore
+          // store their j = 1 tile while even rows store j = 0 and vice versa: the halves alternate, no conflict.
+          const int ul = wu * WR + i * 8 + g;
+          const bool odd = g & 1;
+          const double2 t0 = make_double2(c[i][0][0], c[i][0][1]), t1 = make_double2(c[i][1][0], c[i][1][1]);
+          *reinterpret_cast<double2*>(M + m_off(ul, wv * 16 + (odd ? 8 : 0) + 2 * t)) = odd ? t1 : t0;
+          *reinterpret_cast<double2*>(M + m_off(ul, wv * 16 + (odd ? 0 : 8) + 2 * t)) = odd ? t0 : t1;
+        }
+      }
       if (bulk) fence_async_smem();      // generic-proxy smem writes -> visible to the async (bulk copy) proxy
     }
     cp_async_wait_all();
