@@ -529,6 +529,14 @@ def run_draws(args, w, wname, job):
         stages.update(kMax=kMax, kEst_gpu_pipeline=k_gpu,
                       d_relerr_vs_host_lapack=float(np.max(np.abs(s["d"][:kEst] - d) / d)))
         del s
+        # the single-upload wrapper pipeline (FABLEPosteriorMean, R/FABLE_wrapper.R:80-128) with the library's own stage
+        # marks: the rank search and the row posterior on resident data, apart from the host copies around them
+        ctx.stage_timing(True)
+        for _ in range(2):
+            pm = fb.FABLEPosteriorMean(Y, ctx=ctx)
+        stages["FABLEPosteriorMean_ms"] = dict(total=round(1e3 * pm["runTime"], 3), kEst=int(pm["estRank"]), **ctx.stage_times())
+        ctx.stage_timing(False)
+        del pm
 
     if rank == 0:
         peak, peak_src = _peaks()

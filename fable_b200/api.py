@@ -179,6 +179,17 @@ class Context:
         self.check(_load().fable_ctx_kernel_time(self._h, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
 
+    def stage_timing(self, enable=True):
+        """Make the wrapper pipelines record their stage split (the stream is drained at every stage boundary)."""
+        self.check(_load().fable_ctx_stage_timing(self._h, C.c_int(1 if enable else 0)))
+
+    def stage_times(self):
+        """Stage milliseconds of the last FABLEPosteriorMean / FABLEPosteriorSampler pipeline call on this context."""
+        ms = (C.c_double * 6)()
+        self.check(_load().fable_ctx_stage_times(self._h, ms, C.c_int(6)))
+        names = ("upload_Y", "svd_on_device", "svd_to_host_and_kmax", "rank_search", "row_posterior", "pxp_results_to_host")
+        return {nm: round(float(v), 3) for nm, v in zip(names, ms)}
+
     def measure_fp64_peak(self):
         """DMMA.8x8x4 issue peak of this device in TFLOP/s (diagnostics; the Gram step's roofline denominator)."""
         v = C.c_double()

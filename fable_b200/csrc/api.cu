@@ -5,6 +5,7 @@
 // on the device.  No CPU arithmetic fallback exists for any matrix-sized quantity.
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <new>
@@ -907,6 +908,19 @@ int fable_ctx_kernel_timing(fable_ctx* ctx, int enable) {
   ctx->ev_used = 0;
   for (cudaEvent_t e : ctx->ev_extra) cudaEventDestroy(e);
   ctx->ev_extra.clear();
+  return FABLE_OK;
+}
+
+int fable_ctx_stage_timing(fable_ctx* ctx, int enable) {
+  if (!ctx) return FABLE_ERR_INVALID;
+  ctx->stage_timing = enable != 0;
+  for (double& x : ctx->stage_ms) x = 0.0;
+  return FABLE_OK;
+}
+
+int fable_ctx_stage_times(const fable_ctx* ctx, double* ms, int count) {
+  if (!ctx || !ms || count < 0) return FABLE_ERR_INVALID;
+  for (int i = 0; i < count; ++i) ms[i] = i < 8 ? ctx->stage_ms[i] : 0.0;
   return FABLE_OK;
 }
 
@@ -1871,19 +1885,41 @@ struct Pipeline {
 };
 
 // R/FABLE_wrapper.R:20-27 == :87-94: as.matrix, svd(Y), kMax rule
+// Stage marks of the wrapper pipelines (only when fable_ctx_stage_timing is on: every mark drains the stream).
+// Slots: 0 upload of Y, 1 Gram + eigensolver + back-multiplication, 2 U / d / V to the host + kMax rule, 3 rank search,
+// 4 row posterior (+ hyper-parameters, varInflation), 5 p x p results to the host.
+struct StageClock {
+  fable_ctx* ctx;
+  std::chrono::steady_clock::time_point t0;
+  explicit StageClock(fable_ctx* c) : ctx(c) {
+    if (ctx->stage_timing) { cudaStreamSynchronize(ctx->stream); t0 = std::chrono::steady_clock::now(); }
+  }
+  void mark(int slot) {
+    if (!ctx->stage_timing) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto t1 = std::chrono::steady_clock::now();
+    ctx->stage_ms[slot] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+};
+
 int pipeline_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double maxProp, Pipeline& pl, double* U,
                  double* dOut, double* V) {
   FB_REQUIRE(ctx, Y && n >= 1 && p >= 1, "Y must be a non-empty matrix");
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->stage_timing) for (double& x : ctx->stage_ms) x = 0.0;
+  StageClock clk(ctx);
   const int64_t r = n < p ? n : p;
   Inputs& in = pl.in;
   in.n = n; in.p = p; in.r = r; in.kcols = static_cast<int>(r);
   FB_TRY(upload(ctx, in.Y, Y, static_cast<size_t>(n) * p));
+  clk.mark(0);
   FB_CUDA(ctx, in.U.alloc(static_cast<size_t>(n) * r * sizeof(double)));
   FB_CUDA(ctx, in.V.alloc(static_cast<size_t>(p) * r * sizeof(double)));
   FB_CUDA(ctx, in.d.alloc(static_cast<size_t>(r) * sizeof(double)));
   FB_TRY(fb_svd(ctx, in.Y.d(), n, p, in.U.d(), in.d.d(), in.V.d()));
   in.own_svd = n <= p;        // n <= p: V = Y'U / d column by column and U is the eigensolver's orthogonal factor
+  clk.mark(1);
   pl.d.resize(r);
   FB_TRY(download(ctx, pl.d.data(), in.d.d(), r));
   FB_TRY(download(ctx, U, in.U.d(), static_cast<size_t>(n) * r));
@@ -1892,6 +1928,7 @@ int pipeline_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double m
   if (dOut) std::memcpy(dOut, pl.d.data(), r * sizeof(double));
   if (fable_kmax(pl.d.data(), r, maxProp, &pl.kMax) != FABLE_OK)
     return ctx->fail(FABLE_ERR_INVALID, "kMax rule: no index reaches maxProp");       // R: min(integer(0)) -> Inf
+  clk.mark(2);
   return FABLE_OK;
 }
 }  // namespace
@@ -1907,11 +1944,15 @@ int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int
   FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:87-94
   if (kMaxOut) *kMaxOut = pl.kMax;
   int k = 1;
+  StageClock clk(ctx);
   FB_TRY(rank_dev(ctx, pl.in, pl.kMax, &k));                                     // cpp:457
+  clk.mark(3);
   RowPosterior rp;
   FB_TRY(row_posterior(ctx, pl.in, k, gamma0, delta0sq, /*shrunk=*/1, rp));
+  clk.mark(4);
   *kEst = k;
   if (Cov) FB_TRY(rankk_cov_to_host(ctx, rp.G0.d(), p, rp.sigmahat.d(), p, k, Cov));   // cpp:491, 509-512
+  clk.mark(5);
   return FABLE_OK;
 }
 
@@ -1929,7 +1970,9 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
   FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:20-27
   if (kMaxOut) *kMaxOut = pl.kMax;
   int k = 1;
+  StageClock clk(ctx);
   FB_TRY(rank_dev(ctx, pl.in, pl.kMax, &k));                                     // wrapper:29-33
+  clk.mark(3);
   if (kEstOut) *kEstOut = k;
   double vi = 0.0;
   RowPosterior hyp;                                                              // wrapper:35-39 (unshrunk G0, cpp:390)
@@ -1946,6 +1989,7 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
   }
   if (varInflationOut) *varInflationOut = vi;
   FB_TRY(posterior_from_inputs(ctx, pl.in, gamma0, delta0sq, k, vi, out));       // wrapper:46-54, cpp:553-597
+  clk.mark(4);
   (*out)->hyp_G0 = std::move(hyp.G0);      // R sizes FABLEHyperParameters$G0 (p x kEst) once it knows kEst: fetched later
   return FABLE_OK;
 }

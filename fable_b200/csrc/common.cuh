@@ -20,6 +20,9 @@ struct fable_ctx {
   void* poll_user = nullptr;
   // optional per-kernel CUDA-event timing of the covariance kernel (bench.py roofline)
   bool timing = false;
+  // optional stage split of the wrapper pipelines (fable_ctx_stage_timing): host clock, the stream drained at every mark
+  bool stage_timing = false;
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<cudaEvent_t> ev_pool;     // pairs: [2i] before, [2i+1] after the launch
   size_t ev_used = 0;
   std::vector<cudaEvent_t> ev_extra;    // pairs around work done on behalf of those launches (folding their partial sums): counted in the total time, not as launches

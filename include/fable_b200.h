@@ -91,6 +91,14 @@ void* fable_ctx_stream(fable_ctx* ctx);
  * that fold the launches' partial sums into the accumulators (they are part of the same pass), the count does not. */
 int fable_ctx_kernel_timing(fable_ctx* ctx, int enable);
 int fable_ctx_kernel_time(fable_ctx* ctx, double* total_ms, int64_t* launches);
+/* Stage split of the single-upload wrapper pipelines (fable_wrapper_posterior_mean / fable_wrapper_sampler_begin =
+ * R/FABLE_wrapper.R:80-128 / 12-54).  enable != 0 clears the record and makes the pipelines drain the stream at every
+ * stage boundary (host clock); fable_ctx_stage_times copies the milliseconds of the last pipeline call:
+ * [0] upload of Y, [1] Gram + eigensolver + back-multiplication (R: svd(Y)), [2] U, d, V to the host + kMax rule,
+ * [3] rank search (cpp:281-341), [4] row posterior / hyper-parameters / varInflation, [5] p x p results to the host;
+ * entries past count are not written, entries 6, 7 are zero.  (No reference counterpart: R's runTime is one number.) */
+int fable_ctx_stage_timing(fable_ctx* ctx, int enable);
+int fable_ctx_stage_times(const fable_ctx* ctx, double* ms, int count);
 /* Diagnostics: register-resident issue rate of the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA.8x8x4) on this
  * device, in TFLOP/s -- the denominator bench.py divides the Gram step by (no reference counterpart). */
 int fable_ctx_measure_fp64_peak(fable_ctx* ctx, double* dmma_tflops);

@@ -244,6 +244,25 @@ def test_c1_criterion_large_ranks_use_the_dmma_path(ctx, c1):
         assert abs(fb.CPPCriterionFunction(k, Y, u, v, d, ctx=ctx) / orc.criterion(k, Y, u, v, d) - 1) < TOL
 
 
+def test_wrapper_stage_split_adds_up(ctx, c1):
+    """fable_ctx_stage_timing / fable_ctx_stage_times: the stage marks of the single-upload pipeline cover the call (their sum is
+    within the call's wall time, every stage of FABLEPosteriorMean ran) and switching them on does not change the result."""
+    Y = c1["Y"]
+    plain = fb.FABLEPosteriorMean(Y, ctx=ctx)
+    ctx.stage_timing(True)
+    try:
+        timed = fb.FABLEPosteriorMean(Y, ctx=ctx)
+        st = ctx.stage_times()
+    finally:
+        ctx.stage_timing(False)
+    assert timed["estRank"] == plain["estRank"]
+    np.testing.assert_array_equal(timed["FABLEPostMean"], plain["FABLEPostMean"])
+    assert all(v > 0.0 for v in st.values()), st
+    assert sum(st.values()) <= 1e3 * timed["runTime"] * 1.05, (st, timed["runTime"])
+    fb.FABLEPosteriorMean(Y, ctx=ctx)
+    assert sum(ctx.stage_times().values()) == 0.0                        # switched off: cleared, nothing recorded
+
+
 def test_c1_wrappers_end_to_end(ctx, c1):
     Y = c1["Y"]
     ref = orc.FABLEPosteriorMean(Y)
