@@ -12,6 +12,9 @@
 #include <thread>
 
 #include <sys/mman.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "common.cuh"
 #include "tiles.cuh"
@@ -676,6 +679,49 @@ int upload_bytes(fable_ctx* ctx, void* dptr, const void* h, size_t bytes) {
 }
 
 // dense p x p  A A' + diag(s) into a host buffer, via a device p x p
+// First touch of a large pageable result while the device still computes.  A freshly allocated p x p result is untouched
+// virtual memory and the copy-out pays one page fault (and one page clear) per 4 KB: 109 of the 146 ms of FABLEPosteriorMean at
+// C3 were the 3.2 GB CovPostMean crossing into such memory at 29 GB/s, PCIe alone would need 60.  The pages are therefore
+// touched -- one zero byte per 4 KB, by plain page faults from a few host threads, each on its own slice -- from the moment
+// the entry point knows the destination, i.e. during the upload, the SVD and the rank search; join() is called before the
+// first byte of the result is written.  (The earlier experiment used madvise(MADV_POPULATE_WRITE), which serialises on the
+// address-space lock against the copy threads and doubled the wall time; plain faults do not.)  FABLE_B200_PREFAULT=0: off.
+class HostPrefault {
+ public:
+  HostPrefault() = default;
+  HostPrefault(const HostPrefault&) = delete;
+  HostPrefault& operator=(const HostPrefault&) = delete;
+  ~HostPrefault() { join(); }
+  void start(void* dst, size_t bytes) {
+    const char* e = getenv("FABLE_B200_PREFAULT");
+    if (!dst || bytes < (size_t(256) << 20) || (e && atoi(e) == 0) || !is_pageable(dst)) return;
+    int nt = copy_threads();
+    if (nt <= 0) return;
+    if (nt > 16) nt = 16;
+    hint_huge_pages(static_cast<char*>(dst), bytes);
+    char* base = static_cast<char*>(dst);
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+    for (int t = 0; t < nt; ++t) {
+      const size_t lo = per * t, hi = lo + per < bytes ? lo + per : bytes;
+      if (lo >= hi) break;
+      threads_.emplace_back([base, lo, hi] {
+        // lowest priority: the calling thread drives the eigensolver's sweeps (a launch and a 4-byte read-back per sweep)
+        // and must not queue behind 16 page-faulting threads (measured: SVD stage 19.7 -> 30-35 ms without this)
+        (void)setpriority(PRIO_PROCESS, static_cast<id_t>(syscall(SYS_gettid)), 19);
+        volatile char* q = base;
+        for (size_t off = lo; off < hi; off += 4096) q[off] = 0;
+        q[hi - 1] = 0;
+      });
+    }
+  }
+  void join() {
+    for (std::thread& t : threads_) t.join();
+    threads_.clear();
+  }
+ private:
+  std::vector<std::thread> threads_;
+};
+
 int rankk_cov_to_host(fable_ctx* ctx, const double* dA, int64_t lda, const double* ds, int64_t p, int k,
                       double* hOut) {
   DevBuf out;
@@ -1940,6 +1986,8 @@ int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int
   if (!ctx) return FABLE_ERR_INVALID;
   FB_NO_SHARD(ctx, "FABLEPosteriorMean");
   FB_REQUIRE(ctx, kEst, "posterior_mean: NULL kEst");
+  HostPrefault touch;
+  if (Cov && p >= 1) touch.start(Cov, static_cast<size_t>(p) * p * sizeof(double));
   Pipeline pl;
   FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:87-94
   if (kMaxOut) *kMaxOut = pl.kMax;
@@ -1951,6 +1999,7 @@ int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int
   FB_TRY(row_posterior(ctx, pl.in, k, gamma0, delta0sq, /*shrunk=*/1, rp));
   clk.mark(4);
   *kEst = k;
+  touch.join();
   if (Cov) FB_TRY(rankk_cov_to_host(ctx, rp.G0.d(), p, rp.sigmahat.d(), p, k, Cov));   // cpp:491, 509-512
   clk.mark(5);
   return FABLE_OK;
@@ -1966,6 +2015,8 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
   FB_NO_SHARD(ctx, "FABLEPosteriorSampler");
   FB_REQUIRE(ctx, out, "sampler_begin: NULL out");
   *out = nullptr;
+  HostPrefault touch;
+  if (hypG && p >= 1) touch.start(hypG, static_cast<size_t>(p) * p * sizeof(double));
   Pipeline pl;
   FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:20-27
   if (kMaxOut) *kMaxOut = pl.kMax;
@@ -1984,6 +2035,7 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
     double su, sd;                                                               // wrapper:41-44, B never stored
     FB_TRY(fb_var_inflation(ctx, hyp.sig.d(), hyp.G0.d(), p, p, k, &su, &sd));
     FB_TRY(var_inflation_from_sums(su, sd, p, /*variant=*/0, &vi));
+    touch.join();
     if (hypG) FB_TRY(rankk_cov_to_host(ctx, hyp.G0.d(), p, nullptr, p, k, hypG));     // cpp:391
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
