@@ -557,6 +557,74 @@ bool is_pageable(const void* h) {
   return at.type == cudaMemoryTypeUnregistered;
 }
 
+// First touch of a large pageable result while the device still computes.  A freshly allocated p x p result is untouched
+// virtual memory and the copy-out pays one page fault (and one page clear) per 4 KB: 109 of the 146 ms of FABLEPosteriorMean at
+// C3 were the 3.2 GB CovPostMean crossing into such memory at 29 GB/s, PCIe alone would need 60.  The pages are therefore
+// touched -- one zero byte per 4 KB, by plain page faults from a few host threads, each on its own slice -- from the moment
+// the entry point knows the destination, i.e. during the upload, the SVD and the rank search, and -- being atomic adds of
+// zero -- on through the result copy itself.  (The earlier experiment used madvise(MADV_POPULATE_WRITE), which serialises on the
+// address-space lock against the copy threads and doubled the wall time; plain faults do not.)  FABLE_B200_PREFAULT=0: off.
+class HostPrefault {
+ public:
+  HostPrefault() = default;
+  HostPrefault(const HostPrefault&) = delete;
+  HostPrefault& operator=(const HostPrefault&) = delete;
+  ~HostPrefault() { join(); }
+  // (a copy into a range that an entry point is already touching does not start a second set of threads)
+  void start(fable_ctx* ctx, void* dst, size_t bytes) {
+    const char* e = getenv("FABLE_B200_PREFAULT");
+    if (!dst || bytes < (size_t(256) << 20) || (e && atoi(e) == 0) || !is_pageable(dst)) return;
+    {
+      const char* lo_ = static_cast<const char*>(dst);
+      for (int i = 0; i < 4; ++i)
+        if (ctx->prefault_lo[i] && lo_ < ctx->prefault_hi[i] && ctx->prefault_lo[i] < lo_ + bytes) return;
+      for (int i = 0; i < 4 && !owner_; ++i)
+        if (!ctx->prefault_lo[i]) { ctx->prefault_lo[i] = lo_; ctx->prefault_hi[i] = lo_ + bytes; owner_ = ctx; slot_ = i; }
+    }
+    int nt = copy_threads();
+    if (nt <= 0) return;
+    if (nt > 16) nt = 16;
+    hint_huge_pages(static_cast<char*>(dst), bytes);
+    char* base = static_cast<char*>(dst);
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+    for (int t = 0; t < nt; ++t) {
+      const size_t lo = per * t, hi = lo + per < bytes ? lo + per : bytes;
+      if (lo >= hi) break;
+      threads_.emplace_back([base, lo, hi] {
+        // lowest priority: the calling thread drives the eigensolver's sweeps (a launch and a 4-byte read-back per sweep)
+        // and must not queue behind 16 page-faulting threads (measured: SVD stage 19.7 -> 30-35 ms without this)
+        (void)setpriority(PRIO_PROCESS, static_cast<id_t>(syscall(SYS_gettid)), 19);
+#if defined(__x86_64__)
+        // an atomic add of zero faults the page in and leaves its content alone even if the result copy is already
+        // writing it: the copy does not have to wait for these threads (they are joined when the entry point returns)
+        for (size_t off = lo; off < hi; off += 4096) asm volatile("lock addb $0, (%0)" ::"r"(base + off) : "memory", "cc");
+        asm volatile("lock addb $0, (%0)" ::"r"(base + hi - 1) : "memory", "cc");
+#else
+        volatile char* q = base;
+        for (size_t off = lo; off < hi; off += 4096) q[off] = 0;
+        q[hi - 1] = 0;
+#endif
+      });
+    }
+  }
+  void join() {
+    for (std::thread& t : threads_) t.join();
+    threads_.clear();
+    if (owner_) { owner_->prefault_lo[slot_] = nullptr; owner_->prefault_hi[slot_] = nullptr; owner_ = nullptr; }
+  }
+  // before the first byte of the result is written: nothing to wait for where the touch is an atomic read-modify-write
+  void before_result() {
+#if !defined(__x86_64__)
+    join();
+#endif
+  }
+ private:
+  std::vector<std::thread> threads_;
+  fable_ctx* owner_ = nullptr;
+  int slot_ = 0;
+};
+
+
 int download(fable_ctx* ctx, double* h, const double* dptr, size_t count) {
   if (!h) return FABLE_OK;
   const size_t bytes = count * sizeof(double);
@@ -577,6 +645,8 @@ int download(fable_ctx* ctx, double* h, const double* dptr, size_t count) {
   const char* src = reinterpret_cast<const char*>(dptr);
   char* dst = reinterpret_cast<char*>(h);
   hint_huge_pages(dst, bytes);
+  // (touching the pages from extra threads only once the copy starts does not pay: 103 vs 112 ms for 3.2 GB; HostPrefault is
+  // started by the entry points that have device work to hide it behind)
   const size_t nchunks = (bytes + kStageBytes - 1) / kStageBytes;
   // the staging buffers are shared with the uploads, which may have run on the context's other stream: whatever last
   // used them must have finished before a transfer of this stream writes into them
@@ -679,49 +749,6 @@ int upload_bytes(fable_ctx* ctx, void* dptr, const void* h, size_t bytes) {
 }
 
 // dense p x p  A A' + diag(s) into a host buffer, via a device p x p
-// First touch of a large pageable result while the device still computes.  A freshly allocated p x p result is untouched
-// virtual memory and the copy-out pays one page fault (and one page clear) per 4 KB: 109 of the 146 ms of FABLEPosteriorMean at
-// C3 were the 3.2 GB CovPostMean crossing into such memory at 29 GB/s, PCIe alone would need 60.  The pages are therefore
-// touched -- one zero byte per 4 KB, by plain page faults from a few host threads, each on its own slice -- from the moment
-// the entry point knows the destination, i.e. during the upload, the SVD and the rank search; join() is called before the
-// first byte of the result is written.  (The earlier experiment used madvise(MADV_POPULATE_WRITE), which serialises on the
-// address-space lock against the copy threads and doubled the wall time; plain faults do not.)  FABLE_B200_PREFAULT=0: off.
-class HostPrefault {
- public:
-  HostPrefault() = default;
-  HostPrefault(const HostPrefault&) = delete;
-  HostPrefault& operator=(const HostPrefault&) = delete;
-  ~HostPrefault() { join(); }
-  void start(void* dst, size_t bytes) {
-    const char* e = getenv("FABLE_B200_PREFAULT");
-    if (!dst || bytes < (size_t(256) << 20) || (e && atoi(e) == 0) || !is_pageable(dst)) return;
-    int nt = copy_threads();
-    if (nt <= 0) return;
-    if (nt > 16) nt = 16;
-    hint_huge_pages(static_cast<char*>(dst), bytes);
-    char* base = static_cast<char*>(dst);
-    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
-    for (int t = 0; t < nt; ++t) {
-      const size_t lo = per * t, hi = lo + per < bytes ? lo + per : bytes;
-      if (lo >= hi) break;
-      threads_.emplace_back([base, lo, hi] {
-        // lowest priority: the calling thread drives the eigensolver's sweeps (a launch and a 4-byte read-back per sweep)
-        // and must not queue behind 16 page-faulting threads (measured: SVD stage 19.7 -> 30-35 ms without this)
-        (void)setpriority(PRIO_PROCESS, static_cast<id_t>(syscall(SYS_gettid)), 19);
-        volatile char* q = base;
-        for (size_t off = lo; off < hi; off += 4096) q[off] = 0;
-        q[hi - 1] = 0;
-      });
-    }
-  }
-  void join() {
-    for (std::thread& t : threads_) t.join();
-    threads_.clear();
-  }
- private:
-  std::vector<std::thread> threads_;
-};
-
 int rankk_cov_to_host(fable_ctx* ctx, const double* dA, int64_t lda, const double* ds, int64_t p, int k,
                       double* hOut) {
   DevBuf out;
@@ -1786,6 +1813,15 @@ static int sample_range(fable_posterior* post, int64_t MC, int64_t m0, int64_t l
   // then generated and copied out on the copy stream, so their D2H traffic (8 p (k+1) bytes per draw)
   // overlaps the covariance kernels.  Both read the same immutable row posterior.
   DevBuf dgam, dz;
+  // pageable sample matrices (what R hands over: MC x kp and MC x p doubles, 1.8 GB at C3 with MC = 1000) and dense sums are
+  // touched by background threads from here on; the copies below find most of their pages mapped
+  HostPrefault touch_l, touch_s, touch_sum, touch_sq;
+  if (ldm == MC) {                    // (a row range of a larger matrix is shared with other callers: left alone)
+    if (LambdaSamples) touch_l.start(ctx, LambdaSamples, static_cast<size_t>(MC) * p * kEst * sizeof(double));
+    if (SigmaSqSamples) touch_s.start(ctx, SigmaSqSamples, static_cast<size_t>(MC) * p * sizeof(double));
+  }
+  if (fetch_sum) touch_sum.start(ctx, fetch_sum, static_cast<size_t>(p) * p * sizeof(double));
+  if (fetch_sq) touch_sq.start(ctx, fetch_sq, static_cast<size_t>(p) * p * sizeof(double));
   struct TailChunk { cudaEvent_t ev; int64_t sb0, sb1; };
   struct TailEvents : std::vector<TailChunk> {
     ~TailEvents() { for (auto& t : *this) cudaEventDestroy(t.ev); }
@@ -1987,7 +2023,7 @@ int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int
   FB_NO_SHARD(ctx, "FABLEPosteriorMean");
   FB_REQUIRE(ctx, kEst, "posterior_mean: NULL kEst");
   HostPrefault touch;
-  if (Cov && p >= 1) touch.start(Cov, static_cast<size_t>(p) * p * sizeof(double));
+  if (Cov && p >= 1) touch.start(ctx, Cov, static_cast<size_t>(p) * p * sizeof(double));
   Pipeline pl;
   FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:87-94
   if (kMaxOut) *kMaxOut = pl.kMax;
@@ -1999,7 +2035,7 @@ int fable_wrapper_posterior_mean(fable_ctx* ctx, const double* Y, int64_t n, int
   FB_TRY(row_posterior(ctx, pl.in, k, gamma0, delta0sq, /*shrunk=*/1, rp));
   clk.mark(4);
   *kEst = k;
-  touch.join();
+  touch.before_result();
   if (Cov) FB_TRY(rankk_cov_to_host(ctx, rp.G0.d(), p, rp.sigmahat.d(), p, k, Cov));   // cpp:491, 509-512
   clk.mark(5);
   return FABLE_OK;
@@ -2016,7 +2052,7 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
   FB_REQUIRE(ctx, out, "sampler_begin: NULL out");
   *out = nullptr;
   HostPrefault touch;
-  if (hypG && p >= 1) touch.start(hypG, static_cast<size_t>(p) * p * sizeof(double));
+  if (hypG && p >= 1) touch.start(ctx, hypG, static_cast<size_t>(p) * p * sizeof(double));
   Pipeline pl;
   FB_TRY(pipeline_svd(ctx, Y, n, p, maxProp, pl, U, d, V));                      // wrapper:20-27
   if (kMaxOut) *kMaxOut = pl.kMax;
@@ -2035,7 +2071,7 @@ int fable_wrapper_sampler_begin(fable_ctx* ctx, const double* Y, int64_t n, int6
     double su, sd;                                                               // wrapper:41-44, B never stored
     FB_TRY(fb_var_inflation(ctx, hyp.sig.d(), hyp.G0.d(), p, p, k, &su, &sd));
     FB_TRY(var_inflation_from_sums(su, sd, p, /*variant=*/0, &vi));
-    touch.join();
+    touch.before_result();
     if (hypG) FB_TRY(rankk_cov_to_host(ctx, hyp.G0.d(), p, nullptr, p, k, hypG));     // cpp:391
     FB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }

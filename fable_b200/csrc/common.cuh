@@ -21,6 +21,8 @@ struct fable_ctx {
   // optional per-kernel CUDA-event timing of the covariance kernel (bench.py roofline)
   bool timing = false;
   // optional stage split of the wrapper pipelines (fable_ctx_stage_timing): host clock, the stream drained at every mark
+  const char* prefault_lo[4] = {nullptr, nullptr, nullptr, nullptr};   // pageable result ranges being touched by HostPrefault (api.cu)
+  const char* prefault_hi[4] = {nullptr, nullptr, nullptr, nullptr};
   bool stage_timing = false;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<cudaEvent_t> ev_pool;     // pairs: [2i] before, [2i+1] after the launch
