@@ -1925,6 +1925,8 @@ static int sampler_outputs(fable_posterior* post, int64_t MC, const double* gam_
                            double* LambdaSamples, double* SigmaSqSamples, double* SigmaPostMean, double* SigmaPlugIn,
                            double* tausq, double* G, double* psi_sum, double* psi_sumsq) {
   fable_ctx* ctx = post->ctx;
+  HostPrefault touch_g;               // G (cpp:627) leaves last: its pages are touched while the draws are made and copied
+  if (G) touch_g.start(ctx, G, static_cast<size_t>(post->p) * post->p * sizeof(double));
   FB_TRY(fable_posterior_fixed_outputs(post, SigmaPostMean, SigmaPlugIn, tausq, nullptr));
   if (psi_sum) FB_TRY(fable_posterior_accum_reset(post));
   FB_TRY(sample_range(post, MC, m0, MC, gam_inj, z_inj, LambdaSamples, SigmaSqSamples, psi_sum != nullptr, psi_sum, psi_sumsq));
