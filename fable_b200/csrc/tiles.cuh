@@ -22,7 +22,10 @@
 namespace fbt {
 
 constexpr int TILE = 64;
-constexpr int SB = 16;
+#ifndef FB_SB
+#define FB_SB 16                      // lab builds only: -DFB_SB=32 (every translation unit), see DESIGN.md 3.1
+#endif
+constexpr int SB = FB_SB;
 constexpr int TILE_DOUBLES = TILE * TILE;
 
 // column-major enumeration of an upper triangle: t = J(J+1)/2 + I, 0 <= I <= J
