@@ -158,6 +158,9 @@ k_rowstats(const double* __restrict__ Y, int64_t n, int64_t p, int64_t ldy, cons
 #ifdef ROWS_LAB_TIMING
 __device__ int rows_lab_count = 0;
 #endif
+#ifndef ROWS_ISSUE_LATE
+#define ROWS_ISSUE_LATE 1
+#endif
 constexpr int MW = 16;                 // warps per CTA
 constexpr int ITEM = 32;               // rows per item (4 DMMA column blocks of the transposed product)
 constexpr int MAXS = 8;                // ring stages per warp, at most
@@ -282,11 +285,13 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
 #ifdef ROWS_LAB_TIMING
         const long long lab_a = clock64();
 #endif
+#if !ROWS_ISSUE_LATE
         issue();                                         // item + S - 1 into the stage consumed by the previous step
+#endif
 #ifdef ROWS_LAB_TIMING
         const long long lab_b = clock64();
 #endif
-        asm volatile("cp.async.wait_group %0;" ::"n"(S - 1) : "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(ROWS_ISSUE_LATE ? S - 2 : S - 1) : "memory");
 #ifdef ROWS_LAB_TIMING
         const long long lab_c = clock64();
         lab_issue += lab_b - lab_a; lab_wait += lab_c - lab_b;
@@ -310,6 +315,12 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
           for (int nb = 0; nb < 4; ++nb) dmma_884(acc[nb], a[ks], ub[q][ks][nb]);
 #else
         acc[0].x += a[0] * ub[q][0][0];
+#endif
+#if ROWS_ISSUE_LATE
+        // the copies of item + S - 1 (into the stage read one step earlier) go out BEHIND the DMMAs: the four LDGSTS wait for
+        // their turn in the memory pipe (300-560 cycles per item in the cycle counters) while the tensor pipe works through
+        // the twelve DMMAs this warp has just queued, instead of in front of them
+        issue();
 #endif
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) { ar0 = fma(acc[nb].x, acc[nb].x, ar0); ar1 = fma(acc[nb].y, acc[nb].y, ar1); }
@@ -341,8 +352,17 @@ k_rowstats_mma(const double* __restrict__ Y, int n, int p, int64_t ldy, const do
       lab_bar += clock64() - lab_d;
 #endif
       if (wr == 0 && lane < 16) {
-        double sum = 0.0;
-        for (int w2 = 0; w2 < G; ++w2) sum += red[(buf * MW + w + w2) * 16 + lane];
+        // the group's partial sums, fetched together and added as a fixed tree: the sixteen dependent LDS -> DADD steps of a
+        // plain loop (~700 cycles, on the critical path of every tile: the other warps meet this one at the next barrier)
+        // become one shared-memory latency and four additions
+        double v[MW];
+#pragma unroll
+        for (int w2 = 0; w2 < MW; ++w2) v[w2] = w2 < G ? red[(buf * MW + w + w2) * 16 + lane] : 0.0;
+#pragma unroll
+        for (int h = 1; h < MW; h <<= 1)
+#pragma unroll
+          for (int w2 = 0; w2 + h < MW; w2 += 2 * h) v[w2] += v[w2 + h];
+        const double sum = v[0];
         if (col + (lane & 7) < p) {
           if (lane < 8) resid_out[col + lane] = sum;
           else if (s_out) s_out[col + lane - 8] = sum;
@@ -546,8 +566,17 @@ k_rowstats_tma(const double* __restrict__ Y, int n, int p, const double* __restr
       lab_bar += clock64() - lab_d;
 #endif
       if (wr == 0 && lane < 16) {
-        double sum = 0.0;
-        for (int w2 = 0; w2 < G; ++w2) sum += red[(buf * MW + w + w2) * 16 + lane];
+        // the group's partial sums, fetched together and added as a fixed tree: the sixteen dependent LDS -> DADD steps of a
+        // plain loop (~700 cycles, on the critical path of every tile: the other warps meet this one at the next barrier)
+        // become one shared-memory latency and four additions
+        double v[MW];
+#pragma unroll
+        for (int w2 = 0; w2 < MW; ++w2) v[w2] = w2 < G ? red[(buf * MW + w + w2) * 16 + lane] : 0.0;
+#pragma unroll
+        for (int h = 1; h < MW; h <<= 1)
+#pragma unroll
+          for (int w2 = 0; w2 + h < MW; w2 += 2 * h) v[w2] += v[w2 + h];
+        const double sum = v[0];
         if (col + (lane & 7) < p) {
           if (lane < 8) resid_out[col + lane] = sum;
           else if (s_out) s_out[col + lane - 8] = sum;
