@@ -847,7 +847,7 @@ def test_dmma_gemm(ctx, M, N, K, akf, bkf):
     assert relerr_mat(dC.cpu().numpy().T, 0.5 * A @ B.T) < 1e-13
 
 
-@pytest.mark.parametrize("m", [1, 2, 7, 64, 256, 257, 301, 640, 1000])
+@pytest.mark.parametrize("m", [1, 2, 7, 16, 17, 33, 47, 64, 100, 256, 257, 301, 640, 960, 961, 1000])
 def test_jacobi_eigensolver(ctx, m):
     import torch
     rng = np.random.default_rng(m)
