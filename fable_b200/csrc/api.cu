@@ -590,6 +590,7 @@ class HostPrefault {
     for (int t = 0; t < nt; ++t) {
       const size_t lo = per * t, hi = lo + per < bytes ? lo + per : bytes;
       if (lo >= hi) break;
+      try {
       threads_.emplace_back([base, lo, hi] {
         // lowest priority: the calling thread drives the eigensolver's sweeps (a launch and a 4-byte read-back per sweep)
         // and must not queue behind 16 page-faulting threads (measured: SVD stage 19.7 -> 30-35 ms without this)
@@ -605,6 +606,7 @@ class HostPrefault {
         q[hi - 1] = 0;
 #endif
       });
+      } catch (...) { break; }           // no thread to spare: the copy faults its pages itself, as before
     }
   }
   void join() {
