@@ -207,7 +207,7 @@ k_bj_gram(const double* __restrict__ A, int64_t ld, int64_t rows_per_split, int6
 // 2 = R written here (full ordering / legacy path).
 constexpr int EIGT = 1024;
 #ifdef BJ_LAB
-__device__ int bj_lab_count = 0;
+__device__ int bj_lab_count = 0, bj_lab_count2 = 0;
 #endif
 // The inner solve proper; called by all EIGT threads of a CTA with H (64 x 64, row stride 65) at dsm and, unless REPLAY &&
 // cross_only, R = I behind it.  Returns (uniformly) the mode: 0 = nothing to rotate (R = I), 1 = cross rotations recorded in
@@ -225,6 +225,9 @@ __device__ __forceinline__ int bj_solve(double* dsm, double tol, double floor2, 
   const int tid = threadIdx.x;
   const int nsteps = cross_only ? BW : PW - 1;
   const double tol2 = tol * tol;
+#ifdef BJ_LAB
+  const long long lab_s0 = clock64();
+#endif
   if (tid == 0) { any_rot = 0; need = 0; }
   __syncthreads();
   // does this pair need work at all?  (outer convergence test: |h_ab| > tol sqrt(h_aa h_bb))
@@ -277,6 +280,9 @@ __device__ __forceinline__ int bj_solve(double* dsm, double tol, double floor2, 
         rots_pair[lane] = r0;
       }
       asm volatile("bar.sync 1, 576;" ::: "memory");
+#ifdef BJ_LAB
+      if (blockIdx.x == 0 && tid == 0 && bj_lab_count2 == 300) printf("BJ_LAB(solve) need check + first rotation %lld cycles\n", clock64() - lab_s0);
+#endif
       int cur = 0, nxt = 2 * PW * S;
       int o_a = a, o_b = b, o_l = lane;                  // (index + step) % 32
 #ifdef BJ_LAB
@@ -522,20 +528,31 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
   const int tid = threadIdx.x;
   const double* src = Hpart + static_cast<int64_t>(blockIdx.x) * nsplit * (PW * PW);
   pdl_chain();
+#ifdef BJ_LAB
+  const long long lab_k0 = clock64();
+#endif
   {
     // partial Grams of the row splits, added in split order; the loads of a thread's four entries go out together,
     // eight splits at a time (one load per iteration = nsplit x 4 serial L2 round trips, 20 us of a 50 us kernel)
     constexpr int NE = PW * PW / EIGT;
     double v[NE];
+    // the symmetric cross steps read H on and above the diagonal only: the 8 x 8 tiles below it are not fetched (the fetch
+    // is 13-15 x 32 KB through one SM -- 6000 of the kernel's 44 000 cycles at n = 1000 -- and 28 of the 64 tiles are such)
+    const bool upper_only = REPLAY && cross_only && !(iso & 2);
+    bool want[NE];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) v[e] = 0.0;
+    for (int e = 0; e < NE; ++e) {
+      v[e] = 0.0;
+      const int idx = tid + e * EIGT;
+      want[e] = !upper_only || ((idx & (PW - 1)) >> 3) <= (idx >> 9);
+    }
     for (int s0 = 0; s0 < nsplit; s0 += 8) {
       double x[8][NE];
 #pragma unroll
       for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int e = 0; e < NE; ++e)
-          x[u][e] = (s0 + u < nsplit) ? __ldg(src + static_cast<int64_t>(s0 + u) * (PW * PW) + tid + e * EIGT) : 0.0;
+          x[u][e] = (s0 + u < nsplit && want[e]) ? __ldg(src + static_cast<int64_t>(s0 + u) * (PW * PW) + tid + e * EIGT) : 0.0;
 #pragma unroll
       for (int u = 0; u < 8; ++u)
 #pragma unroll
@@ -548,8 +565,17 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
       if (!(REPLAY && cross_only)) R[a * S + b] = (a == b) ? 1.0 : 0.0;
     }
   }
+#ifdef BJ_LAB
+  __syncthreads();
+  const long long lab_k1 = clock64();
+#endif
   const int md = bj_solve<REPLAY>(dsm, tol, floor2, inner, cross_only, nrot,
                                   REPLAY ? rots + static_cast<int64_t>(blockIdx.x) * (BW * BW) : nullptr, iso);
+#ifdef BJ_LAB
+  if (blockIdx.x == 0 && tid == 0 && REPLAY && atomicAdd(&bj_lab_count2, 1) == 300)
+    printf("BJ_LAB(kernel) fetch of %d partial Grams %lld cycles, solve (need check, first rotation, 32 steps) %lld cycles\n", nsplit, lab_k1 - lab_k0,
+           clock64() - lab_k1);
+#endif
   if (tid == 0 && mode) mode[blockIdx.x] = md;
   if (md != 2) return;                                     // k_bj_replay writes R
   double* Rg = Rout + static_cast<int64_t>(blockIdx.x) * (PW * PW);
