@@ -534,35 +534,42 @@ k_bj_eig(const double* __restrict__ Hpart, int nsplit, double tol, double floor2
   {
     // partial Grams of the row splits, added in split order; the loads of a thread's four entries go out together,
     // eight splits at a time (one load per iteration = nsplit x 4 serial L2 round trips, 20 us of a 50 us kernel)
-    constexpr int NE = PW * PW / EIGT;
-    double v[NE];
-    // the symmetric cross steps read H on and above the diagonal only: the 8 x 8 tiles below it are not fetched (the fetch
-    // is 13-15 x 32 KB through one SM -- 6000 of the kernel's 44 000 cycles at n = 1000 -- and 28 of the 64 tiles are such)
+    // every thread owns two pairs of adjacent rows (16-byte loads: half as many requests as one entry per load -- the fetch is
+    // bound by the number of loads in flight, not by bytes); the symmetric cross steps read H on and above the diagonal only,
+    // so the 8 x 8 tiles below it are not fetched there
+    constexpr int NP = PW * PW / (2 * EIGT);
+    double2 v[NP];
     const bool upper_only = REPLAY && cross_only && !(iso & 2);
-    bool want[NE];
+    bool want[NP];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      v[e] = 0.0;
-      const int idx = tid + e * EIGT;
+    for (int e = 0; e < NP; ++e) {
+      v[e] = make_double2(0.0, 0.0);
+      const int idx = 2 * (tid + e * EIGT);
       want[e] = !upper_only || ((idx & (PW - 1)) >> 3) <= (idx >> 9);
     }
     for (int s0 = 0; s0 < nsplit; s0 += 8) {
-      double x[8][NE];
+      double2 x[8][NP];
 #pragma unroll
       for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int e = 0; e < NE; ++e)
-          x[u][e] = (s0 + u < nsplit && want[e]) ? __ldg(src + static_cast<int64_t>(s0 + u) * (PW * PW) + tid + e * EIGT) : 0.0;
+        for (int e = 0; e < NP; ++e)
+          x[u][e] = (s0 + u < nsplit && want[e])
+                        ? __ldg(reinterpret_cast<const double2*>(src + static_cast<int64_t>(s0 + u) * (PW * PW)) + tid + e * EIGT)
+                        : make_double2(0.0, 0.0);
 #pragma unroll
       for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int e = 0; e < NE; ++e) v[e] += x[u][e];
+        for (int e = 0; e < NP; ++e) { v[e].x += x[u][e].x; v[e].y += x[u][e].y; }
     }
 #pragma unroll
-    for (int e = 0; e < NE; ++e) {
-      const int idx = tid + e * EIGT, a = idx & (PW - 1), b = idx >> 6;
-      H[a * S + b] = v[e];
-      if (!(REPLAY && cross_only)) R[a * S + b] = (a == b) ? 1.0 : 0.0;
+    for (int e = 0; e < NP; ++e) {
+      const int idx = 2 * (tid + e * EIGT), a = idx & (PW - 1), b = idx >> 6;
+      H[a * S + b] = v[e].x;
+      H[(a + 1) * S + b] = v[e].y;
+      if (!(REPLAY && cross_only)) {
+        R[a * S + b] = (a == b) ? 1.0 : 0.0;
+        R[(a + 1) * S + b] = (a + 1 == b) ? 1.0 : 0.0;
+      }
     }
   }
 #ifdef BJ_LAB
