@@ -96,9 +96,13 @@ k_gather_normalise(const double* __restrict__ A, int64_t m, int64_t ld, const in
 //   2. k_bj_eig  : one two-sided cyclic Jacobi sweep on the 64 x 64 matrix H in shared memory -> R
 //                  (inexact inner solve: more inner sweeps cost 0.9 ms per pair and do not reduce the
 //                  number of outer sweeps; measured)
+//                  Rounds 1 .. NB-2 of a sweep rotate only the 32 x 32 cross pairs (bj_solve's symmetric form: H as its
+//                  upper triangle, the rotations recorded) and
+//  2b. k_bj_replay rebuilds R from the 16 KB of rotations on 8 CTAs per pair;
 //   3. k_bj_apply: W <- W R         (FP64 tensor cores, in place, one CTA per 128 rows)
 // so a round streams the matrix through HBM once per 32 columns instead of once per column: m/32 - 1
-// rounds per sweep instead of m - 1.  The working matrix is padded with zero rows (to a multiple of 16)
+// rounds per sweep instead of m - 1.  Where every pair's cluster of 8 CTAs is resident (m <= 960) the whole round is ONE
+// kernel, k_bj_round, with the panel slabs in shared memory.  A sweep is replayed as a CUDA graph.  The working matrix is padded with zero rows (to a multiple of 16)
 // and zero columns (to an even number of blocks); zero columns are never rotated.
 constexpr int BW = 32, PW = 2 * BW;
 constexpr int GKT = 16, GS = GKT + 4;      // Gram stage: 16 rows, column stride 20 (= 4 mod 16: conflict-free fragments)
