@@ -87,9 +87,19 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// PSI_OP_POLICY (lab builds): L2 policy of the operand rows -- 0 evict_last (product), 1 evict_normal.  With k = 20 and 47
+// draws per launch the operands (376 MB) exceed the L2, unlike at c3 (77 MB); measured: c4 share 22.45 vs 22.37 ms, c3 22.24 vs
+// 21.91 ms -- evict_last stays.
+#ifndef PSI_OP_POLICY
+#define PSI_OP_POLICY 0
+#endif
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t pol;
+#if PSI_OP_POLICY == 1
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+#else
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
   return pol;
 }
 // operand rows are re-read by every tile of a block row/column: keep them in L2 (evict_last)
