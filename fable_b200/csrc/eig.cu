@@ -631,30 +631,34 @@ k_bj_replay(const double2* __restrict__ rots, const int* __restrict__ mode, doub
   Rg[row + PW * (BW + lane)] = q;
 }
 
-// W (rows i0..i0+127 of the pair's 64 columns) <- W R, in place
-__global__ void __launch_bounds__(256)
+// W (rows i0 .. i0 + RB - 1 of the pair's 64 columns) <- W R, in place; RB / 16 warps, each a 32 x 32 piece.  RB = 64 (four
+// warps, 66 KB of shared memory: three CTAs per SM, and 256 instead of 128 CTAs at m = 1000, where 128 left twenty SMs idle)
+// is the default; RB = 128 is the round-1 shape (FABLE_B200_BJ_APPLY_ROWS=128).
+template <int RB>
+__global__ void __launch_bounds__(RB * 2)
 k_bj_apply(double* __restrict__ A, int64_t ld, int round, int NB, const double* __restrict__ Rall) {
+  constexpr int NT = RB * 2, AS = RB + 4;               // column stride of the A tile: 4 mod 16 (conflict-free fragments)
   extern __shared__ __align__(16) double sm[];
-  double* TA = sm;                    // [64 cols a][ASTR]  (128 rows each)
-  double* TR = sm + PW * ASTR;        // [64 cols c][RSTR]  (64 entries a each): R[a][c]
+  double* TA = sm;                    // [64 cols a][AS]  (RB rows each)
+  double* TR = sm + PW * AS;          // [64 cols c][RSTR]  (64 entries a each): R[a][c]
   pdl_chain();
   int bi, bj;
   bj_pair(blockIdx.x, round, NB, bi, bj);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * 128;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * RB;
   const double* R = Rall + static_cast<int64_t>(blockIdx.x) * (PW * PW);
-  for (int idx = tid; idx < PW * 64; idx += 256) {         // A tile: 64 columns x 64 chunks of 2 rows
-    const int a = idx >> 6, ch = idx & 63;
-    if (i0 + 2 * ch < ld) cp16(TA + a * ASTR + 2 * ch, A + bj_col(a, bi, bj) * ld + i0 + 2 * ch);
+  for (int idx = tid; idx < PW * (RB / 2); idx += NT) {    // A tile: 64 columns x RB / 2 chunks of 2 rows
+    const int a = idx / (RB / 2), ch = idx % (RB / 2);
+    if (i0 + 2 * ch < ld) cp16(TA + a * AS + 2 * ch, A + bj_col(a, bi, bj) * ld + i0 + 2 * ch);
   }
-  for (int idx = tid; idx < PW * 32; idx += 256) {         // R: 64 columns x 32 chunks
+  for (int idx = tid; idx < PW * 32; idx += NT) {          // R: 64 columns x 32 chunks
     const int cc = idx >> 5, ch = idx & 31;
     cp16(TR + cc * RSTR + 2 * ch, R + cc * PW + 2 * ch);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+  const int wr = (warp % (RB / 32)) * 32, wc = (warp / (RB / 32)) * 32;
   double c[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -664,7 +668,7 @@ k_bj_apply(double* __restrict__ A, int64_t ld, int round, int NB, const double* 
   for (int ks = 0; ks < PW / 4; ++ks) {
     double af[4], bf[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) af[i] = TA[(ks * 4 + t) * ASTR + wr + i * 8 + g];      // A[m = row][k = a]
+    for (int i = 0; i < 4; ++i) af[i] = TA[(ks * 4 + t) * AS + wr + i * 8 + g];        // A[m = row][k = a]
 #pragma unroll
     for (int j = 0; j < 4; ++j) bf[j] = TR[(wc + j * 8 + g) * RSTR + ks * 4 + t];      // B[k = a][n = c] = R[a][c]
 #pragma unroll
@@ -1013,12 +1017,16 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
     k_bj_copy_in<<<dim3(static_cast<unsigned>(ceil_div(ld, 256)), static_cast<unsigned>(ncols)), 256, 0, ctx->stream>>>(
         dG, m, Wbuf.d(), ld, ncols);
     FB_LAUNCHED(ctx);
-    const size_t apply_smem = static_cast<size_t>(PW * ASTR + PW * RSTR) * sizeof(double);
+    const int apply_rows = getenv("FABLE_B200_BJ_APPLY_ROWS") && atoi(getenv("FABLE_B200_BJ_APPLY_ROWS")) == 128 ? 128 : 64;
+    const size_t apply_smem = static_cast<size_t>(PW * (apply_rows + 4) + PW * RSTR) * sizeof(double);
     const size_t eig_smem = static_cast<size_t>(3 * PW * (PW + 1)) * sizeof(double);       // H, R, second H of the pipelined cross steps
     static bool attr_dev[64] = {};
     bool& attr = attr_dev[ctx->device & 63];
     if (!attr) {
-      FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(apply_smem)));
+      FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_apply<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>((PW * (64 + 4) + PW * RSTR) * sizeof(double))));
+      FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_apply<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>((PW * (128 + 4) + PW * RSTR) * sizeof(double))));
       FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_eig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eig_smem)));
       FB_CUDA(ctx, cudaFuncSetAttribute(k_bj_eig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(eig_smem)));
       attr = true;
@@ -1064,7 +1072,7 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
       }
       for (int r = 0; r < NB - 1; ++r) {
         const int cross_only = (cross && r > 0) ? 1 : 0;
-        const dim3 ggrid(npairs, static_cast<unsigned>(nsplit)), agrid(npairs, static_cast<unsigned>(ceil_div(ld, 128)));
+        const dim3 ggrid(npairs, static_cast<unsigned>(nsplit)), agrid(npairs, static_cast<unsigned>(ceil_div(ld, apply_rows)));
         // (the first kernel of a sweep follows a memset: plain dependency)
         e = launch_chain(k_bj_gram, ggrid, dim3(128), 0, ctx->stream, pdl && r > 0, Wbuf.d(), ld, rows_per_split, ld, r, NB, Hpart.d());
         if (e != cudaSuccess) return e;
@@ -1079,7 +1087,9 @@ int fb_syevj(fable_ctx* ctx, double* dG, int64_t m, double* dW, double* dQ, int*
                            cross_only, Rall.d(), static_cast<int*>(cnt.ptr), static_cast<double2*>(nullptr), static_cast<int*>(nullptr), iso);
         }
         if (e != cudaSuccess) return e;
-        e = launch_chain(k_bj_apply, agrid, dim3(256), apply_smem, ctx->stream, pdl, Wbuf.d(), ld, r, NB, static_cast<const double*>(Rall.d()));
+        e = apply_rows == 64
+                ? launch_chain(k_bj_apply<64>, agrid, dim3(128), apply_smem, ctx->stream, pdl, Wbuf.d(), ld, r, NB, static_cast<const double*>(Rall.d()))
+                : launch_chain(k_bj_apply<128>, agrid, dim3(256), apply_smem, ctx->stream, pdl, Wbuf.d(), ld, r, NB, static_cast<const double*>(Rall.d()));
         if (e != cudaSuccess) return e;
       }
       return cudaGetLastError();
