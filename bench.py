@@ -532,11 +532,15 @@ def run_draws(args, w, wname, job):
         # the single-upload wrapper pipeline (FABLEPosteriorMean, R/FABLE_wrapper.R:80-128) with the library's own stage
         # marks: the rank search and the row posterior on resident data, apart from the host copies around them
         ctx.stage_timing(True)
-        for _ in range(2):
-            pm = fb.FABLEPosteriorMean(Y, ctx=ctx)
-        stages["FABLEPosteriorMean_ms"] = dict(total=round(1e3 * pm["runTime"], 3), kEst=int(pm["estRank"]), **ctx.stage_times())
+        best = None
+        for rep in range(4):                  # first call: warm-up; then the fastest of three (the p x p return into fresh pageable
+            pm = fb.FABLEPosteriorMean(Y, ctx=ctx)          # memory depends on what the host is doing: 126-229 ms seen for the same code)
+            rec = dict(total=round(1e3 * pm["runTime"], 3), kEst=int(pm["estRank"]), **ctx.stage_times())
+            del pm
+            if rep and (best is None or rec["total"] < best["total"]):
+                best = rec
+        stages["FABLEPosteriorMean_ms"] = best
         ctx.stage_timing(False)
-        del pm
 
     if rank == 0:
         peak, peak_src = _peaks()
