@@ -106,7 +106,7 @@ k_gather_normalise(const double* __restrict__ A, int64_t m, int64_t ld, const in
 // and zero columns (to an even number of blocks); zero columns are never rotated.
 constexpr int BW = 32, PW = 2 * BW;
 constexpr int GKT = 16, GS = GKT + 4;      // Gram stage: 16 rows, column stride 20 (= 4 mod 16: conflict-free fragments)
-constexpr int ASTR = 128 + 4, RSTR = PW + 4;
+constexpr int RSTR = PW + 4;
 
 // Programmatic dependent launch (the four kernels of a round are a strict chain): a kernel lets its successor be scheduled
 // as soon as all of its own CTAs are resident, and waits for its predecessor's completion (and memory flush) before it
