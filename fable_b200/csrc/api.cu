@@ -571,9 +571,9 @@ class HostPrefault {
   HostPrefault& operator=(const HostPrefault&) = delete;
   ~HostPrefault() { join(); }
   // (a copy into a range that an entry point is already touching does not start a second set of threads)
-  void start(fable_ctx* ctx, void* dst, size_t bytes) {
+  void start(fable_ctx* ctx, void* dst, size_t bytes, size_t min_bytes = size_t(256) << 20) {
     const char* e = getenv("FABLE_B200_PREFAULT");
-    if (!dst || bytes < (size_t(256) << 20) || (e && atoi(e) == 0) || !is_pageable(dst)) return;
+    if (!dst || bytes < min_bytes || (e && atoi(e) == 0) || !is_pageable(dst)) return;
     {
       const char* lo_ = static_cast<const char*>(dst);
       for (int i = 0; i < 4; ++i)
@@ -1995,6 +1995,8 @@ int pipeline_svd(fable_ctx* ctx, const double* Y, int64_t n, int64_t p, double m
   FB_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->stage_timing) for (double& x : ctx->stage_ms) x = 0.0;
   StageClock clk(ctx);
+  HostPrefault touch_v;               // svdY$v (p x r: 160 MB at C3) is known now and written after the eigensolver
+  if (V) touch_v.start(ctx, V, static_cast<size_t>(p) * (n < p ? n : p) * sizeof(double), size_t(64) << 20);
   const int64_t r = n < p ? n : p;
   Inputs& in = pl.in;
   in.n = n; in.p = p; in.r = r; in.kcols = static_cast<int>(r);
