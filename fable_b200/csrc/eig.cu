@@ -99,7 +99,7 @@ k_gather_normalise(const double* __restrict__ A, int64_t m, int64_t ld, const in
 //                  Rounds 1 .. NB-2 of a sweep rotate only the 32 x 32 cross pairs (bj_solve's symmetric form: H as its
 //                  upper triangle, the rotations recorded) and
 //  2b. k_bj_replay rebuilds R from the 16 KB of rotations on 8 CTAs per pair;
-//   3. k_bj_apply: W <- W R         (FP64 tensor cores, in place, one CTA per 128 rows)
+//   3. k_bj_apply: W <- W R         (FP64 tensor cores, in place, one CTA per 64 rows)
 // so a round streams the matrix through HBM once per 32 columns instead of once per column: m/32 - 1
 // rounds per sweep instead of m - 1.  Where every pair's cluster of 8 CTAs is resident (m <= 960) the whole round is ONE
 // kernel, k_bj_round, with the panel slabs in shared memory.  A sweep is replayed as a CUDA graph.  The working matrix is padded with zero rows (to a multiple of 16)
